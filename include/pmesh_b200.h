@@ -1,0 +1,215 @@
+/* pmesh_b200.h -- C ABI of libpmesh_b200.so, the B200 (sm_100a) engine behind
+ * the pmesh Python API.
+ *
+ * Every entry point replaces one native boundary of the reference pmesh
+ * (citations are file:line under the reference tree):
+ *
+ *   pmb_window_query / pmb_window_fwindow
+ *        <- pmesh_painter_init, pmesh_painter_get_fwindow     pmesh/_window_imp.h:76-86
+ *   pmb_paint / pmb_readout
+ *        <- ResampleWindow.paint / .readout (Cython loops)     pmesh/_window.pyx:128-205
+ *           pmesh_painter_paint / pmesh_painter_readout        pmesh/_window_imp.c:461-471
+ *   pmb_decompose
+ *        <- GridND.decompose chunk loop + gridnd_fill          pmesh/domain.py:561-652, pmesh/_domain.pyx:9-122
+ *   pmb_take / pmb_exchange / pmb_gather_sum
+ *        <- Layout._exchange (take + MPI Alltoallv), Layout.gather('sum')
+ *                                                            pmesh/domain.py:173-206, 208-318
+ *   pmb_fft_*
+ *        <- pfft.Partition / pfft.Plan.execute call sites      pmesh/pm.py:226-242, 655-694, 987-1019, 1406-1441
+ *   pmb_transfer
+ *        <- Field.apply with the force-step transfer functions pmesh/pm.py:617-648, examples/nbody.py:154-181
+ *   pmb_comm_*
+ *        <- mpi4py communicator used by domain.py / pfft       pmesh/domain.py:112-114,199-205
+ *
+ * Conventions: plain C types only.  Pointers are DEVICE pointers unless the
+ * name ends in _h.  Every function returns 0 on success or a negative
+ * PMB_E* code; pmb_last_error() gives the message of the last failure on the
+ * calling thread.  The library never frees caller memory.  One pmb_ctx per
+ * process/GPU; all work of a context is ordered on its one CUDA stream.
+ */
+#ifndef PMESH_B200_H
+#define PMESH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMB_OK 0
+#define PMB_EINVAL (-1)   /* bad argument */
+#define PMB_ECUDA (-2)    /* CUDA runtime / cuFFT failure */
+#define PMB_ENCCL (-3)    /* NCCL failure */
+#define PMB_ENOMEM (-4)
+#define PMB_EUNSUPPORTED (-5)
+
+#define PMB_MODE_ATOMIC 0         /* red.global.add scatter, order of additions undefined */
+#define PMB_MODE_DETERMINISTIC 1  /* sort-by-cell + sequential segmented sum: bit-equal to the reference */
+
+typedef struct pmb_ctx pmb_ctx;
+typedef struct pmb_fft pmb_fft;
+
+/* ---- context, memory, timing ------------------------------------------------ */
+const char *pmb_last_error(void);
+int pmb_version(void);
+int pmb_device_count(int *n);
+int pmb_ctx_create(int device, pmb_ctx **out);
+int pmb_ctx_destroy(pmb_ctx *ctx);
+int pmb_ctx_sync(pmb_ctx *ctx);
+int pmb_malloc(pmb_ctx *ctx, size_t nbytes, void **out);
+int pmb_free(pmb_ctx *ctx, void *ptr);
+int pmb_malloc_host(pmb_ctx *ctx, size_t nbytes, void **out_h);  /* pinned */
+int pmb_free_host(pmb_ctx *ctx, void *ptr_h);
+int pmb_memcpy_h2d(pmb_ctx *ctx, void *dst, const void *src_h, size_t nbytes);
+int pmb_memcpy_d2h(pmb_ctx *ctx, void *dst_h, const void *src, size_t nbytes);
+int pmb_memcpy_d2d(pmb_ctx *ctx, void *dst, const void *src, size_t nbytes);
+int pmb_memset(pmb_ctx *ctx, void *dst, int byte, size_t nbytes);
+int pmb_mem_info(pmb_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
+/* CUDA-event stopwatch on the context's stream (slots 0..15) */
+int pmb_timer_start(pmb_ctx *ctx, int slot);
+int pmb_timer_stop(pmb_ctx *ctx, int slot, float *ms);       /* records stop, synchronises, returns elapsed */
+int pmb_launch_count(pmb_ctx *ctx, int64_t *n, int reset);   /* kernels this library launched so far */
+int pmb_flush_l2(pmb_ctx *ctx);                              /* overwrite a 256 MiB scratch buffer */
+
+/* ---- windows ------------------------------------------------------------------ */
+/* upload one lookup table (lanczosN / acgN / dbN / symN); values are host doubles */
+int pmb_window_set_table(pmb_ctx *ctx, int kind, const double *values_h, int n,
+                         double step, double nativesupport, double hsupport);
+/* <- pmesh_painter_init: resolve support. support_req <= 0 means native. */
+int pmb_window_query(int kind, int support_req, int *support, int *nativesupport);
+/* <- pmesh_painter_get_fwindow, vectorised over n host values */
+int pmb_window_fwindow(int kind, int support, const double *w_h, double *out_h, int64_t n);
+
+typedef struct pmb_resample_args {
+    int kind;                 /* window kind (enum of pmesh/_window_imp.h:4-28) */
+    int support;              /* requested integer support, <= 0: native */
+    int ndim;                 /* 1..3 */
+    int order[3];             /* 1 on the axis of differentiation (diffdir), else 0 */
+    double scale[3];          /* Affine.scale */
+    double translate[3];      /* Affine.translate */
+    int64_t period[3];        /* Affine.period, 0 = not periodic */
+    void *mesh;               /* canvas */
+    int mesh_elsize;          /* 4 or 8 */
+    int64_t size[3];          /* local canvas shape */
+    int64_t strides[3];       /* canvas strides in BYTES */
+    const void *pos;          /* (npart, >=ndim) */
+    int pos_elsize;           /* 4 or 8 */
+    int64_t npart;
+    int64_t pos_stride0;      /* bytes between particles */
+    int64_t pos_stride1;      /* bytes between coordinates */
+    const void *mass;         /* paint: per-particle weight, NULL => mass_scalar.  */
+    int mass_elsize;
+    int64_t mass_stride;      /* bytes */
+    double mass_scalar;
+    const void *hsml;         /* per-particle support scaling, NULL => hsml_scalar */
+    int hsml_elsize;
+    int64_t hsml_stride;
+    double hsml_scalar;       /* 1.0 for the native support */
+    void *out;                /* readout: (npart,) result */
+    int out_elsize;
+    int64_t out_stride;       /* bytes */
+    int mode;                 /* paint: PMB_MODE_* */
+    int pcs_gradient_scale_fix; /* 0: bug-compatible tuned-PCS derivative (no scale[d] factor) */
+} pmb_resample_args;
+
+int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a);
+int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a);
+/* fused value + ndim gradients in one neighbour sweep (paint_vjp / readout_vjp helper).
+ * out_value may be NULL; out_grad is (npart, ndim) with byte strides gs0, gs1, element size out_elsize. */
+int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1);
+
+/* elementwise helpers on (strided, up to 3-D) fields */
+int pmb_field_fill(pmb_ctx *ctx, void *mesh, int elsize, int ndim, const int64_t *size,
+                   const int64_t *strides, double value);
+int pmb_field_scale(pmb_ctx *ctx, void *mesh, int elsize, int is_complex, int ndim, const int64_t *size,
+                    const int64_t *strides, double factor);
+int pmb_field_sum(pmb_ctx *ctx, const void *mesh, int elsize, int ndim, const int64_t *size,
+                  const int64_t *strides, double *sum_h);
+
+/* ---- synthetic particles (bench / tests): counter-based, reproducible ------------- */
+/* uniform in [0, box) per axis: pos[i,d] = box[d] * u(seed, i + first, d) */
+int pmb_particles_uniform(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,
+                          const double *box, uint64_t seed, int64_t first);
+/* lattice of shape n[0..ndim) offset by `shift` cells plus a smooth sinusoidal displacement of
+ * amplitude `amp` cells (Zel'dovich-like clustering); rows [first, first+npart) of the C-order lattice */
+int pmb_particles_lattice(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,
+                          const int64_t *n, const double *box, double shift, double amp,
+                          uint64_t seed, int64_t first);
+
+/* ---- domain routing ------------------------------------------------------------- */
+typedef struct pmb_decompose_args {
+    const void *pos;
+    int pos_elsize;
+    int64_t npart;
+    int64_t pos_stride0, pos_stride1;  /* bytes */
+    int ndim;                   /* dimensions of the domain grid (<= 3, <= columns of pos) */
+    double scale[3];            /* transform: x -> scale * x (pm.py:1786-1790) */
+    double smoothing[3];
+    const double *edges_h;      /* concatenated edges of every axis (host) */
+    int nedges[3];              /* len(edges[d]) */
+    int periodic;
+    const int32_t *domain_assign_h;     /* [prod(nedges-1)] domain -> rank */
+    const int16_t *domain_degenerate_h; /* [prod(nedges-1)] */
+    int nranks;                 /* <= 64 */
+} pmb_decompose_args;
+
+/* Phase 1: computes the per-particle target sets and counts_h[nranks]; *ntotal = sum(counts).
+ * Phase 2: pmb_decompose_fill writes indices[ntotal] (int32, grouped by rank asc, particle asc).
+ * Both phases must be called with the same args on the same ctx, back to back. */
+int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *counts_h, int64_t *ntotal);
+int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *indices);
+
+/* out[j] = data[indices[j]]  (records of itemsize bytes) <- ndarray.take(indices, axis=0), domain.py:188 */
+int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const int32_t *indices, int64_t n, void *out);
+/* out[i] = sum_j { data[j] : indices[j] == i } accumulated in ascending j, in float64, cast to out
+ * <- bincountv(indices, recv, minlength=sendlength), domain.py:26-48,300. ncomp values per record.
+ * offsets_h[nranks+1] delimit the per-rank sorted segments of indices. */
+int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
+                   const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize);
+
+/* ---- communicator (NCCL over NVLink), one rank per process ------------------------ */
+int pmb_comm_unique_id(char *id128_h);                      /* 128 bytes */
+int pmb_comm_init_rank(pmb_ctx *ctx, const char *id128_h, int rank, int nranks);
+int pmb_comm_destroy(pmb_ctx *ctx);
+int pmb_comm_rank(pmb_ctx *ctx, int *rank, int *nranks);
+/* alltoallv of byte records: send/recv counts and offsets in records (host arrays, int64) */
+int pmb_alltoallv(pmb_ctx *ctx, const void *send, const int64_t *sendcounts_h, const int64_t *sendoffsets_h,
+                  void *recv, const int64_t *recvcounts_h, const int64_t *recvoffsets_h, int64_t itemsize);
+int pmb_allreduce_f64(pmb_ctx *ctx, double *buf, int64_t n, int op /*0 sum, 1 max, 2 min*/);
+int pmb_allgather_bytes(pmb_ctx *ctx, const void *send, void *recv, int64_t nbytes_per_rank);
+int pmb_barrier(pmb_ctx *ctx);
+
+/* ---- FFT (slab decomposition over the ctx communicator; cuFFT for the local 1-D/2-D FFTs) ---- */
+/* real layout: padded, C order, local shape (n0_local, n1, 2*(n2/2+1)) [ndim 3];
+ * complex "transposed" layout for nranks > 1: distributed along axis 1, memory order (1,2,0);
+ * for nranks == 1: natural order (0,1,2).  dtype_elsize 4 (float) or 8 (double). */
+int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, pmb_fft **out);
+int pmb_fft_destroy(pmb_fft *plan);
+/* real-space and transposed complex-space partition of THIS rank (starts/shapes per logical axis,
+ * complex strides in elements) */
+int pmb_fft_layout(pmb_fft *plan, int64_t *i_start, int64_t *i_shape, int64_t *i_strides,
+                   int64_t *o_start, int64_t *o_shape, int64_t *o_strides,
+                   int64_t *real_alloc_elems, int64_t *complex_alloc_elems);
+/* forward: complex = FFT(real) * scale  (pm.py:689-692 uses scale = 1/prod(Nmesh)); real is preserved
+ * unless real == complex (in place). backward: real = unnormalised inverse FFT(complex) (pm.py:1017);
+ * complex is preserved unless in place. */
+int pmb_fft_r2c(pmb_fft *plan, const void *real, void *cplx, double scale);
+int pmb_fft_c2r(pmb_fft *plan, const void *cplx, void *real);
+/* seconds spent inside cuFFT exec calls since the last reset, measured with events (library time) */
+int pmb_fft_library_ms(pmb_fft *plan, float *ms, int reset);
+
+/* out = T(k) * in on the transposed complex layout of `plan`.  kinds: */
+#define PMB_TF_SCALE 0            /* params[0] */
+#define PMB_TF_GRAVITY_FD4 1      /* i*kfinite_d/k^2, examples/nbody.py:162-170; dir = d */
+#define PMB_TF_GRADIENT_K 2       /* i*k_d/k^2,       examples/nbody.py:154-160 */
+#define PMB_TF_INV_LAPLACE 3      /* -1/k^2,          examples/nbody.py:172-175 */
+#define PMB_TF_GAUSS_LOWPASS 4    /* exp(-0.5 k^2 r^2), params[0] = r, examples/nbody.py:177-181 */
+#define PMB_TF_COMPENSATE 5       /* 1/prod_d fwindow(w_d), window.py:65-80; params[0] = kind, params[1] = support */
+#define PMB_TF_IK 6               /* i*k_d (plain gradient) */
+int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
+                 const void *in, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMESH_B200_H */

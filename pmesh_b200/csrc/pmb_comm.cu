@@ -1,0 +1,135 @@
+// pmb_comm.cu -- the communicator: NCCL over NVLink 5 / NVSwitch, one rank per process.
+//
+// Replaces the mpi4py calls on the data path of the reference:
+//   Alltoallv of packed particle records ... pmesh/domain.py:199-205 (exchange), :274-281 (gather)
+//   PFFT's internal global transposes ...... pmesh/pm.py:689,1017 (plan.execute)
+//   allreduce of scalars ................... pmesh/pm.py:296,739,899 (cgetitem, csum, cdot)
+// On an NVSwitch node every peer is reachable at full bandwidth, so the alltoallv is one flat
+// ncclGroup of P sends + P receives; the self block is a device memcpy.
+#include <nccl.h>
+
+#include "pmb_internal.h"
+
+static int nccl_fail(ncclResult_t r, const char *what, int line)
+{
+    pmb_set_error("NCCL error %d (%s) at %s:%d in %s", (int) r, ncclGetErrorString(r), __FILE__, line, what);
+    return PMB_ENCCL;
+}
+
+#define PMB_NCCL(call)                                                   \
+    do {                                                                 \
+        ncclResult_t _r = (call);                                        \
+        if (_r != ncclSuccess) return nccl_fail(_r, #call, __LINE__);    \
+    } while (0)
+
+extern "C" int pmb_comm_unique_id(char *id128_h)
+{
+    PMB_REQUIRE(id128_h, "null argument");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    PMB_NCCL(ncclGetUniqueId(&id));
+    memcpy(id128_h, &id, sizeof(id));
+    return PMB_OK;
+}
+
+extern "C" int pmb_comm_init_rank(pmb_ctx *ctx, const char *id128_h, int rank, int nranks)
+{
+    PMB_REQUIRE(ctx && id128_h, "null argument");
+    PMB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / %d", rank, nranks);
+    PMB_REQUIRE(!ctx->comm, "communicator already initialised");
+    PMB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128_h, sizeof(id));
+    ncclComm_t comm;
+    PMB_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
+    ctx->comm = (ncclComm *) comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return PMB_OK;
+}
+
+extern "C" int pmb_comm_destroy(pmb_ctx *ctx)
+{
+    if (!ctx || !ctx->comm) return PMB_OK;
+    cudaStreamSynchronize(ctx->stream);
+    ncclCommDestroy((ncclComm_t) ctx->comm);
+    ctx->comm = NULL;
+    ctx->rank = 0;
+    ctx->nranks = 1;
+    return PMB_OK;
+}
+
+extern "C" int pmb_comm_rank(pmb_ctx *ctx, int *rank, int *nranks)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    return PMB_OK;
+}
+
+extern "C" int pmb_alltoallv(pmb_ctx *ctx, const void *send, const int64_t *sendcounts_h, const int64_t *sendoffsets_h,
+                             void *recv, const int64_t *recvcounts_h, const int64_t *recvoffsets_h, int64_t itemsize)
+{
+    PMB_REQUIRE(ctx && sendcounts_h && sendoffsets_h && recvcounts_h && recvoffsets_h && itemsize > 0, "bad alltoallv arguments");
+    const int P = ctx->nranks, me = ctx->rank;
+    PMB_REQUIRE(sendcounts_h[me] == recvcounts_h[me], "self send/recv counts differ");
+    if (sendcounts_h[me] > 0)
+        PMB_CUDA(cudaMemcpyAsync((char *) recv + recvoffsets_h[me] * itemsize,
+                                 (const char *) send + sendoffsets_h[me] * itemsize,
+                                 (size_t) sendcounts_h[me] * itemsize, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (P == 1) return PMB_OK;
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    ncclComm_t comm = (ncclComm_t) ctx->comm;
+    PMB_NCCL(ncclGroupStart());
+    for (int q = 0; q < P; q++) {
+        if (q == me) continue;
+        if (sendcounts_h[q] > 0)
+            PMB_NCCL(ncclSend((const char *) send + sendoffsets_h[q] * itemsize, (size_t) sendcounts_h[q] * itemsize,
+                              ncclChar, q, comm, ctx->stream));
+        if (recvcounts_h[q] > 0)
+            PMB_NCCL(ncclRecv((char *) recv + recvoffsets_h[q] * itemsize, (size_t) recvcounts_h[q] * itemsize,
+                              ncclChar, q, comm, ctx->stream));
+    }
+    PMB_NCCL(ncclGroupEnd());
+    return PMB_OK;
+}
+
+extern "C" int pmb_allreduce_f64(pmb_ctx *ctx, double *buf, int64_t n, int op)
+{
+    PMB_REQUIRE(ctx && (buf || n == 0) && n >= 0, "bad allreduce arguments");
+    PMB_REQUIRE(op >= 0 && op <= 2, "bad reduction op");
+    if (ctx->nranks == 1 || n == 0) return PMB_OK;
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    ncclRedOp_t ops[3] = {ncclSum, ncclMax, ncclMin};
+    PMB_NCCL(ncclAllReduce(buf, buf, (size_t) n, ncclDouble, ops[op], (ncclComm_t) ctx->comm, ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_allgather_bytes(pmb_ctx *ctx, const void *send, void *recv, int64_t nbytes_per_rank)
+{
+    PMB_REQUIRE(ctx && nbytes_per_rank >= 0, "bad allgather arguments");
+    if (nbytes_per_rank == 0) return PMB_OK;
+    PMB_REQUIRE(send && recv, "null buffer");
+    if (ctx->nranks == 1) {
+        if (send != recv)
+            PMB_CUDA(cudaMemcpyAsync(recv, send, (size_t) nbytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+        return PMB_OK;
+    }
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    PMB_NCCL(ncclAllGather(send, recv, (size_t) nbytes_per_rank, ncclChar, (ncclComm_t) ctx->comm, ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_barrier(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (ctx->nranks > 1) {
+        PMB_REQUIRE(ctx->comm, "communicator not initialised");
+        void *token;
+        PMB_CHECK(pmb_scratch(ctx, 256, &token));
+        PMB_CUDA(cudaMemsetAsync(token, 0, 8, ctx->stream));
+        PMB_NCCL(ncclAllReduce(token, token, 1, ncclDouble, ncclSum, (ncclComm_t) ctx->comm, ctx->stream));
+    }
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMB_OK;
+}

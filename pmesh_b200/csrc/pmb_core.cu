@@ -1,0 +1,592 @@
+// pmb_core.cu -- context, memory, timers, window registry and elementwise field helpers.
+#include "pmb_internal.h"
+
+#include <math.h>
+#include <stdlib.h>
+
+static thread_local char g_err[1024] = "";
+
+void pmb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    pmb_set_error("CUDA error %d (%s) at %s:%d in %s", (int) e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? PMB_ENOMEM : PMB_ECUDA;
+}
+
+extern "C" const char *pmb_last_error(void) { return g_err; }
+extern "C" int pmb_version(void) { return 100; }
+
+extern "C" int pmb_device_count(int *n)
+{
+    PMB_REQUIRE(n, "null argument");
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return pmb_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    return PMB_OK;
+}
+
+extern "C" int pmb_ctx_create(int device, pmb_ctx **out)
+{
+    PMB_REQUIRE(out, "null argument");
+    int n = 0;
+    PMB_CUDA(cudaGetDeviceCount(&n));
+    PMB_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    PMB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PMB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        pmb_set_error("device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        return PMB_EUNSUPPORTED;
+    }
+    pmb_ctx *ctx = (pmb_ctx *) calloc(1, sizeof(pmb_ctx));
+    if (!ctx) return PMB_ENOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->nranks = 1;
+    ctx->det_chunk_bytes = (size_t) 2 << 30;
+    PMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < PMB_NTIMERS; i++) {
+        PMB_CUDA(cudaEventCreate(&ctx->t0[i]));
+        PMB_CUDA(cudaEventCreate(&ctx->t1[i]));
+    }
+    *out = ctx;
+    return PMB_OK;
+}
+
+extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
+{
+    if (!ctx) return PMB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pmb_comm_destroy(ctx);
+    for (int i = 0; i < PMB_NTIMERS; i++) {
+        cudaEventDestroy(ctx->t0[i]);
+        cudaEventDestroy(ctx->t1[i]);
+    }
+    for (int k = 0; k < PMB_NKINDS; k++)
+        if (ctx->tables[k].d_values) cudaFree(ctx->tables[k].d_values);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->route_masks) cudaFree(ctx->route_masks);
+    if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+    return PMB_OK;
+}
+
+extern "C" int pmb_ctx_sync(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_malloc(pmb_ctx *ctx, size_t nbytes, void **out)
+{
+    PMB_REQUIRE(ctx && out, "null argument");
+    *out = NULL;
+    if (nbytes == 0) nbytes = 16;
+    PMB_CUDA(cudaMalloc(out, nbytes));
+    return PMB_OK;
+}
+
+extern "C" int pmb_free(pmb_ctx *ctx, void *ptr)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (ptr) {
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PMB_CUDA(cudaFree(ptr));
+    }
+    return PMB_OK;
+}
+
+extern "C" int pmb_malloc_host(pmb_ctx *ctx, size_t nbytes, void **out_h)
+{
+    PMB_REQUIRE(ctx && out_h, "null argument");
+    if (nbytes == 0) nbytes = 16;
+    PMB_CUDA(cudaMallocHost(out_h, nbytes));
+    return PMB_OK;
+}
+
+extern "C" int pmb_free_host(pmb_ctx *ctx, void *ptr_h)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (ptr_h) PMB_CUDA(cudaFreeHost(ptr_h));
+    return PMB_OK;
+}
+
+extern "C" int pmb_memcpy_h2d(pmb_ctx *ctx, void *dst, const void *src_h, size_t nbytes)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (!nbytes) return PMB_OK;
+    PMB_CUDA(cudaMemcpyAsync(dst, src_h, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_memcpy_d2h(pmb_ctx *ctx, void *dst_h, const void *src, size_t nbytes)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (!nbytes) return PMB_OK;
+    PMB_CUDA(cudaMemcpyAsync(dst_h, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_memcpy_d2d(pmb_ctx *ctx, void *dst, const void *src, size_t nbytes)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (!nbytes) return PMB_OK;
+    PMB_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_memset(pmb_ctx *ctx, void *dst, int byte, size_t nbytes)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (!nbytes) return PMB_OK;
+    PMB_CUDA(cudaMemsetAsync(dst, byte, nbytes, ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_mem_info(pmb_ctx *ctx, size_t *free_bytes, size_t *total_bytes)
+{
+    PMB_REQUIRE(ctx && free_bytes && total_bytes, "null argument");
+    PMB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+    return PMB_OK;
+}
+
+extern "C" int pmb_timer_start(pmb_ctx *ctx, int slot)
+{
+    PMB_REQUIRE(ctx && slot >= 0 && slot < PMB_NTIMERS, "bad timer slot");
+    PMB_CUDA(cudaEventRecord(ctx->t0[slot], ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_timer_stop(pmb_ctx *ctx, int slot, float *ms)
+{
+    PMB_REQUIRE(ctx && ms && slot >= 0 && slot < PMB_NTIMERS, "bad timer slot");
+    PMB_CUDA(cudaEventRecord(ctx->t1[slot], ctx->stream));
+    PMB_CUDA(cudaEventSynchronize(ctx->t1[slot]));
+    PMB_CUDA(cudaEventElapsedTime(ms, ctx->t0[slot], ctx->t1[slot]));
+    return PMB_OK;
+}
+
+extern "C" int pmb_launch_count(pmb_ctx *ctx, int64_t *n, int reset)
+{
+    PMB_REQUIRE(ctx && n, "null argument");
+    *n = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return PMB_OK;
+}
+
+int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out)
+{
+    if (nbytes > ctx->scratch_bytes) {
+        if (ctx->scratch) {
+            PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+            PMB_CUDA(cudaFree(ctx->scratch));
+            ctx->scratch = NULL;
+            ctx->scratch_bytes = 0;
+        }
+        size_t want = nbytes + (nbytes >> 3) + 256;
+        PMB_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return PMB_OK;
+}
+
+__global__ void pmb_k_flush(uint4 *buf, size_t n, unsigned v)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_uint4(v, v + 1, v + 2, v + 3);
+}
+
+extern "C" int pmb_flush_l2(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t) 256 << 20;
+        PMB_CUDA(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    static unsigned gen = 0;
+    size_t n = ctx->flush_bytes / sizeof(uint4);
+    pmb_k_flush<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint4 *) ctx->flush_buf, n, gen++);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+// ---------------------------------------------------------------- window registry
+struct KindInfo { int family; int native; int tuned; };
+
+static int kind_info(int kind, KindInfo *ki)
+{
+    switch (kind) {
+    case PMB_NEAREST: *ki = {PMB_FAM_NEAREST, 1, 0}; return 0;
+    case PMB_LINEAR: *ki = {PMB_FAM_LINEAR, 2, 0}; return 0;
+    case PMB_QUADRATIC: *ki = {PMB_FAM_QUADRATIC, 3, 0}; return 0;
+    case PMB_CUBIC: *ki = {PMB_FAM_CUBIC, 4, 0}; return 0;
+    case PMB_TUNED_NNB: *ki = {PMB_FAM_NEAREST, 1, 1}; return 0;
+    case PMB_TUNED_CIC: *ki = {PMB_FAM_LINEAR, 2, 2}; return 0;
+    case PMB_TUNED_TSC: *ki = {PMB_FAM_QUADRATIC, 3, 3}; return 0;
+    case PMB_TUNED_PCS: *ki = {PMB_FAM_CUBIC, 4, 4}; return 0;
+    case PMB_LANCZOS2: case PMB_LANCZOS3: case PMB_LANCZOS4: case PMB_LANCZOS5: case PMB_LANCZOS6:
+        *ki = {PMB_FAM_SYMTABLE, 2 * (kind - PMB_LANCZOS2 + 2), 0}; return 0;
+    case PMB_ACG2: case PMB_ACG3: case PMB_ACG4: case PMB_ACG5: case PMB_ACG6:
+        *ki = {PMB_FAM_SYMTABLE, kind - PMB_ACG2 + 2, 0}; return 0;
+    case PMB_DB6: case PMB_SYM6: *ki = {PMB_FAM_WAVELET, 7, 0}; return 0;
+    case PMB_DB12: case PMB_SYM12: *ki = {PMB_FAM_WAVELET, 10, 0}; return 0;
+    case PMB_DB20: *ki = {PMB_FAM_WAVELET, 13, 0}; return 0;
+    case PMB_SYM20: *ki = {PMB_FAM_WAVELET, 12, 0}; return 0;
+    }
+    pmb_set_error("unknown window kind %d", kind);
+    return PMB_EINVAL;
+}
+
+extern "C" int pmb_window_set_table(pmb_ctx *ctx, int kind, const double *values_h, int n,
+                                    double step, double nativesupport, double hsupport)
+{
+    PMB_REQUIRE(ctx && values_h && n > 1, "bad table");
+    KindInfo ki;
+    PMB_CHECK(kind_info(kind, &ki));
+    PMB_REQUIRE(ki.family == PMB_FAM_SYMTABLE || ki.family == PMB_FAM_WAVELET, "kind %d is not table driven", kind);
+    PMB_REQUIRE((int) nativesupport == ki.native, "table support %g != %d for kind %d", nativesupport, ki.native, kind);
+    pmb_table *t = &ctx->tables[kind];
+    if (t->d_values) {
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PMB_CUDA(cudaFree(t->d_values));
+        t->d_values = NULL;
+    }
+    PMB_CUDA(cudaMalloc(&t->d_values, sizeof(double) * n));
+    PMB_CUDA(cudaMemcpy(t->d_values, values_h, sizeof(double) * n, cudaMemcpyHostToDevice));
+    t->n = n;
+    t->step = step;
+    t->nativesupport = nativesupport;
+    t->hsupport = hsupport;
+    return PMB_OK;
+}
+
+// <- pmesh_painter_init (pmesh/_window_imp.c:246-456)
+int pmb_resolve_window(pmb_ctx *ctx, int kind, int support_req, int ndim, const int *order,
+                       PmbWindow *w, int for_device)
+{
+    KindInfo ki;
+    PMB_CHECK(kind_info(kind, &ki));
+    memset(w, 0, sizeof(*w));
+    w->kind = kind;
+    w->family = ki.family;
+    w->nativesupport = ki.native;
+    PmbWinInfo info;
+    pmb_window_info(ki.native, (double) support_req, &info);
+    w->support = info.support;
+    w->tuned = 0;
+    if (ki.tuned && ndim <= 3) {
+        int ok = 1;
+        for (int d = 0; d < ndim; d++) if (order && order[d] > 1) ok = 0;
+        if (ok) w->tuned = ki.tuned;
+    }
+    if (ki.family == PMB_FAM_SYMTABLE || ki.family == PMB_FAM_WAVELET) {
+        if (for_device) {
+            PMB_REQUIRE(ctx && ctx->tables[kind].d_values, "lookup table of window kind %d was not uploaded", kind);
+            w->table = ctx->tables[kind].d_values;
+            w->tablesize = ctx->tables[kind].n;
+            w->step = ctx->tables[kind].step;
+            w->hsupport = ctx->tables[kind].hsupport;
+        }
+    }
+    return PMB_OK;
+}
+
+extern "C" int pmb_window_query(int kind, int support_req, int *support, int *nativesupport)
+{
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(NULL, kind, support_req, 0, NULL, &w, 0));
+    if (support) *support = w.support;
+    if (nativesupport) *nativesupport = w.nativesupport;
+    return PMB_OK;
+}
+
+static double sinc_unnormed(double x)
+{
+    if (x < 1e-5 && x > -1e-5) {
+        double x2 = x * x;
+        return 1.0 - x2 / 6. + x2 * x2 / 120.;
+    }
+    return sin(x) / x;
+}
+
+// <- pmesh_painter_get_fwindow (pmesh/_window_imp.c:473-484): sinc^p(w/2/vfactor), 1.0 for table windows
+extern "C" int pmb_window_fwindow(int kind, int support, const double *w_h, double *out_h, int64_t n)
+{
+    PMB_REQUIRE(n == 0 || (w_h && out_h), "null argument");
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(NULL, kind, support, 0, NULL, &w, 0));
+    PmbWinInfo info;
+    pmb_window_info(w.nativesupport, (double) support, &info);
+    int p = 0;
+    if (w.family == PMB_FAM_NEAREST) p = 1;
+    else if (w.family == PMB_FAM_LINEAR) p = 2;
+    else if (w.family == PMB_FAM_QUADRATIC) p = 3;
+    else if (w.family == PMB_FAM_CUBIC) p = 4;
+    for (int64_t i = 0; i < n; i++) {
+        if (!p) { out_h[i] = 1.0; continue; }
+        double t = sinc_unnormed(0.5 * (w_h[i] / info.vfactor));
+        double r = t;
+        for (int j = 1; j < p; j++) r = r * t;
+        out_h[i] = r;
+    }
+    return PMB_OK;
+}
+
+// ---------------------------------------------------------------- field helpers
+struct FieldView {
+    int64_t size[3];
+    int64_t strides[3];
+    int64_t n;
+};
+
+static int make_view(int ndim, const int64_t *size, const int64_t *strides, FieldView *v)
+{
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3 && size && strides, "bad field view");
+    // left-pad to 3-D
+    int pad = 3 - ndim;
+    v->n = 1;
+    for (int d = 0; d < 3; d++) {
+        if (d < pad) { v->size[d] = 1; v->strides[d] = 0; }
+        else { v->size[d] = size[d - pad]; v->strides[d] = strides[d - pad]; }
+        v->n *= v->size[d];
+    }
+    return PMB_OK;
+}
+
+__device__ __forceinline__ int64_t view_offset(const FieldView &v, int64_t i)
+{
+    int64_t k = i % v.size[2];
+    int64_t r = i / v.size[2];
+    int64_t j = r % v.size[1];
+    int64_t a = r / v.size[1];
+    return a * v.strides[0] + j * v.strides[1] + k * v.strides[2];
+}
+
+template <typename T>
+__global__ void pmb_k_fill(char *mesh, FieldView v, T value)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < v.n; i += stride) *(T *) (mesh + view_offset(v, i)) = value;
+}
+
+template <typename T>
+__global__ void pmb_k_scale(char *mesh, FieldView v, double factor)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < v.n; i += stride) {
+        T *p = (T *) (mesh + view_offset(v, i));
+        *p = (T) (*p * (T) factor);
+    }
+}
+
+extern "C" int pmb_field_fill(pmb_ctx *ctx, void *mesh, int elsize, int ndim, const int64_t *size,
+                              const int64_t *strides, double value)
+{
+    PMB_REQUIRE(ctx && mesh, "null argument");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "elsize must be 4 or 8");
+    FieldView v;
+    PMB_CHECK(make_view(ndim, size, strides, &v));
+    if (v.n == 0) return PMB_OK;
+    int grid = pmb_grid(ctx, v.n, 256, 8);
+    if (elsize == 8) pmb_k_fill<double><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, value);
+    else pmb_k_fill<float><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, (float) value);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+// numpy semantics of `value[...] *= factor`: real fields multiply in their own dtype
+// (pm.py:692 multiplies a complex array by a python float: component-wise in the field dtype)
+extern "C" int pmb_field_scale(pmb_ctx *ctx, void *mesh, int elsize, int is_complex, int ndim,
+                               const int64_t *size, const int64_t *strides, double factor)
+{
+    PMB_REQUIRE(ctx && mesh, "null argument");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "elsize must be 4 or 8 (per real component)");
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3, "bad ndim");
+    int64_t sz[3], st[3];
+    for (int d = 0; d < ndim; d++) { sz[d] = size[d]; st[d] = strides[d]; }
+    if (is_complex) {
+        // view the complex array as reals with the last axis doubled (requires a contiguous last axis)
+        PMB_REQUIRE(st[ndim - 1] == 2 * elsize || ndim < 3,
+                    "complex scale needs a contiguous last axis or ndim < 3");
+        if (st[ndim - 1] == 2 * elsize) {
+            sz[ndim - 1] *= 2;
+            st[ndim - 1] = elsize;
+        } else {
+            // prepend nothing: add a trailing axis of 2 components
+            sz[ndim] = 2; st[ndim] = elsize; ndim += 1;
+        }
+    }
+    FieldView v;
+    PMB_CHECK(make_view(ndim, sz, st, &v));
+    if (v.n == 0) return PMB_OK;
+    int grid = pmb_grid(ctx, v.n, 256, 8);
+    if (elsize == 8) pmb_k_scale<double><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, factor);
+    else pmb_k_scale<float><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, factor);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+template <typename T>
+__global__ void pmb_k_sum(const char *mesh, FieldView v, double *out)
+{
+    __shared__ double sh[32];
+    double acc = 0;
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < v.n; i += stride) acc += (double) *(const T *) (mesh + view_offset(v, i));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[blockIdx.x] = acc;
+    }
+}
+
+// not bit-reproducible against numpy's pairwise sum; used for csum/cmean style diagnostics (pm.py:725-743)
+extern "C" int pmb_field_sum(pmb_ctx *ctx, const void *mesh, int elsize, int ndim, const int64_t *size,
+                             const int64_t *strides, double *sum_h)
+{
+    PMB_REQUIRE(ctx && mesh && sum_h, "null argument");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "elsize must be 4 or 8");
+    FieldView v;
+    PMB_CHECK(make_view(ndim, size, strides, &v));
+    *sum_h = 0;
+    if (v.n == 0) return PMB_OK;
+    int grid = pmb_grid(ctx, v.n, 256, 4);
+    void *partial;
+    PMB_CHECK(pmb_scratch(ctx, sizeof(double) * grid, &partial));
+    if (elsize == 8) pmb_k_sum<double><<<grid, 256, 0, ctx->stream>>>((const char *) mesh, v, (double *) partial);
+    else pmb_k_sum<float><<<grid, 256, 0, ctx->stream>>>((const char *) mesh, v, (double *) partial);
+    PMB_LAUNCH_CHECK(ctx);
+    double *h = (double *) malloc(sizeof(double) * grid);
+    if (!h) return PMB_ENOMEM;
+    cudaError_t e = cudaMemcpyAsync(h, partial, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); return pmb_cuda_fail(e, "sum copy", __FILE__, __LINE__); }
+    double s = 0;
+    for (int i = 0; i < grid; i++) s += h[i];
+    free(h);
+    *sum_h = s;
+    return PMB_OK;
+}
+
+// ---------------------------------------------------------------- synthetic particles
+// splitmix64 counter hash -> uniform double in [0,1): reproducible for any launch geometry.
+__host__ __device__ static inline uint64_t pmb_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ static inline double pmb_u01(uint64_t seed, uint64_t i, uint64_t d)
+{
+    uint64_t h = pmb_mix64(pmb_mix64(seed ^ (d * 0xD6E8FEB86659FD93ull)) + i);
+    return (double) (h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void pmb_k_uniform(void *pos, int elsize, int64_t npart, int ndim, double b0, double b1, double b2,
+                              uint64_t seed, int64_t first)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    double box[3] = {b0, b1, b2};
+    for (; i < npart; i += stride)
+        for (int d = 0; d < ndim; d++) {
+            double x = box[d] * pmb_u01(seed, (uint64_t) (i + first), d);
+            if (elsize == 4) {
+                float xf = (float) x;
+                if (xf >= (float) box[d]) xf = 0.f;
+                ((float *) pos)[i * ndim + d] = xf;
+            } else ((double *) pos)[i * ndim + d] = x;
+        }
+}
+
+extern "C" int pmb_particles_uniform(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,
+                                     const double *box, uint64_t seed, int64_t first)
+{
+    PMB_REQUIRE(ctx && pos && box, "null argument");
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3 && (pos_elsize == 4 || pos_elsize == 8), "bad ndim/elsize");
+    if (!npart) return PMB_OK;
+    double b[3] = {box[0], ndim > 1 ? box[1] : 0, ndim > 2 ? box[2] : 0};
+    pmb_k_uniform<<<pmb_grid(ctx, npart, 256, 8), 256, 0, ctx->stream>>>(pos, pos_elsize, npart, ndim, b[0], b[1], b[2], seed, first);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+struct LatticeArgs {
+    int ndim;
+    int64_t n[3];
+    double box[3];
+    double shift, amp;
+    double phase[3][3];
+};
+
+// x_d = (q_d + shift + amp * sum_e sin(2 pi m (q_e + shift)/n_e + phase_de) / ndim) * box_d / n_d  (mod box)
+__global__ void pmb_k_lattice(void *pos, int elsize, int64_t npart, LatticeArgs a, int64_t first)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        int64_t r = i + first;
+        int64_t q[3] = {0, 0, 0};
+        for (int d = a.ndim - 1; d >= 0; d--) { q[d] = r % a.n[d]; r /= a.n[d]; }
+        for (int d = 0; d < a.ndim; d++) {
+            double disp = 0;
+            for (int e = 0; e < a.ndim; e++)
+                disp += sin(6.283185307179586 * 4.0 * ((double) q[e] + a.shift) / (double) a.n[e] + a.phase[d][e]);
+            double g = (double) q[d] + a.shift + a.amp * disp / a.ndim;
+            double nn = (double) a.n[d];
+            g = g - floor(g / nn) * nn;
+            if (g >= nn) g = 0;
+            double x = g * (a.box[d] / nn);
+            if (elsize == 4) {
+                float xf = (float) x;
+                if (xf >= (float) a.box[d]) xf = 0.f;
+                ((float *) pos)[i * a.ndim + d] = xf;
+            } else ((double *) pos)[i * a.ndim + d] = x;
+        }
+    }
+}
+
+extern "C" int pmb_particles_lattice(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,
+                                     const int64_t *n, const double *box, double shift, double amp,
+                                     uint64_t seed, int64_t first)
+{
+    PMB_REQUIRE(ctx && pos && box && n, "null argument");
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3 && (pos_elsize == 4 || pos_elsize == 8), "bad ndim/elsize");
+    if (!npart) return PMB_OK;
+    LatticeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ndim = ndim;
+    for (int d = 0; d < ndim; d++) { a.n[d] = n[d]; a.box[d] = box[d]; }
+    a.shift = shift;
+    a.amp = amp;
+    for (int d = 0; d < 3; d++)
+        for (int e = 0; e < 3; e++) a.phase[d][e] = 6.283185307179586 * pmb_u01(seed, d * 3 + e, 7);
+    pmb_k_lattice<<<pmb_grid(ctx, npart, 256, 8), 256, 0, ctx->stream>>>(pos, pos_elsize, npart, a, first);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}

@@ -1,0 +1,414 @@
+// pmb_domain.cu -- GPU particle routing: rank/cell assignment, stable compaction, take, ghost sum.
+//
+// Replaces the host path  GridND.decompose (numpy digitize chunks, pmesh/domain.py:606-639)
+//                       + gridnd_fill       (two-pass count/fill,   pmesh/_domain.pyx:9-122)
+//                       + ndarray.take      (pmesh/domain.py:188)
+//                       + bincountv         (pmesh/domain.py:26-48, gather mode 'sum').
+// All integer results are bit-identical to the reference: `indices` lists particle ids grouped by
+// target rank ascending and, within a rank, by particle id ascending (the reference's fill order).
+//
+// Design: the per-particle target set is a 64-bit rank mask (<= 64 ranks), which makes the
+// reference's insertion sort + de-duplication (_domain.pyx:86-113) implicit.  A block owns a
+// contiguous range of particles; per-(block, rank) histograms + one tiny scan give every block its
+// write cursor, and ballots inside the block keep the particle order stable.
+#include "pmb_internal.h"
+
+#define ROUTE_BLOCK 256
+#define ROUTE_MAXRANKS 64
+#define ROUTE_MAXEDGES 1024
+
+struct RouteGeom {
+    int ndim;
+    int periodic;
+    int nranks;
+    int ndomains;
+    int shape[3];
+    int dstride[3];
+    double scale[3];
+    double smoothing[3];
+    const double *edges[3];      // device
+    int nedges[3];
+    const int32_t *assign;       // device [ndomains]
+    const int16_t *degenerate;   // device [ndomains]
+};
+
+// numpy floored modulo for doubles (npy_divmod): result has the sign of b, may round up to b itself
+// (-1e-17 % 64.0 == 64.0); ref use: pmesh/domain.py:616-619
+__device__ __forceinline__ double pmb_pymod(double a, double b)
+{
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if ((b < 0) != (m < 0)) m += b;
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+// numpy.digitize(x, bins, right=False) for increasing bins: number of bins <= x (len(bins) for NaN)
+__device__ __forceinline__ int pmb_digitize(double x, const double *bins, int n)
+{
+    if (x != x) return n;
+    int lo = 0, hi = n;            // first index with bins[idx] > x
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (bins[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// python non-negative integer modulo
+__device__ __forceinline__ int pmb_imod(int a, int n)
+{
+    int m = a % n;
+    return m < 0 ? m + n : m;
+}
+
+// per-particle rank mask; ref: pmesh/domain.py:609-630 (sil/sir) + pmesh/_domain.pyx:62-100 (patch walk)
+__device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t i)
+{
+    int sil[3], sir[3];
+    for (int d = 0; d < g.ndim; d++) {
+        const double x = g.scale[d] * pmb_ld_real(pos, i * ps0 + d * ps1, elsize);
+        const double sm = g.smoothing[d];
+        const double *e = g.edges[d];
+        const int ne = g.nedges[d];
+        int l, r;
+        if (g.periodic) {
+            const double box = e[ne - 1];
+            const double c = pmb_pymod(x, box);
+            l = pmb_digitize(pmb_pymod(c - sm, box), e, ne);
+            r = pmb_digitize(pmb_pymod(c + sm, box), e, ne);
+            const int p = pmb_digitize(c, e, ne);
+            l = p - pmb_imod(p - l, g.shape[d]) - 1;
+            r = p + pmb_imod(r - p, g.shape[d]);
+        } else {
+            l = pmb_digitize(x - sm, e, ne);
+            r = pmb_digitize(x + sm, e, ne);
+            l = l - 1;
+            l = l < 0 ? 0 : (l > g.shape[d] ? g.shape[d] : l);
+            r = r < 0 ? 0 : (r > g.shape[d] ? g.shape[d] : r);
+        }
+        sil[d] = (int) (int16_t) l;     // the reference stores sil/sir as int16 (domain.py:603-604)
+        sir[d] = (int) (int16_t) r;
+    }
+    long long patch = 1;
+    int p[3];
+    for (int d = 0; d < g.ndim; d++) { patch *= (sir[d] - sil[d]); p[d] = sil[d]; }
+    uint64_t mask = 0;
+    for (long long q = 0; q < patch; q++) {
+        int target = 0;
+        for (int d = 0; d < g.ndim; d++) {
+            int t = p[d];
+            if (g.periodic) t = pmb_imod(t, g.shape[d]);
+            target += t * g.dstride[d];
+        }
+        if (target >= 0 && target < g.ndomains) {
+            const int rank = g.assign[target];
+            // quirk kept: the degenerate flag is looked up by RANK, not by domain (_domain.pyx:81-83)
+            const int deg = (rank >= 0 && rank < g.ndomains) ? g.degenerate[rank] : 0;
+            if (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) mask |= (uint64_t) 1 << rank;
+        }
+        p[g.ndim - 1] += 1;
+        for (int d = g.ndim - 1; d > 0; d--) {
+            if (p[d] == sir[d]) { p[d] = sil[d]; p[d - 1] += 1; } else break;
+        }
+    }
+    return mask;
+}
+
+// block b owns particles [b*per_block, (b+1)*per_block)
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t npart,
+                  int64_t per_block, uint64_t *masks, int32_t *blockhist)
+{
+    __shared__ int hist[ROUTE_MAXRANKS];
+    if (threadIdx.x < ROUTE_MAXRANKS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t begin = blockIdx.x * per_block;
+    const int64_t end = min(begin + per_block, npart);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = begin; base < end; base += ROUTE_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        uint64_t mask = 0;
+        if (i < end) {
+            mask = pmb_route_mask(g, pos, elsize, ps0, ps1, i);
+            masks[i] = mask;
+        }
+        for (int r = 0; r < g.nranks; r++) {
+            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
+            if (lane == 0 && b) atomicAdd(&hist[r], __popc(b));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < g.nranks) blockhist[(int64_t) blockIdx.x * g.nranks + threadIdx.x] = hist[threadIdx.x];
+}
+
+// one thread per rank: totals and exclusive per-block cursors (rank-major output order)
+__global__ void pmb_k_route_scan(int32_t *blockhist, int nblocks, int nranks, int64_t *totals)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    int64_t t = 0;
+    for (int b = 0; b < nblocks; b++) t += blockhist[(int64_t) b * nranks + r];
+    totals[r] = t;
+}
+
+__global__ void pmb_k_route_cursors(int32_t *blockhist, int nblocks, int nranks, const int64_t *totals)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    int64_t base = 0;
+    for (int q = 0; q < r; q++) base += totals[q];
+    for (int b = 0; b < nblocks; b++) {
+        int32_t c = blockhist[(int64_t) b * nranks + r];
+        blockhist[(int64_t) b * nranks + r] = (int32_t) base;
+        base += c;
+    }
+}
+
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+pmb_k_route_fill(int nranks, int64_t npart, int64_t per_block, const uint64_t *masks,
+                 const int32_t *blockcursor, int32_t *indices)
+{
+    __shared__ int cursor[ROUTE_MAXRANKS];
+    __shared__ int warpcount[ROUTE_BLOCK / 32][ROUTE_MAXRANKS];
+    if (threadIdx.x < nranks) cursor[threadIdx.x] = blockcursor[(int64_t) blockIdx.x * nranks + threadIdx.x];
+    __syncthreads();
+    const int64_t begin = blockIdx.x * per_block;
+    const int64_t end = min(begin + per_block, npart);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t base = begin; base < end; base += ROUTE_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        const uint64_t mask = i < end ? masks[i] : 0;
+        for (int r = 0; r < nranks; r++) {
+            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
+            if (lane == 0) warpcount[warp][r] = __popc(b);
+        }
+        __syncthreads();
+        for (int r = 0; r < nranks; r++) {
+            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
+            if ((mask >> r) & 1) {
+                int pos = cursor[r];
+                for (int w = 0; w < warp; w++) pos += warpcount[w][r];
+                pos += __popc(b & lt);
+                indices[pos] = (int32_t) i;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < nranks) {
+            int s = 0;
+            for (int w = 0; w < ROUTE_BLOCK / 32; w++) s += warpcount[w][threadIdx.x];
+            cursor[threadIdx.x] += s;
+        }
+        __syncthreads();
+    }
+}
+
+static int route_setup(pmb_ctx *ctx, const pmb_decompose_args *a, RouteGeom *g, void **dev_tables)
+{
+    PMB_REQUIRE(ctx && a, "null argument");
+    PMB_REQUIRE(a->ndim >= 1 && a->ndim <= 3, "domain grid must be 1..3 dimensional");
+    PMB_REQUIRE(a->nranks >= 1 && a->nranks <= ROUTE_MAXRANKS, "routing supports 1..%d ranks", ROUTE_MAXRANKS);
+    PMB_REQUIRE(a->pos_elsize == 4 || a->pos_elsize == 8, "pos must be float32 or float64");
+    PMB_REQUIRE(a->npart >= 0 && a->npart < ((int64_t) 1 << 31), "npart must be < 2^31 (domain.py:590)");
+    PMB_REQUIRE(a->edges_h && a->domain_assign_h && a->domain_degenerate_h, "null domain tables");
+    memset(g, 0, sizeof(*g));
+    g->ndim = a->ndim;
+    g->periodic = a->periodic;
+    g->nranks = a->nranks;
+    int ndomains = 1, tot_edges = 0;
+    for (int d = 0; d < a->ndim; d++) {
+        PMB_REQUIRE(a->nedges[d] >= 2 && a->nedges[d] <= ROUTE_MAXEDGES, "bad number of edges on axis %d", d);
+        g->shape[d] = a->nedges[d] - 1;
+        g->nedges[d] = a->nedges[d];
+        g->scale[d] = a->scale[d];
+        g->smoothing[d] = a->smoothing[d];
+        ndomains *= g->shape[d];
+        tot_edges += a->nedges[d];
+    }
+    g->ndomains = ndomains;
+    int st = 1;
+    for (int d = a->ndim - 1; d >= 0; d--) { g->dstride[d] = st; st *= g->shape[d]; }
+    // one small device allocation holds edges | assign | degenerate
+    size_t b_edges = sizeof(double) * tot_edges;
+    size_t b_assign = (sizeof(int32_t) * ndomains + 7) & ~(size_t) 7;
+    size_t b_deg = (sizeof(int16_t) * ndomains + 7) & ~(size_t) 7;
+    char *dev;
+    PMB_CUDA(cudaMalloc(&dev, b_edges + b_assign + b_deg));
+    cudaError_t e = cudaMemcpyAsync(dev, a->edges_h, b_edges, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev + b_edges, a->domain_assign_h, sizeof(int32_t) * ndomains, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev + b_edges + b_assign, a->domain_degenerate_h, sizeof(int16_t) * ndomains, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(dev); return pmb_cuda_fail(e, "route tables", __FILE__, __LINE__); }
+    int o = 0;
+    for (int d = 0; d < a->ndim; d++) { g->edges[d] = (const double *) dev + o; o += a->nedges[d]; }
+    g->assign = (const int32_t *) (dev + b_edges);
+    g->degenerate = (const int16_t *) (dev + b_edges + b_assign);
+    *dev_tables = dev;
+    return PMB_OK;
+}
+
+static int ensure(void **buf, size_t *have, size_t need, cudaStream_t s)
+{
+    if (need <= *have) return PMB_OK;
+    if (*buf) { PMB_CUDA(cudaStreamSynchronize(s)); PMB_CUDA(cudaFree(*buf)); *buf = NULL; *have = 0; }
+    size_t want = need + (need >> 3) + 256;
+    PMB_CUDA(cudaMalloc(buf, want));
+    *have = want;
+    return PMB_OK;
+}
+
+extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *counts_h, int64_t *ntotal)
+{
+    PMB_REQUIRE(counts_h && ntotal, "null output");
+    RouteGeom g;
+    void *tables = NULL;
+    PMB_CHECK(route_setup(ctx, a, &g, &tables));
+    for (int r = 0; r < a->nranks; r++) counts_h[r] = 0;
+    *ntotal = 0;
+    ctx->route_npart = a->npart;
+    ctx->route_nblocks = 0;
+    if (a->npart == 0) { cudaFree(tables); return PMB_OK; }
+
+    int64_t nblocks = (a->npart + ROUTE_BLOCK - 1) / ROUTE_BLOCK;
+    const int64_t cap = (int64_t) ctx->sm_count * 8;
+    if (nblocks > cap) nblocks = cap;
+    int64_t per_block = (a->npart + nblocks - 1) / nblocks;
+    per_block = (per_block + ROUTE_BLOCK - 1) / ROUTE_BLOCK * ROUTE_BLOCK;
+    nblocks = (a->npart + per_block - 1) / per_block;
+    int rc = ensure(&ctx->route_masks, &ctx->route_masks_bytes, sizeof(uint64_t) * a->npart, ctx->stream);
+    if (rc == PMB_OK)
+        rc = ensure(&ctx->route_blockhist, &ctx->route_blockhist_bytes,
+                    sizeof(int32_t) * nblocks * a->nranks + sizeof(int64_t) * ROUTE_MAXRANKS, ctx->stream);
+    if (rc != PMB_OK) { cudaFree(tables); return rc; }
+    int32_t *hist = (int32_t *) ctx->route_blockhist;
+    int64_t *totals = (int64_t *) ((char *) ctx->route_blockhist + ((sizeof(int32_t) * nblocks * a->nranks + 7) & ~(size_t) 7));
+    // keep totals inside the allocation
+    if ((char *) (totals + ROUTE_MAXRANKS) > (char *) ctx->route_blockhist + ctx->route_blockhist_bytes) {
+        cudaFree(tables);
+        pmb_set_error("internal: routing scratch too small");
+        return PMB_EINVAL;
+    }
+    pmb_k_route_count<<<(int) nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
+        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_block,
+        (uint64_t *) ctx->route_masks, hist);
+    ctx->launches++;
+    pmb_k_route_scan<<<1, ROUTE_MAXRANKS, 0, ctx->stream>>>(hist, (int) nblocks, a->nranks, totals);
+    ctx->launches++;
+    pmb_k_route_cursors<<<1, ROUTE_MAXRANKS, 0, ctx->stream>>>(hist, (int) nblocks, a->nranks, totals);
+    ctx->launches++;
+    int64_t totals_h[ROUTE_MAXRANKS];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(totals_h, totals, sizeof(int64_t) * a->nranks, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tables);
+    if (e != cudaSuccess) return pmb_cuda_fail(e, "route count", __FILE__, __LINE__);
+    int64_t tot = 0;
+    for (int r = 0; r < a->nranks; r++) {
+        PMB_REQUIRE(totals_h[r] < ((int64_t) 1 << 31), "more than 2^31 particles routed to rank %d", r);
+        counts_h[r] = (int32_t) totals_h[r];
+        tot += totals_h[r];
+    }
+    PMB_REQUIRE(tot < ((int64_t) 1 << 31), "routed particle count overflows int32 offsets (domain.py:590)");
+    *ntotal = tot;
+    ctx->route_nblocks = (int) nblocks;
+    ctx->route_per_block = per_block;
+    return PMB_OK;
+}
+
+extern "C" int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *indices)
+{
+    PMB_REQUIRE(ctx && a, "null argument");
+    PMB_REQUIRE(ctx->route_npart == a->npart, "pmb_decompose_fill must follow pmb_decompose_count with the same particles");
+    if (a->npart == 0 || ctx->route_nblocks == 0) return PMB_OK;
+    PMB_REQUIRE(indices, "null indices");
+    const int64_t per_block = ctx->route_per_block;
+    pmb_k_route_fill<<<ctx->route_nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
+        a->nranks, a->npart, per_block, (const uint64_t *) ctx->route_masks,
+        (const int32_t *) ctx->route_blockhist, indices);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+// ------------------------------------------------------------------ take (gather-pack)
+template <typename W>
+__global__ void pmb_k_take(const W *data, int64_t words, const int32_t *indices, int64_t n, W *out)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t total = n * words;
+    for (; t < total; t += stride) {
+        const int64_t j = t / words, w = t - j * words;
+        out[t] = data[(int64_t) indices[j] * words + w];
+    }
+}
+
+extern "C" int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const int32_t *indices, int64_t n, void *out)
+{
+    PMB_REQUIRE(ctx && itemsize > 0 && n >= 0, "bad take arguments");
+    if (n == 0) return PMB_OK;
+    PMB_REQUIRE(data && indices && out, "null argument");
+    const uintptr_t al = (uintptr_t) data | (uintptr_t) out | (uintptr_t) itemsize;
+    if ((al & 7) == 0) {
+        int64_t words = itemsize / 8;
+        pmb_k_take<uint64_t><<<pmb_grid(ctx, n * words, 256, 8), 256, 0, ctx->stream>>>((const uint64_t *) data, words, indices, n, (uint64_t *) out);
+    } else if ((al & 3) == 0) {
+        int64_t words = itemsize / 4;
+        pmb_k_take<uint32_t><<<pmb_grid(ctx, n * words, 256, 8), 256, 0, ctx->stream>>>((const uint32_t *) data, words, indices, n, (uint32_t *) out);
+    } else {
+        pmb_k_take<uint8_t><<<pmb_grid(ctx, n * itemsize, 256, 8), 256, 0, ctx->stream>>>((const uint8_t *) data, itemsize, indices, n, (uint8_t *) out);
+    }
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+// ------------------------------------------------------------------ ghost reduction (gather 'sum')
+struct GatherSegs {
+    int nranks;
+    int64_t off[ROUTE_MAXRANKS + 1];
+};
+
+// out[i] = sum over ranks r (ascending) of data[j] where indices[j] == i inside segment r.
+// Each segment is sorted ascending by construction, and holds a particle at most once.
+__global__ void pmb_k_gather_sum(const void *data, int data_elsize, int ncomp, const int32_t *indices,
+                                 GatherSegs segs, int64_t nout, void *out, int out_elsize)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t total = nout * ncomp;
+    for (; t < total; t += stride) {
+        const int64_t i = t / ncomp;
+        const int c = (int) (t - i * ncomp);
+        double acc = 0.0;
+        for (int r = 0; r < segs.nranks; r++) {
+            int64_t lo = segs.off[r], hi = segs.off[r + 1];
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (indices[mid] < i) lo = mid + 1; else hi = mid;
+            }
+            if (lo < segs.off[r + 1] && indices[lo] == i)
+                acc += pmb_ld_real(data, (lo * ncomp + c) * data_elsize, data_elsize);
+        }
+        pmb_st_real(out, t * out_elsize, out_elsize, acc);
+    }
+}
+
+extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
+                              const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize)
+{
+    PMB_REQUIRE(ctx && offsets_h && ncomp >= 1 && nout >= 0, "bad gather arguments");
+    PMB_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXRANKS, "gather supports 1..%d ranks", ROUTE_MAXRANKS);
+    PMB_REQUIRE((data_elsize == 4 || data_elsize == 8) && (out_elsize == 4 || out_elsize == 8), "float32/float64 only");
+    if (nout == 0) return PMB_OK;
+    PMB_REQUIRE(out, "null out");
+    GatherSegs segs;
+    segs.nranks = nranks;
+    for (int r = 0; r <= nranks; r++) segs.off[r] = offsets_h[r];
+    PMB_REQUIRE(segs.off[nranks] == 0 || (data && indices), "null data / indices");
+    pmb_k_gather_sum<<<pmb_grid(ctx, nout * ncomp, 256, 8), 256, 0, ctx->stream>>>(
+        data, data_elsize, ncomp, indices, segs, nout, out, out_elsize);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}

@@ -1,0 +1,564 @@
+// pmb_fft.cu -- r2c / c2r on the padded pmesh layouts, slab-decomposed over the communicator,
+// plus the k-space transfer kernels of the PM force step.
+//
+// Replaces pfft.Plan.execute as used by RealField.r2c / ComplexField.c2r (pmesh/pm.py:655-694,
+// 987-1019): forward = unnormalised DFT times `scale` (the caller passes 1/prod(Nmesh), pm.py:692),
+// backward = unnormalised inverse.  cuFFT does the local batched 1-D/2-D transforms (library time,
+// accounted separately with events); the pack / global transpose / unpack(+scale) around the NCCL
+// all-to-all and the transfer functions are this library's kernels.
+//
+// Layouts (elements of the real dtype T, complex = 2 T):
+//   real  : C order (n0_local, n1, 2*(n2/2+1)), last axis padded -- PFFT_PADDED_R2C (pm.py:1335)
+//   complex, 1 rank : C order (n0, n1, nc)
+//   complex, P ranks: distributed along axis 1, memory order (1, 2, 0) = (n1_local, nc, n0)
+//                     -- the "transposed out" representation (TransposedComplexField, pm.py:1078-1086)
+#include <cufft.h>
+#include <stdlib.h>
+
+#include "pmb_internal.h"
+
+#define FFT_NEV 32
+
+struct pmb_fft {
+    pmb_ctx *ctx;
+    int ndim;
+    int64_t n[3];      // left-padded to 3-D: (1, 1, n) / (1, n0, n1) / (n0, n1, n2)
+    int64_t nc;        // n[2] / 2 + 1
+    int elsize;        // 4 or 8
+    int P, rank;
+    int64_t s0, m0, blk0;   // real-space slab of this rank along the first distributed axis
+    int64_t s1, m1, blk1;   // complex-space slab along axis 1
+    int dist_axis;          // index in n[] of the real-space distributed axis (P > 1): 0
+    cufftHandle full_r2c, full_c2r;         // P == 1
+    cufftHandle slab_r2c, slab_c2r, line;   // P > 1
+    bool have_full, have_slab;
+    void *work0, *work1;
+    size_t work_bytes;
+    cudaEvent_t ev[FFT_NEV][2];
+    int nev;
+    float lib_ms;
+};
+
+static int cufft_fail(cufftResult r, const char *what, int line)
+{
+    pmb_set_error("cuFFT error %d at %s:%d in %s", (int) r, __FILE__, line, what);
+    return PMB_ECUDA;
+}
+#define PMB_CUFFT(call)                                                  \
+    do {                                                                 \
+        cufftResult _r = (call);                                         \
+        if (_r != CUFFT_SUCCESS) return cufft_fail(_r, #call, __LINE__); \
+    } while (0)
+
+static void block_partition(int64_t n, int P, int rank, int64_t *blk, int64_t *start, int64_t *len)
+{
+    // FFTW/PFFT default block: ceil(n / P); trailing ranks may own fewer (or zero) rows
+    int64_t b = (n + P - 1) / P;
+    int64_t s = b * rank;
+    if (s > n) s = n;
+    int64_t e = s + b;
+    if (e > n) e = n;
+    *blk = b; *start = s; *len = e - s;
+}
+
+static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long long *inembed, long long idist,
+                     long long *onembed, long long odist, cufftType type, long long batch)
+{
+    PMB_CUFFT(cufftCreate(h));
+    size_t ws = 0;
+    PMB_CUFFT(cufftMakePlanMany64(*h, rank, n, inembed, 1, idist, onembed, 1, odist, type, batch, &ws));
+    PMB_CUFFT(cufftSetStream(*h, f->ctx->stream));
+    return PMB_OK;
+}
+
+extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, pmb_fft **out)
+{
+    PMB_REQUIRE(ctx && nmesh && out, "null argument");
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3, "FFT supports 1..3 dimensions");
+    PMB_REQUIRE(dtype_elsize == 4 || dtype_elsize == 8, "FFT dtype must be float32 or float64");
+    for (int d = 0; d < ndim; d++) PMB_REQUIRE(nmesh[d] >= 1, "bad mesh size");
+    PMB_REQUIRE(ctx->nranks == 1 || ndim == 3, "multi-rank FFT is implemented for 3-D meshes (slab decomposition)");
+    pmb_fft *f = (pmb_fft *) calloc(1, sizeof(pmb_fft));
+    if (!f) return PMB_ENOMEM;
+    f->ctx = ctx;
+    f->ndim = ndim;
+    for (int d = 0; d < 3; d++) f->n[d] = 1;
+    for (int d = 0; d < ndim; d++) f->n[3 - ndim + d] = nmesh[d];
+    f->nc = f->n[2] / 2 + 1;
+    f->elsize = dtype_elsize;
+    f->P = ctx->nranks;
+    f->rank = ctx->rank;
+    PMB_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < FFT_NEV; i++) {
+        PMB_CUDA(cudaEventCreate(&f->ev[i][0]));
+        PMB_CUDA(cudaEventCreate(&f->ev[i][1]));
+    }
+    const bool dbl = dtype_elsize == 8;
+    if (f->P == 1) {
+        f->s0 = 0; f->m0 = f->n[0]; f->s1 = 0; f->m1 = f->n[1];
+        long long n[3], inr[3], inc[3];
+        int r = ndim;
+        for (int d = 0; d < ndim; d++) {
+            n[d] = f->n[3 - ndim + d];
+            inr[d] = n[d];
+            inc[d] = n[d];
+        }
+        inr[r - 1] = 2 * f->nc;
+        inc[r - 1] = f->nc;
+        long long rdist = 1, cdist = 1;
+        for (int d = 0; d < r; d++) { rdist *= inr[d]; cdist *= inc[d]; }
+        PMB_CHECK(make_plan(f, &f->full_r2c, r, n, inr, rdist, inc, cdist, dbl ? CUFFT_D2Z : CUFFT_R2C, 1));
+        PMB_CHECK(make_plan(f, &f->full_c2r, r, n, inc, cdist, inr, rdist, dbl ? CUFFT_Z2D : CUFFT_C2R, 1));
+        f->have_full = true;
+    } else {
+        block_partition(f->n[0], f->P, f->rank, &f->blk0, &f->s0, &f->m0);
+        block_partition(f->n[1], f->P, f->rank, &f->blk1, &f->s1, &f->m1);
+        if (f->m0 > 0) {
+            long long n2[2] = {f->n[1], f->n[2]};
+            long long inr[2] = {f->n[1], 2 * f->nc};
+            long long inc[2] = {f->n[1], f->nc};
+            PMB_CHECK(make_plan(f, &f->slab_r2c, 2, n2, inr, f->n[1] * 2 * f->nc, inc, f->n[1] * f->nc,
+                                dbl ? CUFFT_D2Z : CUFFT_R2C, f->m0));
+            PMB_CHECK(make_plan(f, &f->slab_c2r, 2, n2, inc, f->n[1] * f->nc, inr, f->n[1] * 2 * f->nc,
+                                dbl ? CUFFT_Z2D : CUFFT_C2R, f->m0));
+        }
+        if (f->m1 > 0) {
+            long long n1[1] = {f->n[0]};
+            long long emb[1] = {f->n[0]};
+            PMB_CHECK(make_plan(f, &f->line, 1, n1, emb, f->n[0], emb, f->n[0], dbl ? CUFFT_Z2Z : CUFFT_C2C, f->m1 * f->nc));
+        }
+        f->have_slab = true;
+        int64_t celems = f->m0 * f->n[1] * f->nc;
+        int64_t t = f->m1 * f->nc * f->n[0];
+        if (t > celems) celems = t;
+        f->work_bytes = (size_t) celems * 2 * dtype_elsize + 256;
+        PMB_CUDA(cudaMalloc(&f->work0, f->work_bytes));
+        PMB_CUDA(cudaMalloc(&f->work1, f->work_bytes));
+    }
+    *out = f;
+    return PMB_OK;
+}
+
+extern "C" int pmb_fft_destroy(pmb_fft *f)
+{
+    if (!f) return PMB_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    if (f->have_full) { cufftDestroy(f->full_r2c); cufftDestroy(f->full_c2r); }
+    if (f->have_slab) {
+        if (f->m0 > 0) { cufftDestroy(f->slab_r2c); cufftDestroy(f->slab_c2r); }
+        if (f->m1 > 0) cufftDestroy(f->line);
+    }
+    if (f->work0) cudaFree(f->work0);
+    if (f->work1) cudaFree(f->work1);
+    for (int i = 0; i < FFT_NEV; i++) { cudaEventDestroy(f->ev[i][0]); cudaEventDestroy(f->ev[i][1]); }
+    free(f);
+    return PMB_OK;
+}
+
+extern "C" int pmb_fft_layout(pmb_fft *f, int64_t *i_start, int64_t *i_shape, int64_t *i_strides,
+                              int64_t *o_start, int64_t *o_shape, int64_t *o_strides,
+                              int64_t *real_alloc_elems, int64_t *complex_alloc_elems)
+{
+    PMB_REQUIRE(f && i_start && i_shape && i_strides && o_start && o_shape && o_strides, "null argument");
+    const int nd = f->ndim, pad = 3 - nd;
+    int64_t is[3] = {f->s0, 0, 0}, ish[3] = {f->m0, f->n[1], f->n[2]};
+    int64_t ist[3] = {f->n[1] * 2 * f->nc, 2 * f->nc, 1};
+    int64_t os[3], osh[3], ost[3];
+    if (f->P == 1) {
+        os[0] = os[1] = os[2] = 0;
+        osh[0] = f->n[0]; osh[1] = f->n[1]; osh[2] = f->nc;
+        ost[0] = f->n[1] * f->nc; ost[1] = f->nc; ost[2] = 1;
+    } else {
+        os[0] = 0; os[1] = f->s1; os[2] = 0;
+        osh[0] = f->n[0]; osh[1] = f->m1; osh[2] = f->nc;
+        ost[0] = 1; ost[1] = f->nc * f->n[0]; ost[2] = f->n[0];
+    }
+    for (int d = 0; d < nd; d++) {
+        i_start[d] = is[pad + d]; i_shape[d] = ish[pad + d]; i_strides[d] = ist[pad + d];
+        o_start[d] = os[pad + d]; o_shape[d] = osh[pad + d]; o_strides[d] = ost[pad + d];
+    }
+    int64_t relems = f->m0 * f->n[1] * 2 * f->nc;
+    int64_t celems = f->P == 1 ? f->n[0] * f->n[1] * f->nc : f->m1 * f->nc * f->n[0];
+    // either buffer may serve as the in-place partner of the other
+    int64_t both = relems > 2 * celems ? relems : 2 * celems;
+    if (real_alloc_elems) *real_alloc_elems = both > 0 ? both : 2;
+    if (complex_alloc_elems) *complex_alloc_elems = both / 2 > 0 ? both / 2 : 1;
+    return PMB_OK;
+}
+
+// ---- cuFFT time accounting ------------------------------------------------------
+static int lib_flush(pmb_fft *f)
+{
+    if (f->nev == 0) return PMB_OK;
+    PMB_CUDA(cudaEventSynchronize(f->ev[f->nev - 1][1]));
+    for (int i = 0; i < f->nev; i++) {
+        float ms = 0;
+        PMB_CUDA(cudaEventElapsedTime(&ms, f->ev[i][0], f->ev[i][1]));
+        f->lib_ms += ms;
+    }
+    f->nev = 0;
+    return PMB_OK;
+}
+static int lib_begin(pmb_fft *f)
+{
+    if (f->nev == FFT_NEV) PMB_CHECK(lib_flush(f));
+    PMB_CUDA(cudaEventRecord(f->ev[f->nev][0], f->ctx->stream));
+    return PMB_OK;
+}
+static int lib_end(pmb_fft *f)
+{
+    PMB_CUDA(cudaEventRecord(f->ev[f->nev][1], f->ctx->stream));
+    f->nev++;
+    return PMB_OK;
+}
+extern "C" int pmb_fft_library_ms(pmb_fft *f, float *ms, int reset)
+{
+    PMB_REQUIRE(f && ms, "null argument");
+    PMB_CHECK(lib_flush(f));
+    *ms = f->lib_ms;
+    if (reset) f->lib_ms = 0;
+    return PMB_OK;
+}
+
+// ---- kernels ------------------------------------------------------------------
+template <typename C>   // C = float2 / double2
+__global__ void pmb_k_cscale(C *a, int64_t n, double s)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        C v = a[i];
+        v.x = (decltype(v.x)) (v.x * (decltype(v.x)) s);
+        v.y = (decltype(v.y)) (v.y * (decltype(v.y)) s);
+        a[i] = v;
+    }
+}
+
+// out (C rows, R cols) = transpose(in (R rows, C cols)) * s ; 32x32 tiles through shared memory so
+// that both the global reads and writes are coalesced 512-byte (double2) rows.
+template <typename C>
+__global__ void __launch_bounds__(256)
+pmb_k_transpose(const C *__restrict__ in, C *__restrict__ out, int64_t R, int64_t Cc, double s,
+                int64_t tiles_r, int64_t tiles_c)
+{
+    __shared__ C tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int64_t ntiles = tiles_r * tiles_c;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t tr = t / tiles_c, tc = t - tr * tiles_c;
+        const int64_t r0 = tr * 32, c0 = tc * 32;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < R && c < Cc) tile[ty + 8 * k][tx] = in[r * Cc + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t c = c0 + ty + 8 * k, r = r0 + tx;
+            if (r < R && c < Cc) {
+                C v = tile[tx][ty + 8 * k];
+                v.x = (decltype(v.x)) (v.x * (decltype(v.x)) s);
+                v.y = (decltype(v.y)) (v.y * (decltype(v.y)) s);
+                out[c * R + r] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// forward pack: A (m0, n1, nc) -> per-destination blocks (m0, m1_q, nc) at offset m0 * s1_q * nc.
+// backward unpack is the inverse copy (dir = 1).
+template <typename C>
+__global__ void pmb_k_slab_pack(const C *__restrict__ src, C *__restrict__ dst, int64_t m0, int64_t n1, int64_t nc,
+                                int64_t blk1, int dir)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t total = m0 * n1 * nc;
+    for (; t < total; t += stride) {
+        const int64_t k = t % nc;
+        const int64_t r = t / nc;
+        const int64_t j = r % n1;
+        const int64_t i = r / n1;
+        const int64_t q = j / blk1;
+        const int64_t s1q = q * blk1;
+        int64_t m1q = n1 - s1q;
+        if (m1q > blk1) m1q = blk1;
+        const int64_t packed = m0 * s1q * nc + (i * m1q + (j - s1q)) * nc + k;
+        if (dir == 0) dst[packed] = src[t]; else dst[t] = src[packed];
+    }
+}
+
+template <typename C>
+static int transpose(pmb_fft *f, const void *in, void *out, int64_t R, int64_t Cc, double s)
+{
+    if (R == 0 || Cc == 0) return PMB_OK;
+    const int64_t tr = (R + 31) / 32, tc = (Cc + 31) / 32;
+    int64_t grid = tr * tc;
+    const int64_t cap = (int64_t) f->ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    pmb_k_transpose<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, (C *) out, R, Cc, s, tr, tc);
+    PMB_LAUNCH_CHECK(f->ctx);
+    return PMB_OK;
+}
+
+template <typename C>
+static int slab_pack(pmb_fft *f, const void *src, void *dst, int dir)
+{
+    const int64_t total = f->m0 * f->n[1] * f->nc;
+    if (total == 0) return PMB_OK;
+    pmb_k_slab_pack<C><<<pmb_grid(f->ctx, total, 256, 8), 256, 0, f->ctx->stream>>>(
+        (const C *) src, (C *) dst, f->m0, f->n[1], f->nc, f->blk1, dir);
+    PMB_LAUNCH_CHECK(f->ctx);
+    return PMB_OK;
+}
+
+// counts / offsets (in complex elements) of the global transpose.
+// fwd: send to q the block (m0, m1_q, nc); receive from p the block (m0_p, m1, nc).
+static void slab_counts(const pmb_fft *f, int fwd, int64_t *sc, int64_t *so, int64_t *rc, int64_t *ro)
+{
+    for (int q = 0; q < f->P; q++) {
+        int64_t b, s0q, m0q, s1q, m1q;
+        block_partition(f->n[0], f->P, q, &b, &s0q, &m0q);
+        block_partition(f->n[1], f->P, q, &b, &s1q, &m1q);
+        const int64_t a_cnt = f->m0 * m1q * f->nc, a_off = f->m0 * s1q * f->nc;   // (m0, m1_q, nc) blocks
+        const int64_t b_cnt = m0q * f->m1 * f->nc, b_off = s0q * f->m1 * f->nc;   // (m0_q, m1, nc) blocks
+        if (fwd) { sc[q] = a_cnt; so[q] = a_off; rc[q] = b_cnt; ro[q] = b_off; }
+        else { sc[q] = b_cnt; so[q] = b_off; rc[q] = a_cnt; ro[q] = a_off; }
+    }
+}
+
+static int exec_r2c(pmb_fft *f, cufftHandle h, const void *in, void *out)
+{
+    PMB_CHECK(lib_begin(f));
+    if (f->elsize == 8) PMB_CUFFT(cufftExecD2Z(h, (cufftDoubleReal *) in, (cufftDoubleComplex *) out));
+    else PMB_CUFFT(cufftExecR2C(h, (cufftReal *) in, (cufftComplex *) out));
+    PMB_CHECK(lib_end(f));
+    return PMB_OK;
+}
+static int exec_c2r(pmb_fft *f, cufftHandle h, void *in, void *out)
+{
+    PMB_CHECK(lib_begin(f));
+    if (f->elsize == 8) PMB_CUFFT(cufftExecZ2D(h, (cufftDoubleComplex *) in, (cufftDoubleReal *) out));
+    else PMB_CUFFT(cufftExecC2R(h, (cufftComplex *) in, (cufftReal *) out));
+    PMB_CHECK(lib_end(f));
+    return PMB_OK;
+}
+static int exec_c2c(pmb_fft *f, cufftHandle h, void *in, void *out, int dir)
+{
+    PMB_CHECK(lib_begin(f));
+    if (f->elsize == 8) PMB_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *) in, (cufftDoubleComplex *) out, dir));
+    else PMB_CUFFT(cufftExecC2C(h, (cufftComplex *) in, (cufftComplex *) out, dir));
+    PMB_CHECK(lib_end(f));
+    return PMB_OK;
+}
+
+extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scale)
+{
+    PMB_REQUIRE(f && real && cplx, "null argument");
+    pmb_ctx *ctx = f->ctx;
+    const size_t csz = 2 * (size_t) f->elsize;
+    if (f->P == 1) {
+        PMB_CHECK(exec_r2c(f, f->full_r2c, real, cplx));
+        if (scale != 1.0) {
+            const int64_t n = f->n[0] * f->n[1] * f->nc;
+            if (f->elsize == 8) pmb_k_cscale<double2><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>((double2 *) cplx, n, scale);
+            else pmb_k_cscale<float2><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>((float2 *) cplx, n, scale);
+            PMB_LAUNCH_CHECK(ctx);
+        }
+        return PMB_OK;
+    }
+    // 1. local planes: 2-D r2c over (n1, n2):  real (m0, n1, 2nc) -> work0 (m0, n1, nc)
+    if (f->m0 > 0) PMB_CHECK(exec_r2c(f, f->slab_r2c, real, f->work0));
+    // 2. pack per destination
+    if (f->elsize == 8) PMB_CHECK(slab_pack<double2>(f, f->work0, f->work1, 0));
+    else PMB_CHECK(slab_pack<float2>(f, f->work0, f->work1, 0));
+    // 3. global transpose
+    int64_t sc[64], so[64], rc[64], ro[64];
+    PMB_REQUIRE(f->P <= 64, "at most 64 ranks");
+    slab_counts(f, 1, sc, so, rc, ro);
+    PMB_CHECK(pmb_alltoallv(ctx, f->work1, sc, so, f->work0, rc, ro, (int64_t) csz));
+    // 4. work0 is now (n0, m1*nc): transpose to (m1*nc, n0) with the normalisation folded in
+    if (f->elsize == 8) PMB_CHECK(transpose<double2>(f, f->work0, cplx, f->n[0], f->m1 * f->nc, scale));
+    else PMB_CHECK(transpose<float2>(f, f->work0, cplx, f->n[0], f->m1 * f->nc, scale));
+    // 5. lines along axis 0
+    if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, cplx, cplx, CUFFT_FORWARD));
+    return PMB_OK;
+}
+
+static int c2r_from_work(pmb_fft *f, void *real);
+
+extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
+{
+    PMB_REQUIRE(f && real && cplx, "null argument");
+    pmb_ctx *ctx = f->ctx;
+    const size_t csz = 2 * (size_t) f->elsize;
+    if (f->P == 1) {
+        // cuFFT's multi-dimensional C2R may overwrite its input: go through the output buffer
+        if (cplx != real)
+            PMB_CUDA(cudaMemcpyAsync(real, cplx, (size_t) (f->n[0] * f->n[1] * f->nc) * csz, cudaMemcpyDeviceToDevice, ctx->stream));
+        PMB_CHECK(exec_c2r(f, f->full_c2r, real, real));
+        return PMB_OK;
+    }
+    // 1. inverse lines along axis 0: cplx (m1*nc, n0) -> work0 (input preserved)
+    if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx, f->work0, CUFFT_INVERSE));
+    return c2r_from_work(f, real);
+}
+
+// steps 2-5 of the backward transform; work0 holds the axis-0 inverse-transformed lines (m1*nc, n0)
+static int c2r_from_work(pmb_fft *f, void *real)
+{
+    pmb_ctx *ctx = f->ctx;
+    const size_t csz = 2 * (size_t) f->elsize;
+    // 2. (m1*nc, n0) -> (n0, m1*nc): rows of destination p are contiguous
+    if (f->elsize == 8) PMB_CHECK(transpose<double2>(f, f->work0, f->work1, f->m1 * f->nc, f->n[0], 1.0));
+    else PMB_CHECK(transpose<float2>(f, f->work0, f->work1, f->m1 * f->nc, f->n[0], 1.0));
+    // 3. global transpose back
+    int64_t sc[64], so[64], rc[64], ro[64];
+    slab_counts(f, 0, sc, so, rc, ro);
+    PMB_CHECK(pmb_alltoallv(ctx, f->work1, sc, so, f->work0, rc, ro, (int64_t) csz));
+    // 4. unpack blocks (m0, m1_q, nc) into the in-place complex view (m0, n1, nc) of the real buffer
+    if (f->elsize == 8) PMB_CHECK(slab_pack<double2>(f, f->work0, real, 1));
+    else PMB_CHECK(slab_pack<float2>(f, f->work0, real, 1));
+    // 5. planes: 2-D c2r in place
+    if (f->m0 > 0) PMB_CHECK(exec_c2r(f, f->slab_c2r, real, real));
+    return PMB_OK;
+}
+
+// ---- transfer functions -----------------------------------------------------------
+struct TfArgs {
+    int kind, dir, ndim, P;
+    int64_t n[3], nc, s1, m1;
+    double box[3];
+    double p0, p1;
+    int win_p;          // sinc power of the compensated window (0: none)
+    double win_vfactor;
+};
+
+// wavenumber of global index i on an axis of n points, box length L (ref: pm.py:1213-1219):
+// Nyquist and above map to negative frequencies.
+__device__ __forceinline__ double pmb_wavenumber(int64_t i, int64_t n, double L)
+{
+    double w = (double) (i >= n / 2 ? i - n : i);
+    w = w * (2 * 3.141592653589793 / (double) n);
+    return w * (double) n / L;
+}
+
+__device__ __forceinline__ double pmb_sinc_unnormed(double x)
+{
+    if (x < 1e-5 && x > -1e-5) {
+        double x2 = x * x;
+        return 1.0 - x2 / 6. + x2 * x2 / 120.;
+    }
+    return sin(x) / x;
+}
+
+template <typename C>
+__global__ void pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t total, TfArgs a)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        int64_t idx[3];
+        if (a.P == 1) {
+            idx[2] = t % a.nc;
+            int64_t r = t / a.nc;
+            idx[1] = r % a.n[1];
+            idx[0] = r / a.n[1];
+        } else {
+            idx[0] = t % a.n[0];
+            int64_t r = t / a.n[0];
+            idx[2] = r % a.nc;
+            idx[1] = a.s1 + r / a.nc;
+        }
+        const int pad = 3 - a.ndim;
+        double k[3] = {0, 0, 0};
+        double k2 = 0;
+        for (int d = pad; d < 3; d++) {
+            k[d] = pmb_wavenumber(idx[d], a.n[d], a.box[d]);
+            k2 = k2 + k[d] * k[d];
+        }
+        const int dd = a.dir + pad;
+        double re = 1.0, im = 0.0;   // multiplier
+        switch (a.kind) {
+        case PMB_TF_SCALE: re = a.p0; break;
+        case PMB_TF_GRAVITY_FD4: {
+            if (k2 == 0) k2 = 1.0;
+            const double Cc = a.box[dd] / (double) a.n[dd];
+            const double w = k[dd] * Cc;
+            const double kfinite = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
+            re = 0; im = kfinite / k2;
+        } break;
+        case PMB_TF_GRADIENT_K:
+            if (k2 == 0) k2 = 1.0;
+            re = 0; im = k[dd] / k2;
+            break;
+        case PMB_TF_INV_LAPLACE:
+            if (k2 == 0) k2 = 1.0;
+            re = -1. / k2;
+            break;
+        case PMB_TF_GAUSS_LOWPASS:
+            re = exp(-0.5 * k2 * (a.p0 * a.p0));
+            break;
+        case PMB_TF_COMPENSATE: {
+            double tf = 1.0;
+            for (int d = pad; d < 3; d++) {
+                const double w = k[d] * a.box[d] / (double) a.n[d];
+                double s = 1.0;
+                if (a.win_p) {
+                    const double b = pmb_sinc_unnormed(0.5 * (w / a.win_vfactor));
+                    s = b;
+                    for (int j = 1; j < a.win_p; j++) s = s * b;
+                }
+                tf = tf * s;
+            }
+            re = 1.0 / tf;
+        } break;
+        case PMB_TF_IK:
+            re = 0; im = k[dd];
+            break;
+        }
+        const C v = in[t];
+        C o;
+        o.x = (decltype(o.x)) ((double) v.x * re - (double) v.y * im);
+        o.y = (decltype(o.y)) ((double) v.x * im + (double) v.y * re);
+        out[t] = o;
+    }
+}
+
+extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_h, const double *boxsize_h,
+                            const void *in, void *out)
+{
+    PMB_REQUIRE(f && boxsize_h && in && out, "null argument");
+    PMB_REQUIRE(kind >= PMB_TF_SCALE && kind <= PMB_TF_IK, "unknown transfer kind %d", kind);
+    PMB_REQUIRE(dir >= 0 && dir < f->ndim, "bad direction %d", dir);
+    TfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kind = kind; a.dir = dir; a.ndim = f->ndim; a.P = f->P;
+    for (int d = 0; d < 3; d++) { a.n[d] = f->n[d]; a.box[d] = 1.0; }
+    for (int d = 0; d < f->ndim; d++) a.box[3 - f->ndim + d] = boxsize_h[d];
+    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1;
+    a.p0 = params_h ? params_h[0] : 0.0;
+    a.p1 = params_h ? params_h[1] : 0.0;
+    if (kind == PMB_TF_COMPENSATE) {
+        PMB_REQUIRE(params_h, "compensation needs params = {kind, support}");
+        PmbWindow w;
+        PMB_CHECK(pmb_resolve_window(NULL, (int) params_h[0], (int) params_h[1], 0, NULL, &w, 0));
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, (double) (int) params_h[1], &info);
+        a.win_vfactor = info.vfactor;
+        a.win_p = w.family == PMB_FAM_NEAREST ? 1 : w.family == PMB_FAM_LINEAR ? 2
+                  : w.family == PMB_FAM_QUADRATIC ? 3 : w.family == PMB_FAM_CUBIC ? 4 : 0;
+    }
+    const int64_t total = f->P == 1 ? f->n[0] * f->n[1] * f->nc : f->m1 * f->nc * f->n[0];
+    if (total == 0) return PMB_OK;
+    pmb_ctx *ctx = f->ctx;
+    if (f->elsize == 8)
+        pmb_k_transfer<double2><<<pmb_grid(ctx, total, 256, 8), 256, 0, ctx->stream>>>((const double2 *) in, (double2 *) out, total, a);
+    else
+        pmb_k_transfer<float2><<<pmb_grid(ctx, total, 256, 8), 256, 0, ctx->stream>>>((const float2 *) in, (float2 *) out, total, a);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}

@@ -1,0 +1,104 @@
+// pmb_internal.h -- context, error plumbing and small device helpers shared by the
+// translation units of libpmesh_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pmesh_b200.h"
+#include "pmb_window.h"
+
+struct ncclComm;
+
+#define PMB_NTIMERS 16
+
+struct pmb_table {
+    double *d_values;
+    int n;
+    double step, nativesupport, hsupport;
+};
+
+struct pmb_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    cudaEvent_t t0[PMB_NTIMERS], t1[PMB_NTIMERS];
+    int64_t launches;
+    // growable scratch (deterministic paint, routing, pack buffers)
+    void *scratch;
+    size_t scratch_bytes;
+    void *flush_buf;
+    size_t flush_bytes;
+    pmb_table tables[PMB_NKINDS];
+    // communicator
+    ncclComm *comm;
+    int rank, nranks;
+    // routing state kept between pmb_decompose_count and pmb_decompose_fill
+    void *route_masks;       // uint64 per particle
+    size_t route_masks_bytes;
+    void *route_blockhist;   // int32 [nblocks][nranks]
+    size_t route_blockhist_bytes;
+    int64_t route_npart;
+    int route_nblocks;
+    int64_t route_per_block;
+    size_t det_chunk_bytes;  // workspace budget of the deterministic paint
+};
+
+void pmb_set_error(const char *fmt, ...);
+int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out);
+int pmb_resolve_window(pmb_ctx *ctx, int kind, int support_req, int ndim, const int *order,
+                       PmbWindow *w, int for_device);
+
+#define PMB_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return pmb_cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PMB_CHECK(call)                     \
+    do {                                    \
+        int _r = (call);                    \
+        if (_r != PMB_OK) return _r;        \
+    } while (0)
+
+#define PMB_LAUNCH_CHECK(ctx)                                                 \
+    do {                                                                      \
+        (ctx)->launches++;                                                    \
+        cudaError_t _e = cudaGetLastError();                                  \
+        if (_e != cudaSuccess) return pmb_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define PMB_REQUIRE(cond, ...)              \
+    do {                                    \
+        if (!(cond)) {                      \
+            pmb_set_error(__VA_ARGS__);     \
+            return PMB_EINVAL;              \
+        }                                   \
+    } while (0)
+
+// grid size for a grid-stride kernel: a whole number of waves of resident CTAs over the SMs
+static inline int pmb_grid(const pmb_ctx *ctx, int64_t work_items, int block, int ctas_per_sm)
+{
+    int64_t need = (work_items + block - 1) / block;
+    int64_t cap = (int64_t) ctx->sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < cap ? need : cap);
+}
+
+#ifdef __CUDACC__
+// strided scalar loads of f4/f8 columns promoted to double (ref: fused postype/masstype/hsmltype,
+// pmesh/_window.pyx:6-16,157-165)
+__device__ __forceinline__ double pmb_ld_real(const void *base, int64_t byteoff, int elsize)
+{
+    const char *p = (const char *) base + byteoff;
+    return elsize == 8 ? *(const double *) p : (double) *(const float *) p;
+}
+__device__ __forceinline__ void pmb_st_real(void *base, int64_t byteoff, int elsize, double v)
+{
+    char *p = (char *) base + byteoff;
+    if (elsize == 8) *(double *) p = v; else *(float *) p = (float) v;
+}
+#endif

@@ -1,0 +1,577 @@
+// pmb_resample.cu -- paint (scatter-add) and readout (gather) kernels.
+//
+// Replaces the per-particle Cython/C loops of the reference
+// (pmesh/_window.pyx:157-165,198-205 -> pmesh/_window_imp.c:461-471 -> _window_generics.h /
+// _window_tuned_*.h).  Three paint paths:
+//   * atomic   : one thread per particle, red.global.add.{f64,f32} per stencil point.
+//   * deterministic : expand (cell, value) pairs in particle order -> stable radix sort by cell ->
+//                 sequential per-cell sum `acc = (T)((double)acc + f)`; bit-equal to the reference,
+//                 which visits particles in index order (proved in SURVEY section 7).
+// Readout is a gather of the same stencil, summed in the reference's point order.
+#include <cub/cub.cuh>
+#include <stdlib.h>
+
+#include "pmb_stencil.cuh"
+
+// ------------------------------------------------------------------ atomic paint
+template <typename MeshT>
+__device__ __forceinline__ void pmb_red_add(char *mesh, int64_t off, double f)
+{
+    atomicAdd((MeshT *) (mesh + off), (MeshT) f);
+}
+
+template <typename MeshT, int NDIM, int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_paint_tuned(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double m = pmb_load_mass(p, i);
+        PmbAxes<NDIM, FAM> A;
+        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+        pmb_for_points_fixed<NDIM, FAM>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+            if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(true, m, v0, v1, v2));
+        });
+    }
+}
+
+template <typename MeshT, int NDIM>
+__global__ void __launch_bounds__(128)
+pmb_k_paint_dyn(PmbGeom g, PmbWindow w, PmbParticles p, char *mesh, int64_t npart, int pcsfix)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double m = pmb_load_mass(p, i);
+        const double h = pmb_load_hsml(p, i);
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, w.support * h, &info);
+        if (info.support <= PMB_MAX_SUPPORT) {
+            PmbAxes<NDIM, PMB_MAX_SUPPORT> A;
+            pmb_axes_dyn<NDIM>(g, w, info, g.order, x, pcsfix, A);
+            const bool tuned = A.tuned;
+            pmb_for_points_dyn<NDIM, PMB_MAX_SUPPORT>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(tuned, m, v0, v1, v2));
+            });
+        } else {
+            pmb_for_points_wide<NDIM>(g, w, info, g.order, x, [&](int, int64_t off, double v0, double v1, double v2) {
+                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(false, m, v0, v1, v2));
+            });
+        }
+    }
+}
+
+// ------------------------------------------------------------------ readout
+template <typename MeshT>
+__device__ __forceinline__ double pmb_mesh_ld(const char *mesh, int64_t off)
+{
+    return (double) __ldg((const MeshT *) (mesh + off));
+}
+
+template <typename MeshT, int NDIM, int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_readout_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
+                    void *out, int out_elsize, int64_t out_stride)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        PmbAxes<NDIM, FAM> A;
+        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+        double value = 0;
+        pmb_for_points_fixed<NDIM, FAM>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+            if (off != PMB_OFF_INVALID) value += pmb_mesh_ld<MeshT>(mesh, off) * ((v0 * v1) * v2);
+        });
+        pmb_st_real(out, i * out_stride, out_elsize, value);
+    }
+}
+
+template <typename MeshT, int NDIM>
+__global__ void __launch_bounds__(128)
+pmb_k_readout_dyn(PmbGeom g, PmbWindow w, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
+                  void *out, int out_elsize, int64_t out_stride)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double h = pmb_load_hsml(p, i);
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, w.support * h, &info);
+        double value = 0;
+        auto acc = [&](int, int64_t off, double v0, double v1, double v2) {
+            if (off != PMB_OFF_INVALID) value += ((v0 * v1) * v2) * pmb_mesh_ld<MeshT>(mesh, off);
+        };
+        if (info.support <= PMB_MAX_SUPPORT) {
+            PmbAxes<NDIM, PMB_MAX_SUPPORT> A;
+            pmb_axes_dyn<NDIM>(g, w, info, g.order, x, pcsfix, A);
+            pmb_for_points_dyn<NDIM, PMB_MAX_SUPPORT>(A, acc);
+        } else {
+            pmb_for_points_wide<NDIM>(g, w, info, g.order, x, acc);
+        }
+        pmb_st_real(out, i * out_stride, out_elsize, value);
+    }
+}
+
+// fused value + NDIM gradients: one sweep over the neighbourhood, four accumulators.  Each
+// accumulator sees the same addends in the same order as a separate readout(gradient=d) would.
+template <typename MeshT, int NDIM, int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
+                         void *out, int out_elsize, int64_t out_stride,
+                         void *grad, int64_t gs0, int64_t gs1)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int zero[3] = {0, 0, 0};
+    const int one[3] = {1, 1, 1};
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        PmbAxes<NDIM, FAM> A, D;
+        pmb_axes_tuned<NDIM, FAM>(g, zero, x, pcsfix, A);
+        pmb_axes_tuned<NDIM, FAM>(g, one, x, pcsfix, D);
+        double value = 0, gr[3] = {0, 0, 0};
+        // walk the stencil by ordinal to address both weight sets
+        int ord = 0;
+#pragma unroll
+        for (int a = 0; a < FAM; a++) {
+#pragma unroll
+            for (int b = 0; b < (NDIM > 1 ? FAM : 1); b++) {
+#pragma unroll
+                for (int c = 0; c < (NDIM > 2 ? FAM : 1); c++, ord++) {
+                    int64_t o0 = A.off[0][a];
+                    int64_t o1 = NDIM > 1 ? A.off[NDIM > 1 ? 1 : 0][b] : 0;
+                    int64_t o2 = NDIM > 2 ? A.off[NDIM > 2 ? 2 : 0][c] : 0;
+                    if (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID || o2 == PMB_OFF_INVALID) continue;
+                    const double mval = pmb_mesh_ld<MeshT>(mesh, o0 + o1 + o2);
+                    const double v0 = A.V[0][a], d0 = D.V[0][a];
+                    const double v1 = NDIM > 1 ? A.V[NDIM > 1 ? 1 : 0][b] : 1.0;
+                    const double d1 = NDIM > 1 ? D.V[NDIM > 1 ? 1 : 0][b] : 1.0;
+                    const double v2 = NDIM > 2 ? A.V[NDIM > 2 ? 2 : 0][c] : 1.0;
+                    const double d2 = NDIM > 2 ? D.V[NDIM > 2 ? 2 : 0][c] : 1.0;
+                    value += mval * ((v0 * v1) * v2);
+                    gr[0] += mval * ((d0 * v1) * v2);
+                    if (NDIM > 1) gr[1] += mval * ((v0 * d1) * v2);
+                    if (NDIM > 2) gr[2] += mval * ((v0 * v1) * d2);
+                }
+            }
+        }
+        if (out) pmb_st_real(out, i * out_stride, out_elsize, value);
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) pmb_st_real(grad, i * gs0 + d * gs1, out_elsize, gr[d]);
+    }
+}
+
+// ------------------------------------------------------------------ deterministic paint
+// per-axis dense indices variant of the stencil walk for the deterministic path: we need the
+// C-order cell number (sort key), not the byte offset.  To share all arithmetic with the atomic
+// path the geometry handed to these kernels has strides replaced by the dense C-order strides in
+// ELEMENTS (g.strides[d] = prod(size[d+1:])), so `off` IS the linear cell index.
+template <typename KeyT, int NDIM, int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_expand_tuned(PmbGeom g, PmbParticles p, int64_t first, int64_t count, int pcsfix,
+                   KeyT *keys, double *vals)
+{
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    int npts = 1;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) npts *= FAM;
+    for (; j < count; j += stride) {
+        const int64_t i = first + j;
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double m = pmb_load_mass(p, i);
+        PmbAxes<NDIM, FAM> A;
+        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+        KeyT *kk = keys + j * npts;
+        double *vv = vals + j * npts;
+        pmb_for_points_fixed<NDIM, FAM>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+            kk[ord] = off == PMB_OFF_INVALID ? (KeyT) ~(KeyT) 0 : (KeyT) off;
+            vv[ord] = pmb_paint_value(true, m, v0, v1, v2);
+        });
+    }
+}
+
+template <typename KeyT, int NDIM>
+__global__ void __launch_bounds__(128)
+pmb_k_expand_dyn(PmbGeom g, PmbWindow w, PmbParticles p, int64_t first, int64_t count, int pcsfix,
+                 int64_t npts_max, KeyT *keys, double *vals)
+{
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < count; j += stride) {
+        const int64_t i = first + j;
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double m = pmb_load_mass(p, i);
+        const double h = pmb_load_hsml(p, i);
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, w.support * h, &info);
+        KeyT *kk = keys + j * npts_max;
+        double *vv = vals + j * npts_max;
+        // slots beyond this particle's own point count keep the sentinel written by the memset
+        if (info.support <= PMB_MAX_SUPPORT) {
+            PmbAxes<NDIM, PMB_MAX_SUPPORT> A;
+            pmb_axes_dyn<NDIM>(g, w, info, g.order, x, pcsfix, A);
+            const bool tuned = A.tuned;
+            pmb_for_points_dyn<NDIM, PMB_MAX_SUPPORT>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+                kk[ord] = off == PMB_OFF_INVALID ? (KeyT) ~(KeyT) 0 : (KeyT) off;
+                vv[ord] = pmb_paint_value(tuned, m, v0, v1, v2);
+            });
+        } else {
+            pmb_for_points_wide<NDIM>(g, w, info, g.order, x, [&](int ord, int64_t off, double v0, double v1, double v2) {
+                kk[ord] = off == PMB_OFF_INVALID ? (KeyT) ~(KeyT) 0 : (KeyT) off;
+                vv[ord] = pmb_paint_value(false, m, v0, v1, v2);
+            });
+        }
+    }
+}
+
+// one thread per sorted pair; the thread sitting on the first pair of a cell walks the cell's run
+// and performs the reference's `*(FLOAT*)p += f` sequence (_window_generics.h:155).
+template <typename KeyT, typename MeshT>
+__global__ void __launch_bounds__(256)
+pmb_k_segment_sum(const KeyT *keys, const double *vals, int64_t n, char *mesh,
+                  int64_t sz1, int64_t sz2, int64_t st0, int64_t st1, int64_t st2)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const KeyT sentinel = (KeyT) ~(KeyT) 0;
+    for (; i < n; i += stride) {
+        const KeyT k = keys[i];
+        if (k == sentinel) continue;
+        if (i > 0 && keys[i - 1] == k) continue;
+        int64_t lin = (int64_t) k;
+        int64_t c = lin % sz2;
+        int64_t r = lin / sz2;
+        int64_t b = r % sz1;
+        int64_t a = r / sz1;
+        MeshT *cell = (MeshT *) (mesh + a * st0 + b * st1 + c * st2);
+        MeshT acc = *cell;
+        for (int64_t j = i; j < n && keys[j] == k; j++) acc = (MeshT) ((double) acc + vals[j]);
+        *cell = acc;
+    }
+}
+
+template <typename T>
+__global__ void pmb_k_max_real(const void *a, int elsize, int64_t stride_bytes, int64_t n, double *out)
+{
+    __shared__ double sh[32];
+    double acc = -1e300;
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) acc = fmax(acc, pmb_ld_real(a, i * stride_bytes, elsize));
+    for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < (blockDim.x >> 5) ? sh[lane] : -1e300;
+        for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (lane == 0) out[blockIdx.x] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static int check_args(pmb_ctx *ctx, const pmb_resample_args *a, int need_out)
+{
+    PMB_REQUIRE(ctx && a, "null argument");
+    PMB_REQUIRE(a->ndim >= 1 && a->ndim <= 3, "ndim %d not supported (1..3)", a->ndim);
+    PMB_REQUIRE(a->mesh_elsize == 4 || a->mesh_elsize == 8, "canvas must be float32 or float64");
+    PMB_REQUIRE(a->pos_elsize == 4 || a->pos_elsize == 8, "pos must be float32 or float64");
+    PMB_REQUIRE(a->npart >= 0, "negative particle count");
+    PMB_REQUIRE(a->npart == 0 || (a->pos && a->mesh), "null pos / mesh");
+    if (a->mass) PMB_REQUIRE(a->mass_elsize == 4 || a->mass_elsize == 8, "mass must be float32 or float64");
+    if (a->hsml) PMB_REQUIRE(a->hsml_elsize == 4 || a->hsml_elsize == 8, "hsml must be float32 or float64");
+    if (need_out) {
+        PMB_REQUIRE(a->npart == 0 || a->out, "null out");
+        PMB_REQUIRE(a->out_elsize == 4 || a->out_elsize == 8, "out must be float32 or float64");
+    }
+    for (int d = 0; d < a->ndim; d++) {
+        PMB_REQUIRE(a->size[d] >= 0, "negative canvas size");
+        PMB_REQUIRE(a->order[d] >= 0, "negative order");
+    }
+    return PMB_OK;
+}
+
+static void fill_geom(const pmb_resample_args *a, PmbGeom *g)
+{
+    memset(g, 0, sizeof(*g));
+    g->ndim = a->ndim;
+    for (int d = 0; d < a->ndim; d++) {
+        g->order[d] = a->order[d];
+        g->scale[d] = a->scale[d];
+        g->translate[d] = a->translate[d];
+        g->period[d] = a->period[d];
+        g->size[d] = a->size[d];
+        g->strides[d] = a->strides[d];
+    }
+}
+
+static void fill_particles(const pmb_resample_args *a, PmbParticles *p)
+{
+    p->pos = a->pos; p->pos_elsize = a->pos_elsize; p->ps0 = a->pos_stride0; p->ps1 = a->pos_stride1;
+    p->mass = a->mass; p->mass_elsize = a->mass_elsize; p->ms = a->mass_stride; p->mass_scalar = a->mass_scalar;
+    p->hsml = a->hsml; p->hsml_elsize = a->hsml_elsize; p->hs = a->hsml_stride; p->hsml_scalar = a->hsml_scalar;
+}
+
+// the compile-time tuned kernels apply when no per-particle hsml is given and the (scalar-hsml
+// scaled) support equals the native support of a tuned kind
+static int fixed_family(const PmbWindow &w, const pmb_resample_args *a)
+{
+    if (!w.tuned || a->hsml) return 0;
+    PmbWinInfo info;
+    pmb_window_info(w.nativesupport, w.support * a->hsml_scalar, &info);
+    return info.support == w.tuned ? w.tuned : 0;
+}
+
+#define PMB_DISPATCH_FAM(FAMV, NDIMV, CALL)                 \
+    switch (FAMV) {                                         \
+    case 1: { constexpr int FAM = 1; CALL; } break;         \
+    case 2: { constexpr int FAM = 2; CALL; } break;         \
+    case 3: { constexpr int FAM = 3; CALL; } break;         \
+    default: { constexpr int FAM = 4; CALL; } break;        \
+    }
+
+#define PMB_DISPATCH_NDIM(NDIMV, CALL)                      \
+    switch (NDIMV) {                                        \
+    case 1: { constexpr int NDIM = 1; CALL; } break;        \
+    case 2: { constexpr int NDIM = 2; CALL; } break;        \
+    default: { constexpr int NDIM = 3; CALL; } break;       \
+    }
+
+template <typename MeshT>
+static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
+                        const PmbParticles &p)
+{
+    const int fam = fixed_family(w, a);
+    char *mesh = (char *) a->mesh;
+    if (fam) {
+        int grid = pmb_grid(ctx, a->npart, 256, 8);
+        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_paint_tuned<MeshT, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix))));
+    } else {
+        int grid = pmb_grid(ctx, a->npart, 128, 8);
+        PMB_DISPATCH_NDIM(a->ndim,
+            (pmb_k_paint_dyn<MeshT, NDIM><<<grid, 128, 0, ctx->stream>>>(g, w, p, mesh, a->npart, a->pcs_gradient_scale_fix)));
+    }
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+template <typename KeyT, typename MeshT>
+static int paint_deterministic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g_in, const PmbWindow &w,
+                               const PmbParticles &p)
+{
+    // dense C-order element strides so the stencil walk yields linear cell numbers
+    PmbGeom g = g_in;
+    int64_t acc = 1;
+    for (int d = a->ndim - 1; d >= 0; d--) { g.strides[d] = acc; acc *= g.size[d]; }
+    int64_t ncell = acc;
+    if (ncell == 0) return PMB_OK;
+    const int fam = fixed_family(w, a);
+
+    // widest per-particle stencil
+    int64_t smax;
+    if (fam) smax = fam;
+    else {
+        double hmax = a->hsml_scalar;
+        if (a->hsml) {
+            int grid = pmb_grid(ctx, a->npart, 256, 4);
+            void *part;
+            PMB_CHECK(pmb_scratch(ctx, sizeof(double) * grid, &part));
+            pmb_k_max_real<double><<<grid, 256, 0, ctx->stream>>>(a->hsml, a->hsml_elsize, a->hsml_stride, a->npart, (double *) part);
+            PMB_LAUNCH_CHECK(ctx);
+            double *h = (double *) malloc(sizeof(double) * grid);
+            if (!h) return PMB_ENOMEM;
+            cudaError_t e = cudaMemcpyAsync(h, part, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { free(h); return pmb_cuda_fail(e, "hsml max", __FILE__, __LINE__); }
+            hmax = h[0];
+            for (int i = 1; i < grid; i++) hmax = hmax > h[i] ? hmax : h[i];
+            free(h);
+        }
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, w.support * hmax, &info);
+        smax = info.support;
+    }
+    int64_t npts = 1;
+    for (int d = 0; d < a->ndim; d++) npts *= smax;
+
+    // bits of the sort key actually used (sentinel = all ones sorts last as long as end_bit covers it)
+    int key_bits = (int) sizeof(KeyT) * 8;
+
+    // chunk size from the workspace budget: 2x keys + 2x values + cub temp
+    const size_t per_pair = 2 * sizeof(KeyT) + 2 * sizeof(double);
+    int64_t chunk = (int64_t) (ctx->det_chunk_bytes / (per_pair * (size_t) npts));
+    if (chunk < 1) chunk = 1;
+    if (chunk > a->npart) chunk = a->npart;
+    const int64_t max_pairs = (int64_t) 1 << 30;   // keep cub item counts well inside int32
+    if (chunk * npts > max_pairs) chunk = max_pairs / npts > 0 ? max_pairs / npts : 1;
+    const int64_t pairs = chunk * npts;
+    PMB_REQUIRE(pairs < ((int64_t) 1 << 31), "stencil of %lld points is too wide for the deterministic path", (long long) npts);
+
+    size_t temp_bytes = 0;
+    {
+        cub::DoubleBuffer<KeyT> kb((KeyT *) NULL, (KeyT *) NULL);
+        cub::DoubleBuffer<double> vb((double *) NULL, (double *) NULL);
+        PMB_CUDA(cub::DeviceRadixSort::SortPairs(NULL, temp_bytes, kb, vb, (int) pairs, 0, key_bits, ctx->stream));
+    }
+    size_t off_k0 = 0;
+    size_t off_k1 = off_k0 + ((sizeof(KeyT) * pairs + 255) & ~(size_t) 255);
+    size_t off_v0 = off_k1 + ((sizeof(KeyT) * pairs + 255) & ~(size_t) 255);
+    size_t off_v1 = off_v0 + ((sizeof(double) * pairs + 255) & ~(size_t) 255);
+    size_t off_t = off_v1 + ((sizeof(double) * pairs + 255) & ~(size_t) 255);
+    void *ws;
+    PMB_CHECK(pmb_scratch(ctx, off_t + temp_bytes + 256, &ws));
+    char *wsb = (char *) ws;
+    KeyT *k0 = (KeyT *) (wsb + off_k0), *k1 = (KeyT *) (wsb + off_k1);
+    double *v0 = (double *) (wsb + off_v0), *v1 = (double *) (wsb + off_v1);
+
+    for (int64_t first = 0; first < a->npart; first += chunk) {
+        const int64_t count = (a->npart - first) < chunk ? (a->npart - first) : chunk;
+        const int64_t n = count * npts;
+        if (fam) {
+            int grid = pmb_grid(ctx, count, 256, 8);
+            PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+                (pmb_k_expand_tuned<KeyT, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(g, p, first, count, a->pcs_gradient_scale_fix, k0, v0))));
+        } else {
+            PMB_CUDA(cudaMemsetAsync(k0, 0xFF, sizeof(KeyT) * n, ctx->stream));
+            PMB_CUDA(cudaMemsetAsync(v0, 0, sizeof(double) * n, ctx->stream));
+            int grid = pmb_grid(ctx, count, 128, 8);
+            PMB_DISPATCH_NDIM(a->ndim,
+                (pmb_k_expand_dyn<KeyT, NDIM><<<grid, 128, 0, ctx->stream>>>(g, w, p, first, count, a->pcs_gradient_scale_fix, npts, k0, v0)));
+        }
+        PMB_LAUNCH_CHECK(ctx);
+        cub::DoubleBuffer<KeyT> kb(k0, k1);
+        cub::DoubleBuffer<double> vb(v0, v1);
+        size_t tb = temp_bytes;
+        PMB_CUDA(cub::DeviceRadixSort::SortPairs(wsb + off_t, tb, kb, vb, (int) n, 0, key_bits, ctx->stream));
+        ctx->launches += 4;
+        int grid = pmb_grid(ctx, n, 256, 8);
+        pmb_k_segment_sum<KeyT, MeshT><<<grid, 256, 0, ctx->stream>>>(
+            kb.Current(), vb.Current(), n, (char *) a->mesh,
+            a->ndim > 1 ? g_in.size[a->ndim - 2] : 1, g_in.size[a->ndim - 1],
+            a->ndim > 2 ? g_in.strides[a->ndim - 3] : 0,
+            a->ndim > 1 ? g_in.strides[a->ndim - 2] : 0,
+            g_in.strides[a->ndim - 1]);
+        PMB_LAUNCH_CHECK(ctx);
+    }
+    return PMB_OK;
+}
+
+extern "C" int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a)
+{
+    PMB_CHECK(check_args(ctx, a, 0));
+    PMB_REQUIRE(a->mode == PMB_MODE_ATOMIC || a->mode == PMB_MODE_DETERMINISTIC, "bad paint mode %d", a->mode);
+    if (a->npart == 0) return PMB_OK;
+    PmbGeom g;
+    fill_geom(a, &g);
+    PmbParticles p;
+    fill_particles(a, &p);
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
+    for (int d = 0; d < a->ndim; d++) if (a->size[d] == 0) return PMB_OK;
+    if (a->mode == PMB_MODE_ATOMIC) {
+        if (a->mesh_elsize == 8) return paint_atomic<double>(ctx, a, g, w, p);
+        return paint_atomic<float>(ctx, a, g, w, p);
+    }
+    int64_t ncell = 1;
+    for (int d = 0; d < a->ndim; d++) ncell *= a->size[d];
+    const bool small = ncell < (int64_t) 0xFFFFFFFFll;
+    if (a->mesh_elsize == 8)
+        return small ? paint_deterministic<uint32_t, double>(ctx, a, g, w, p)
+                     : paint_deterministic<uint64_t, double>(ctx, a, g, w, p);
+    return small ? paint_deterministic<uint32_t, float>(ctx, a, g, w, p)
+                 : paint_deterministic<uint64_t, float>(ctx, a, g, w, p);
+}
+
+template <typename MeshT>
+static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
+                        const PmbParticles &p)
+{
+    const int fam = fixed_family(w, a);
+    const char *mesh = (const char *) a->mesh;
+    if (fam) {
+        int grid = pmb_grid(ctx, a->npart, 256, 8);
+        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_tuned<MeshT, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride))));
+    } else {
+        int grid = pmb_grid(ctx, a->npart, 128, 8);
+        PMB_DISPATCH_NDIM(a->ndim,
+            (pmb_k_readout_dyn<MeshT, NDIM><<<grid, 128, 0, ctx->stream>>>(
+                g, w, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride)));
+    }
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+extern "C" int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a)
+{
+    PMB_CHECK(check_args(ctx, a, 1));
+    if (a->npart == 0) return PMB_OK;
+    PmbGeom g;
+    fill_geom(a, &g);
+    PmbParticles p;
+    fill_particles(a, &p);
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
+    if (a->mesh_elsize == 8) return readout_impl<double>(ctx, a, g, w, p);
+    return readout_impl<float>(ctx, a, g, w, p);
+}
+
+extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1)
+{
+    PMB_REQUIRE(ctx && a, "null argument");
+    PMB_REQUIRE(a->ndim >= 1 && a->ndim <= 3, "ndim %d not supported (1..3)", a->ndim);
+    PMB_REQUIRE(a->npart == 0 || out_grad, "null out_grad");
+    PMB_REQUIRE(a->out_elsize == 4 || a->out_elsize == 8, "out must be float32 or float64");
+    PMB_REQUIRE(a->mesh_elsize == 4 || a->mesh_elsize == 8, "canvas must be float32 or float64");
+    for (int d = 0; d < a->ndim; d++)
+        PMB_REQUIRE(a->order[d] == 0, "gradient of gradient is not supported (pm.py:822-823)");
+    if (a->npart == 0) return PMB_OK;
+    PmbGeom g;
+    fill_geom(a, &g);
+    PmbParticles p;
+    fill_particles(a, &p);
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
+    const int fam = fixed_family(w, a);
+    if (!fam) {
+        // generic windows: value pass + one pass per axis through the ordinary readout kernel
+        pmb_resample_args b = *a;
+        if (a->out) PMB_CHECK(pmb_readout(ctx, &b));
+        for (int d = 0; d < a->ndim; d++) {
+            b = *a;
+            b.order[d] = 1;
+            b.out = (char *) out_grad + d * gs1;
+            b.out_stride = gs0;
+            PMB_CHECK(pmb_readout(ctx, &b));
+        }
+        return PMB_OK;
+    }
+    const char *mesh = (const char *) a->mesh;
+    int grid = pmb_grid(ctx, a->npart, 256, 8);
+    if (a->mesh_elsize == 8) {
+        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_grad_tuned<double, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1))));
+    } else {
+        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_grad_tuned<float, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1))));
+    }
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
