@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- the PM force step of BASELINE.json on N B200s of one node.
+
+A "step" is one full CIC particle-mesh force evaluation (examples/nbody.py:199-218 of the
+reference): decompose -> exchange -> paint -> x N^3/Np -> r2c -> {gravity transfer -> c2r ->
+readout -> ghost sum} x 3, for `--nmesh`^3 particles on a `--nmesh`^3 mesh (default 1024: the
+configuration BASELINE.json's metric "PM force step ms (1024^3)" is quoted on; it fits one GPU).
+Total work is fixed as N grows (strong scaling); each rank starts with the particles of its own
+lattice slab, displaced Zel'dovich-style.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference's CPU kernels on the host cores
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the library's stream, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PM force step ms (1024^3 CIC: decompose, paint, r2c, gravity transfer, c2r x3, readout x3)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nmesh", type=int, default=1024)
+    ap.add_argument("--window", default="cic")
+    ap.add_argument("--dtype", default="f8")
+    ap.add_argument("--particles", default="zeldovich", choices=["zeldovich", "uniform"])
+    ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
+    ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="side of the CPU-baseline sample problem")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.p = None
+        self.device = device
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(numpy.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ ours
+def make_particles(pm, args, comm):
+    """device-resident positions of this rank: the rank's slab of the Nmesh^3 lattice (shift 0.5),
+    displaced by a smooth periodic field of ~3 cells rms ('zeldovich'), or uniform random."""
+    import ctypes
+    from pmesh_b200 import _lib
+    from pmesh_b200.device import DeviceArray
+    M = args.nmesh
+    ntot = M ** 3
+    per = (ntot + comm.size - 1) // comm.size
+    # whole lattice planes per rank so that particles start (mostly) inside their own slab
+    planes = (M + comm.size - 1) // comm.size
+    first = min(comm.rank * planes, M) * M * M
+    n = min((comm.rank + 1) * planes, M) * M * M - first
+    X = DeviceArray.empty((n, 3), "f8")
+    ctx = X.ctx
+    box = (ctypes.c_double * 3)(*[float(b) for b in pm.BoxSize])
+    if args.particles == "uniform":
+        _lib.check(ctx.lib.pmb_particles_uniform(ctx.handle, X.ptr, 8, n, 3, box, 45, first))
+    else:
+        nn = (ctypes.c_int64 * 3)(M, M, M)
+        _lib.check(ctx.lib.pmb_particles_lattice(ctx.handle, X.ptr, 8, n, 3, nn, box, 0.5, 3.0, 44, first))
+    ctx.sync()
+    return X, ntot
+
+
+class ForceStep(object):
+    """The force step on device-resident particles, written against the public pmesh API."""
+    def __init__(self, pm, args):
+        from pmesh_b200 import transfer as T
+        self.pm, self.args = pm, args
+        self.rho = pm.create("real")
+        self.rhok = pm.create("complex")
+        self.tmp = pm.create("complex")
+        self.tf = [T.GravityFD4(d) for d in range(3)]
+        self.stage = {}
+
+    def _t(self, name, fn):
+        if not self.args.breakdown:
+            return fn()
+        ctx = self.pm.ctx
+        ctx.timer_start(1)
+        r = fn()
+        self.stage[name] = self.stage.get(name, 0.0) + ctx.timer_stop(1)
+        return r
+
+    def __call__(self, X, ntot, F):
+        pm = self.pm
+        layout = self._t("decompose", lambda: pm.decompose(X, smoothing=1.0 * pm.resampler.support))
+        lpos = self._t("exchange", lambda: layout.exchange(X))
+        self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
+        self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
+        self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
+        for d in range(3):
+            self._t("transfer", lambda: self.rhok.apply(self.tf[d], out=self.tmp))
+            real = self._t("c2r", lambda: self.tmp.c2r(out=Ellipsis))
+            loc = self._t("readout", lambda: real.readout(lpos, out=self._local(lpos.shape[0])))
+            self._t("gather", lambda: layout.gather(loc, out=F[d]))
+        return F
+
+    def _local(self, n):
+        from pmesh_b200.device import DeviceArray
+        if getattr(self, "_loc", None) is None or self._loc.shape[0] != n:
+            self._loc = DeviceArray.empty((n,), "f8")
+        return self._loc
+
+
+def run_ours(args):
+    from pmesh_b200 import _lib, comm as C
+    from pmesh_b200.device import DeviceArray, PinnedArray
+    from pmesh_b200.pm import ParticleMesh
+
+    comm = C.world()
+    if comm.size != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE is %d (launch with torch.distributed.run)" % (args.gpus, comm.size))
+    M = args.nmesh
+    pm = ParticleMesh(BoxSize=float(M), Nmesh=[M, M, M], dtype=args.dtype, resampler=args.window, comm=comm)
+    ctx = pm.ctx
+    X, ntot = make_particles(pm, args, comm)
+    n = X.shape[0]
+    F = [DeviceArray.empty((n,), "f8") for d in range(3)]     # force components (SoA)
+    step = ForceStep(pm, args)
+
+    for _ in range(args.warmup):
+        step(X, ntot, F)
+    if args.breakdown:
+        step.stage = {}
+    comm.Barrier()
+    ctx.sync()
+    clocks = ClockSampler(ctx.device)
+    ctx.launch_count(reset=True)
+    pm.fft_library_ms(reset=True)
+    ctx.timer_start(0)
+    for _ in range(args.steps):
+        step(X, ntot, F)
+    ms = ctx.timer_stop(0)
+    comm.Barrier()
+    launches = ctx.launch_count()
+    fft_ms = pm.fft_library_ms()
+    clk = clocks.stop()
+    ms_step = comm.allreduce(ms / args.steps, op=C.MAX)
+    fft_step = comm.allreduce(fft_ms / args.steps, op=C.MAX)
+
+    # ---- dominant kernels alone: paint and readout on the local particles (roofline) ----
+    peak, peak_src = peaks()
+    es = pm.dtype.itemsize
+    layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
+    lpos = layout.exchange(X)
+    nl = lpos.shape[0]
+    ncell_local = int(numpy.prod(pm._layout['i_shape']))
+    rho = pm.create("real")
+    R = 5
+    for _ in range(2):
+        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+    ctx.timer_start(2)
+    for _ in range(R):
+        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+    t_paint = ctx.timer_stop(2) / R
+    out = DeviceArray.empty((nl,), "f8")
+    for _ in range(2):
+        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
+    ctx.timer_start(2)
+    for _ in range(R):
+        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
+    t_read = ctx.timer_stop(2) / R
+    ab_paint = nl * 24.0 + ncell_local * es          # pos (3 x f8) read + one mesh write pass
+    ab_read = nl * (24.0 + 8.0) + ncell_local * es   # pos read + f8 result write + one mesh read pass
+    gp_s = comm.allreduce(nl, op=C.SUM) / ((comm.allreduce(t_paint, op=C.MAX) + comm.allreduce(t_read, op=C.MAX)) * 1e-3) / 1e9
+    dom = ("paint", t_paint, ab_paint) if t_paint >= t_read else ("readout", t_read, ab_read)
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pmb_k_%s_tuned<%s>" % (dom[0], args.window), "achieved": round(achieved, 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "ms_per_launch": round(dom[1], 4),
+                "algorithmic_bytes_per_launch": dom[2],
+                "paint_ms": round(t_paint, 4), "readout_ms": round(t_read, 4),
+                "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),
+                "readout_frac": round(ab_read / (t_read * 1e-3) / 1e9 / peak, 4)}
+    del lpos, layout, rho, out
+
+    # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timing ----
+    e2e = None
+    if not args.no_e2e:
+        Xh = PinnedArray((n, 3), "f8")
+        Fh = PinnedArray((3, n), "f8")
+        ctx.d2h(Xh.array, X.ptr, X.nbytes)
+        ke = max(1, min(args.steps, 2))
+        comm.Barrier()
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            Xd = DeviceArray.empty((n, 3), "f8")
+            ctx.h2d(Xd.ptr, Xh.array, Xd.nbytes)
+            step(Xd, ntot, F)
+            for d in range(3):
+                ctx.d2h(Fh.array[d], F[d].ptr, F[d].nbytes)
+            del Xd
+        ctx.sync()
+        comm.Barrier()
+        e2e_ms = comm.allreduce((time.perf_counter() - t0) * 1e3 / ke, op=C.MAX)
+        e2e = {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(X.nbytes),
+               "d2h_bytes_per_step": int(3 * F[0].nbytes), "steps": ke}
+        del Xh, Fh
+
+    cpu = None
+    if comm.rank == 0 and comm.size == 1 and not args.no_cpu:
+        cpu = cpu_force_step(args, cores=1, steps=1)
+
+    if comm.rank == 0:
+        line = {
+            "metric": METRIC, "value": round(ms_step, 3), "unit": "ms", "n_gpus": comm.size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f8" if args.dtype == "f8" else "f4", "data": "synthetic",
+            "config": {"workload": "CIC PM force step, %d^3 %s particles on a %d^3 mesh (BASELINE configs[2] shape)%s"
+                                   % (M, args.particles, M, "" if comm.size > 1 else ", single GPU"),
+                       "nmesh": M, "nparticles": ntot, "window": args.window, "paint_mode": args.paint_mode,
+                       "decomposition": "slab np=[%d]" % comm.size,
+                       "l2": "inputs (%.1f GB positions + %.1f GB mesh per rank) are larger than L2"
+                             % (X.nbytes / 1e9, ncell_local * es / 1e9)},
+            "paint_readout_gparticles_per_s": round(gp_s, 3),
+            "particles_per_s_force_step": round(ntot / (ms_step * 1e-3), 1),
+            "cufft_library_ms_per_step": round(fft_step, 3),
+            "gpu_launches": int(launches),
+            "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        if args.breakdown:
+            line["stage_ms_per_step"] = dict((k, round(v / args.steps, 3)) for k, v in step.stage.items())
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_kernels():
+    """(paint, readout, kind): the compiled reference (oracle/_ref) when present, else the oracle port"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    import oracle
+    oracle.build()
+    mods = build_ref.load()
+    if mods is not None:
+        w = mods[0]
+
+        class RW(w.ResampleWindow):
+            pass
+
+        def paint(real, pos, kind, scale, period):
+            nd = real.ndim
+            RW(oracle.NAMES[kind]).paint(real, pos, None, numpy.ones(len(pos)), numpy.zeros(nd, dtype=int),
+                                         numpy.full(nd, scale), numpy.zeros(nd), numpy.full(nd, period, dtype=numpy.intp))
+
+        def readout(real, pos, kind, scale, period):
+            nd = real.ndim
+            out = numpy.zeros(len(pos))
+            RW(oracle.NAMES[kind]).readout(real, pos, None, out, numpy.zeros(nd, dtype=int),
+                                           numpy.full(nd, scale), numpy.zeros(nd), numpy.full(nd, period, dtype=numpy.intp))
+            return out
+        return paint, readout, "reference", oracle
+
+    def paint(real, pos, kind, scale, period):
+        oracle.paint(real, pos, kind, scale=scale, period=period)
+
+    def readout(real, pos, kind, scale, period):
+        return oracle.readout(real, pos, kind, scale=scale, period=period)
+    return paint, readout, "port", oracle
+
+
+def _cpu_worker(job):
+    """one 'rank' of the reference's SPMD model: paint / readout its own particle chunk"""
+    what, kind, n, pos, mesh = job
+    paint, readout, _, _ = _cpu_kernels()
+    if what == "paint":
+        real = numpy.zeros((n, n, n))
+        paint(real, pos, kind, 1.0, n)
+        return real
+    return readout(mesh, pos, kind, 1.0, n)
+
+
+def cpu_force_step(args, cores, steps):
+    """The reference's CPU path for the same force step on a bounded sample: `--cpu-sample`^3
+    particles / mesh (BoxSize = side so scale = 1), reference C paint/readout + the oracle's
+    decompose (numpy digitize + gridnd_fill) + numpy/scipy FFT as the labelled stand-in for PFFT
+    (not installable here).  Reported scaled to the 1024^3 workload by particle count."""
+    paint, readout, kind, oracle = _cpu_kernels()
+    n = args.cpu_sample
+    rng = numpy.random.default_rng(44)
+    q = (numpy.indices((n, n, n)).reshape(3, -1).T + 0.5)
+    X = (q + 3.0 * numpy.sin(2 * numpy.pi * 4 * q[:, ::-1] / n)) % n
+    edges = [numpy.array([0.0, n])] * 3
+    pool = None
+    if cores > 1:
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(cores)
+    try:
+        import scipy.fft as sfft
+        fftw = dict(workers=cores)
+        rfftn, irfftn = (lambda a: sfft.rfftn(a, **fftw)), (lambda a, s: sfft.irfftn(a, s=s, **fftw))
+    except Exception:
+        rfftn, irfftn = numpy.fft.rfftn, (lambda a, s: numpy.fft.irfftn(a, s=s))
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        counts, indices = oracle.decompose(X, edges, 1, smoothing=2.0)
+        lpos = X.take(indices, axis=0)
+        chunks = numpy.array_split(lpos, cores)
+        if pool:
+            mesh = sum(pool.map(_cpu_worker, [("paint", args.window, n, c, None) for c in chunks]))
+        else:
+            mesh = numpy.zeros((n, n, n))
+            paint(mesh, lpos, args.window, 1.0, n)
+        mesh *= 1.0
+        ck = rfftn(mesh) / mesh.size
+        for d in range(3):
+            fr = irfftn(oracle.transfer(ck, [n] * 3, [float(n)] * 3, "gravity_fd4", d), (n, n, n)) * mesh.size
+            if pool:
+                f = numpy.concatenate(pool.map(_cpu_worker, [("readout", args.window, n, c, fr) for c in chunks]))
+            else:
+                f = readout(fr, lpos, args.window, 1.0, n)
+            oracle.bincount_sum(indices, f, len(X))
+        times.append(time.perf_counter() - t0)
+    if pool:
+        pool.close()
+    t = float(numpy.mean(times))
+    factor = (args.nmesh / float(n)) ** 3
+    return {"value": round(t * 1e3 * factor, 1), "unit": "ms", "cores": cores, "kind": kind,
+            "sample": "%d^3 particles on a %d^3 mesh, one CIC force step in %.2f s on %d core(s); scaled x%.0f by "
+                      "particle count to %d^3; FFT = numpy/scipy stand-in for PFFT (no MPI/PFFT in the image)"
+                      % (n, n, t, cores, factor, args.nmesh),
+            "sample_seconds": round(t, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_force_step(args, cores=cores, steps=1)
+    r = cpu_force_step(args, cores=cores, steps=max(1, min(args.steps, 3)))
+    M = args.nmesh
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "ms", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["value"], "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f8", "data": "synthetic",
+        "config": {"workload": "CIC PM force step, %d^3 zeldovich particles on a %d^3 mesh (BASELINE configs[2] shape)" % (M, M),
+                   "nmesh": M, "nparticles": M ** 3, "window": args.window},
+        "cpu_baseline": r,
+        "e2e": {"value": r["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

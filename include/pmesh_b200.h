@@ -70,6 +70,8 @@ int pmb_timer_start(pmb_ctx *ctx, int slot);
 int pmb_timer_stop(pmb_ctx *ctx, int slot, float *ms);       /* records stop, synchronises, returns elapsed */
 int pmb_launch_count(pmb_ctx *ctx, int64_t *n, int reset);   /* kernels this library launched so far */
 int pmb_flush_l2(pmb_ctx *ctx);                              /* overwrite a 256 MiB scratch buffer */
+/* workspace budget (bytes) of the deterministic paint: particles are processed in chunks that fit */
+int pmb_set_workspace_limit(pmb_ctx *ctx, size_t nbytes);
 
 /* ---- windows ------------------------------------------------------------------ */
 /* upload one lookup table (lanczosN / acgN / dbN / symN); values are host doubles */

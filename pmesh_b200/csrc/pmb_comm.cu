@@ -6,13 +6,63 @@
 //   allreduce of scalars ................... pmesh/pm.py:296,739,899 (cgetitem, csum, cdot)
 // On an NVSwitch node every peer is reachable at full bandwidth, so the alltoallv is one flat
 // ncclGroup of P sends + P receives; the self block is a device memcpy.
+#include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include "pmb_internal.h"
 
+// NCCL is bound at run time (dlopen), not at link time: a process that also imports torch must end
+// up with ONE libnccl.so.2 -- whichever is already loaded (torch bundles its own, newer than the
+// system one) -- and loading this library must not pin the system copy first.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+static int g_nccl_state = 0;   // 0 not tried, 1 ok, -1 failed
+
+static int nccl_load(void)
+{
+    if (g_nccl_state == 1) return PMB_OK;
+    if (g_nccl_state == -1) { pmb_set_error("NCCL library could not be loaded"); return PMB_ENCCL; }
+    const char *env = getenv("PMESH_B200_NCCL_LIB");
+    void *h = dlopen(env && *env ? env : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        g_nccl_state = -1;
+        pmb_set_error("dlopen(libnccl.so.2) failed: %s", dlerror());
+        return PMB_ENCCL;
+    }
+#define PMB_SYM(field, name)                                              \
+    *(void **) (&g_nccl.field) = dlsym(h, name);                          \
+    if (!g_nccl.field) { g_nccl_state = -1; pmb_set_error("NCCL symbol %s missing", name); return PMB_ENCCL; }
+    PMB_SYM(GetUniqueId, "ncclGetUniqueId");
+    PMB_SYM(CommInitRank, "ncclCommInitRank");
+    PMB_SYM(CommDestroy, "ncclCommDestroy");
+    PMB_SYM(Send, "ncclSend");
+    PMB_SYM(Recv, "ncclRecv");
+    PMB_SYM(GroupStart, "ncclGroupStart");
+    PMB_SYM(GroupEnd, "ncclGroupEnd");
+    PMB_SYM(AllReduce, "ncclAllReduce");
+    PMB_SYM(AllGather, "ncclAllGather");
+    PMB_SYM(GetErrorString, "ncclGetErrorString");
+#undef PMB_SYM
+    g_nccl_state = 1;
+    return PMB_OK;
+}
+
 static int nccl_fail(ncclResult_t r, const char *what, int line)
 {
-    pmb_set_error("NCCL error %d (%s) at %s:%d in %s", (int) r, ncclGetErrorString(r), __FILE__, line, what);
+    pmb_set_error("NCCL error %d (%s) at %s:%d in %s", (int) r,
+                  g_nccl_state == 1 ? g_nccl.GetErrorString(r) : "?", __FILE__, line, what);
     return PMB_ENCCL;
 }
 
@@ -26,8 +76,9 @@ extern "C" int pmb_comm_unique_id(char *id128_h)
 {
     PMB_REQUIRE(id128_h, "null argument");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    PMB_CHECK(nccl_load());
     ncclUniqueId id;
-    PMB_NCCL(ncclGetUniqueId(&id));
+    PMB_NCCL(g_nccl.GetUniqueId(&id));
     memcpy(id128_h, &id, sizeof(id));
     return PMB_OK;
 }
@@ -37,11 +88,12 @@ extern "C" int pmb_comm_init_rank(pmb_ctx *ctx, const char *id128_h, int rank, i
     PMB_REQUIRE(ctx && id128_h, "null argument");
     PMB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / %d", rank, nranks);
     PMB_REQUIRE(!ctx->comm, "communicator already initialised");
+    PMB_CHECK(nccl_load());
     PMB_CUDA(cudaSetDevice(ctx->device));
     ncclUniqueId id;
     memcpy(&id, id128_h, sizeof(id));
     ncclComm_t comm;
-    PMB_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
+    PMB_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
     ctx->comm = (ncclComm *) comm;
     ctx->rank = rank;
     ctx->nranks = nranks;
@@ -52,7 +104,7 @@ extern "C" int pmb_comm_destroy(pmb_ctx *ctx)
 {
     if (!ctx || !ctx->comm) return PMB_OK;
     cudaStreamSynchronize(ctx->stream);
-    ncclCommDestroy((ncclComm_t) ctx->comm);
+    if (g_nccl_state == 1) g_nccl.CommDestroy((ncclComm_t) ctx->comm);
     ctx->comm = NULL;
     ctx->rank = 0;
     ctx->nranks = 1;
@@ -80,17 +132,17 @@ extern "C" int pmb_alltoallv(pmb_ctx *ctx, const void *send, const int64_t *send
     if (P == 1) return PMB_OK;
     PMB_REQUIRE(ctx->comm, "communicator not initialised");
     ncclComm_t comm = (ncclComm_t) ctx->comm;
-    PMB_NCCL(ncclGroupStart());
+    PMB_NCCL(g_nccl.GroupStart());
     for (int q = 0; q < P; q++) {
         if (q == me) continue;
         if (sendcounts_h[q] > 0)
-            PMB_NCCL(ncclSend((const char *) send + sendoffsets_h[q] * itemsize, (size_t) sendcounts_h[q] * itemsize,
+            PMB_NCCL(g_nccl.Send((const char *) send + sendoffsets_h[q] * itemsize, (size_t) sendcounts_h[q] * itemsize,
                               ncclChar, q, comm, ctx->stream));
         if (recvcounts_h[q] > 0)
-            PMB_NCCL(ncclRecv((char *) recv + recvoffsets_h[q] * itemsize, (size_t) recvcounts_h[q] * itemsize,
+            PMB_NCCL(g_nccl.Recv((char *) recv + recvoffsets_h[q] * itemsize, (size_t) recvcounts_h[q] * itemsize,
                               ncclChar, q, comm, ctx->stream));
     }
-    PMB_NCCL(ncclGroupEnd());
+    PMB_NCCL(g_nccl.GroupEnd());
     return PMB_OK;
 }
 
@@ -101,7 +153,7 @@ extern "C" int pmb_allreduce_f64(pmb_ctx *ctx, double *buf, int64_t n, int op)
     if (ctx->nranks == 1 || n == 0) return PMB_OK;
     PMB_REQUIRE(ctx->comm, "communicator not initialised");
     ncclRedOp_t ops[3] = {ncclSum, ncclMax, ncclMin};
-    PMB_NCCL(ncclAllReduce(buf, buf, (size_t) n, ncclDouble, ops[op], (ncclComm_t) ctx->comm, ctx->stream));
+    PMB_NCCL(g_nccl.AllReduce(buf, buf, (size_t) n, ncclDouble, ops[op], (ncclComm_t) ctx->comm, ctx->stream));
     return PMB_OK;
 }
 
@@ -116,7 +168,7 @@ extern "C" int pmb_allgather_bytes(pmb_ctx *ctx, const void *send, void *recv, i
         return PMB_OK;
     }
     PMB_REQUIRE(ctx->comm, "communicator not initialised");
-    PMB_NCCL(ncclAllGather(send, recv, (size_t) nbytes_per_rank, ncclChar, (ncclComm_t) ctx->comm, ctx->stream));
+    PMB_NCCL(g_nccl.AllGather(send, recv, (size_t) nbytes_per_rank, ncclChar, (ncclComm_t) ctx->comm, ctx->stream));
     return PMB_OK;
 }
 
@@ -128,7 +180,7 @@ extern "C" int pmb_barrier(pmb_ctx *ctx)
         void *token;
         PMB_CHECK(pmb_scratch(ctx, 256, &token));
         PMB_CUDA(cudaMemsetAsync(token, 0, 8, ctx->stream));
-        PMB_NCCL(ncclAllReduce(token, token, 1, ncclDouble, ncclSum, (ncclComm_t) ctx->comm, ctx->stream));
+        PMB_NCCL(g_nccl.AllReduce(token, token, 1, ncclDouble, ncclSum, (ncclComm_t) ctx->comm, ctx->stream));
     }
     PMB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PMB_OK;

@@ -189,6 +189,13 @@ extern "C" int pmb_launch_count(pmb_ctx *ctx, int64_t *n, int reset)
     return PMB_OK;
 }
 
+extern "C" int pmb_set_workspace_limit(pmb_ctx *ctx, size_t nbytes)
+{
+    PMB_REQUIRE(ctx && nbytes >= 4096, "workspace limit too small");
+    ctx->det_chunk_bytes = nbytes;
+    return PMB_OK;
+}
+
 int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out)
 {
     if (nbytes > ctx->scratch_bytes) {
@@ -228,40 +235,14 @@ extern "C" int pmb_flush_l2(pmb_ctx *ctx)
 }
 
 // ---------------------------------------------------------------- window registry
-struct KindInfo { int family; int native; int tuned; };
-
-static int kind_info(int kind, KindInfo *ki)
-{
-    switch (kind) {
-    case PMB_NEAREST: *ki = {PMB_FAM_NEAREST, 1, 0}; return 0;
-    case PMB_LINEAR: *ki = {PMB_FAM_LINEAR, 2, 0}; return 0;
-    case PMB_QUADRATIC: *ki = {PMB_FAM_QUADRATIC, 3, 0}; return 0;
-    case PMB_CUBIC: *ki = {PMB_FAM_CUBIC, 4, 0}; return 0;
-    case PMB_TUNED_NNB: *ki = {PMB_FAM_NEAREST, 1, 1}; return 0;
-    case PMB_TUNED_CIC: *ki = {PMB_FAM_LINEAR, 2, 2}; return 0;
-    case PMB_TUNED_TSC: *ki = {PMB_FAM_QUADRATIC, 3, 3}; return 0;
-    case PMB_TUNED_PCS: *ki = {PMB_FAM_CUBIC, 4, 4}; return 0;
-    case PMB_LANCZOS2: case PMB_LANCZOS3: case PMB_LANCZOS4: case PMB_LANCZOS5: case PMB_LANCZOS6:
-        *ki = {PMB_FAM_SYMTABLE, 2 * (kind - PMB_LANCZOS2 + 2), 0}; return 0;
-    case PMB_ACG2: case PMB_ACG3: case PMB_ACG4: case PMB_ACG5: case PMB_ACG6:
-        *ki = {PMB_FAM_SYMTABLE, kind - PMB_ACG2 + 2, 0}; return 0;
-    case PMB_DB6: case PMB_SYM6: *ki = {PMB_FAM_WAVELET, 7, 0}; return 0;
-    case PMB_DB12: case PMB_SYM12: *ki = {PMB_FAM_WAVELET, 10, 0}; return 0;
-    case PMB_DB20: *ki = {PMB_FAM_WAVELET, 13, 0}; return 0;
-    case PMB_SYM20: *ki = {PMB_FAM_WAVELET, 12, 0}; return 0;
-    }
-    pmb_set_error("unknown window kind %d", kind);
-    return PMB_EINVAL;
-}
-
 extern "C" int pmb_window_set_table(pmb_ctx *ctx, int kind, const double *values_h, int n,
                                     double step, double nativesupport, double hsupport)
 {
     PMB_REQUIRE(ctx && values_h && n > 1, "bad table");
-    KindInfo ki;
-    PMB_CHECK(kind_info(kind, &ki));
-    PMB_REQUIRE(ki.family == PMB_FAM_SYMTABLE || ki.family == PMB_FAM_WAVELET, "kind %d is not table driven", kind);
-    PMB_REQUIRE((int) nativesupport == ki.native, "table support %g != %d for kind %d", nativesupport, ki.native, kind);
+    int family, native, tuned;
+    PMB_REQUIRE(pmb_kind_info(kind, &family, &native, &tuned) == 0, "unknown window kind %d", kind);
+    PMB_REQUIRE(family == PMB_FAM_SYMTABLE || family == PMB_FAM_WAVELET, "kind %d is not table driven", kind);
+    PMB_REQUIRE((int) nativesupport == native, "table support %g != %d for kind %d", nativesupport, native, kind);
     pmb_table *t = &ctx->tables[kind];
     if (t->d_values) {
         PMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -277,33 +258,17 @@ extern "C" int pmb_window_set_table(pmb_ctx *ctx, int kind, const double *values
     return PMB_OK;
 }
 
-// <- pmesh_painter_init (pmesh/_window_imp.c:246-456)
+// <- pmesh_painter_init (pmesh/_window_imp.c:246-456); attaches the device lookup table
 int pmb_resolve_window(pmb_ctx *ctx, int kind, int support_req, int ndim, const int *order,
                        PmbWindow *w, int for_device)
 {
-    KindInfo ki;
-    PMB_CHECK(kind_info(kind, &ki));
-    memset(w, 0, sizeof(*w));
-    w->kind = kind;
-    w->family = ki.family;
-    w->nativesupport = ki.native;
-    PmbWinInfo info;
-    pmb_window_info(ki.native, (double) support_req, &info);
-    w->support = info.support;
-    w->tuned = 0;
-    if (ki.tuned && ndim <= 3) {
-        int ok = 1;
-        for (int d = 0; d < ndim; d++) if (order && order[d] > 1) ok = 0;
-        if (ok) w->tuned = ki.tuned;
-    }
-    if (ki.family == PMB_FAM_SYMTABLE || ki.family == PMB_FAM_WAVELET) {
-        if (for_device) {
-            PMB_REQUIRE(ctx && ctx->tables[kind].d_values, "lookup table of window kind %d was not uploaded", kind);
-            w->table = ctx->tables[kind].d_values;
-            w->tablesize = ctx->tables[kind].n;
-            w->step = ctx->tables[kind].step;
-            w->hsupport = ctx->tables[kind].hsupport;
-        }
+    PMB_REQUIRE(pmb_window_resolve(kind, support_req, ndim, order, w) == 0, "unknown window kind %d", kind);
+    if ((w->family == PMB_FAM_SYMTABLE || w->family == PMB_FAM_WAVELET) && for_device) {
+        PMB_REQUIRE(ctx && ctx->tables[kind].d_values, "lookup table of window kind %d was not uploaded", kind);
+        w->table = ctx->tables[kind].d_values;
+        w->tablesize = ctx->tables[kind].n;
+        w->step = ctx->tables[kind].step;
+        w->hsupport = ctx->tables[kind].hsupport;
     }
     return PMB_OK;
 }

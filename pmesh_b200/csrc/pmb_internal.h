@@ -88,17 +88,15 @@ static inline int pmb_grid(const pmb_ctx *ctx, int64_t work_items, int block, in
     return (int) (need < cap ? need : cap);
 }
 
-#ifdef __CUDACC__
 // strided scalar loads of f4/f8 columns promoted to double (ref: fused postype/masstype/hsmltype,
 // pmesh/_window.pyx:6-16,157-165)
-__device__ __forceinline__ double pmb_ld_real(const void *base, int64_t byteoff, int elsize)
+PMB_HD double pmb_ld_real(const void *base, int64_t byteoff, int elsize)
 {
     const char *p = (const char *) base + byteoff;
     return elsize == 8 ? *(const double *) p : (double) *(const float *) p;
 }
-__device__ __forceinline__ void pmb_st_real(void *base, int64_t byteoff, int elsize, double v)
+PMB_HD void pmb_st_real(void *base, int64_t byteoff, int elsize, double v)
 {
     char *p = (char *) base + byteoff;
     if (elsize == 8) *(double *) p = v; else *(float *) p = (float) v;
 }
-#endif

@@ -25,22 +25,22 @@ struct PmbAxes {
 };
 
 template <int NDIM>
-__device__ __forceinline__ void pmb_load_pos(const PmbParticles &p, int64_t i, double *x)
+PMB_HD void pmb_load_pos(const PmbParticles &p, int64_t i, double *x)
 {
 #pragma unroll
     for (int d = 0; d < NDIM; d++) x[d] = pmb_ld_real(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize);
 }
-__device__ __forceinline__ double pmb_load_mass(const PmbParticles &p, int64_t i)
+PMB_HD double pmb_load_mass(const PmbParticles &p, int64_t i)
 {
     return p.mass ? pmb_ld_real(p.mass, i * p.ms, p.mass_elsize) : p.mass_scalar;
 }
-__device__ __forceinline__ double pmb_load_hsml(const PmbParticles &p, int64_t i)
+PMB_HD double pmb_load_hsml(const PmbParticles &p, int64_t i)
 {
     return p.hsml ? pmb_ld_real(p.hsml, i * p.hs, p.hsml_elsize) : p.hsml_scalar;
 }
 
 template <int FAM>
-__device__ __forceinline__ void pmb_axis_tuned(double X, int order, double scale, int pcsfix, int *I, double *V)
+PMB_HD void pmb_axis_tuned(double X, int order, double scale, int pcsfix, int *I, double *V)
 {
     if (FAM == 1) pmb_axis_nnb(X, order, scale, I, V);
     else if (FAM == 2) pmb_axis_cic(X, order, scale, I, V);
@@ -50,7 +50,7 @@ __device__ __forceinline__ void pmb_axis_tuned(double X, int order, double scale
 
 // tuned stencil with compile-time support FAM (1 nnb, 2 cic, 3 tsc, 4 pcs)
 template <int NDIM, int FAM>
-__device__ __forceinline__ void pmb_axes_tuned(const PmbGeom &g, const int *order, const double *x, int pcsfix,
+PMB_HD void pmb_axes_tuned(const PmbGeom &g, const int *order, const double *x, int pcsfix,
                                                PmbAxes<NDIM, FAM> &A)
 {
     A.S = FAM;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void pmb_axes_tuned(const PmbGeom &g, const int *orde
 // run-time support (<= PMB_MAX_SUPPORT): tuned formulas when the per-particle support equals the
 // native one (getfastmethod, _window_tuned_cic.h:135-157), the generic _fill_k otherwise.
 template <int NDIM>
-__device__ __forceinline__ void pmb_axes_dyn(const PmbGeom &g, const PmbWindow &w, const PmbWinInfo &info,
+PMB_HD void pmb_axes_dyn(const PmbGeom &g, const PmbWindow &w, const PmbWinInfo &info,
                                              const int *order, const double *x, int pcsfix,
                                              PmbAxes<NDIM, PMB_MAX_SUPPORT> &A)
 {
@@ -110,7 +110,7 @@ __device__ __forceinline__ void pmb_axes_dyn(const PmbGeom &g, const PmbWindow &
 // visit all S^NDIM points in C order: f(ordinal, offset_or_INVALID, v0, v1, v2)
 // FIXED: compile-time support SMAX, fully unrolled (tuned kernels).
 template <int NDIM, int SMAX, class F>
-__device__ __forceinline__ void pmb_for_points_fixed(const PmbAxes<NDIM, SMAX> &A, F &&f)
+PMB_HD void pmb_for_points_fixed(const PmbAxes<NDIM, SMAX> &A, F &&f)
 {
     int ord = 0;
 #pragma unroll
@@ -140,7 +140,7 @@ __device__ __forceinline__ void pmb_for_points_fixed(const PmbAxes<NDIM, SMAX> &
 
 // run-time support A.S: plain loops, no unrolling
 template <int NDIM, int SMAX, class F>
-__device__ __forceinline__ void pmb_for_points_dyn(const PmbAxes<NDIM, SMAX> &A, F &&f)
+PMB_HD void pmb_for_points_dyn(const PmbAxes<NDIM, SMAX> &A, F &&f)
 {
     const int S = A.S;
     int ord = 0;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void pmb_for_points_dyn(const PmbAxes<NDIM, SMAX> &A,
 // stencils wider than PMB_MAX_SUPPORT (e.g. LANCZOS2.resize(400), tests/test_window.py:215-219):
 // nothing is cached, each point re-evaluates its per-axis weights.  Never tuned.
 template <int NDIM, class F>
-__device__ void pmb_for_points_wide(const PmbGeom &g, const PmbWindow &w, const PmbWinInfo &info,
+PMB_HD void pmb_for_points_wide(const PmbGeom &g, const PmbWindow &w, const PmbWinInfo &info,
                                     const int *order, const double *x, F &&f)
 {
     int I0[NDIM];
@@ -202,7 +202,7 @@ __device__ void pmb_for_points_wide(const PmbGeom &g, const PmbWindow &w, const 
 
 // value deposited by paint for one point (ref: tuned `V0[0] *= weight; Va*Vb*Vc`, _window_tuned_cic.h:41-50;
 // generic `weight * kernel`, _window_generics.h:61)
-__device__ __forceinline__ double pmb_paint_value(bool tuned, double m, double v0, double v1, double v2)
+PMB_HD double pmb_paint_value(bool tuned, double m, double v0, double v1, double v2)
 {
     return tuned ? ((v0 * m) * v1) * v2 : m * ((v0 * v1) * v2);
 }

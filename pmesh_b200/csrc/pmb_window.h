@@ -84,6 +84,50 @@ PMB_HD void pmb_window_info(int nativesupport, double support, PmbWinInfo *info)
     info->vfactor = nativesupport / (1. * support);
 }
 
+// family / native support / tuned family (0 none, else 1 nnb, 2 cic, 3 tsc, 4 pcs) of a kind.
+// ref: the switch of pmesh_painter_init, pmesh/_window_imp.c:259-452.  Returns 0, or -1 for a bad kind.
+PMB_HD int pmb_kind_info(int kind, int *family, int *native, int *tuned)
+{
+    *tuned = 0;
+    if (kind == PMB_NEAREST || kind == PMB_TUNED_NNB) { *family = PMB_FAM_NEAREST; *native = 1; *tuned = kind == PMB_TUNED_NNB ? 1 : 0; return 0; }
+    if (kind == PMB_LINEAR || kind == PMB_TUNED_CIC) { *family = PMB_FAM_LINEAR; *native = 2; *tuned = kind == PMB_TUNED_CIC ? 2 : 0; return 0; }
+    if (kind == PMB_QUADRATIC || kind == PMB_TUNED_TSC) { *family = PMB_FAM_QUADRATIC; *native = 3; *tuned = kind == PMB_TUNED_TSC ? 3 : 0; return 0; }
+    if (kind == PMB_CUBIC || kind == PMB_TUNED_PCS) { *family = PMB_FAM_CUBIC; *native = 4; *tuned = kind == PMB_TUNED_PCS ? 4 : 0; return 0; }
+    if (kind >= PMB_LANCZOS2 && kind <= PMB_LANCZOS6) { *family = PMB_FAM_SYMTABLE; *native = 2 * (kind - PMB_LANCZOS2 + 2); return 0; }
+    if (kind >= PMB_ACG2 && kind <= PMB_ACG6) { *family = PMB_FAM_SYMTABLE; *native = kind - PMB_ACG2 + 2; return 0; }
+    if (kind == PMB_DB6 || kind == PMB_SYM6) { *family = PMB_FAM_WAVELET; *native = 7; return 0; }
+    if (kind == PMB_DB12 || kind == PMB_SYM12) { *family = PMB_FAM_WAVELET; *native = 10; return 0; }
+    if (kind == PMB_DB20) { *family = PMB_FAM_WAVELET; *native = 13; return 0; }
+    if (kind == PMB_SYM20) { *family = PMB_FAM_WAVELET; *native = 12; return 0; }
+    return -1;
+}
+
+// resolve everything of a window but its lookup table (<- pmesh_painter_init, _window_imp.c:246-456):
+// integer support from the request, and whether the tuned fast path is eligible
+// (tuned kind, order <= 1 on every axis, ndim <= 3).
+PMB_HD int pmb_window_resolve(int kind, int support_req, int ndim, const int *order, PmbWindow *w)
+{
+    int family, native, tuned;
+    if (pmb_kind_info(kind, &family, &native, &tuned) != 0) return -1;
+    w->kind = kind;
+    w->family = family;
+    w->nativesupport = native;
+    w->tablesize = 0;
+    w->step = 0;
+    w->hsupport = 0;
+    w->table = 0;
+    PmbWinInfo info;
+    pmb_window_info(native, (double) support_req, &info);
+    w->support = info.support;
+    w->tuned = 0;
+    if (tuned && ndim <= 3) {
+        int ok = 1;
+        for (int d = 0; d < ndim; d++) if (order && order[d] > 1) ok = 0;
+        if (ok) w->tuned = tuned;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- kernels
 PMB_HD double pmb_table_lerp(const double *t, int i, double f)
 {

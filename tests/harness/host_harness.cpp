@@ -1,0 +1,210 @@
+// host_harness.cpp -- TEST-ONLY host build of the device stencil code.
+//
+// The window / stencil arithmetic of the CUDA kernels lives in headers that compile for host and
+// device (pmesh_b200/csrc/pmb_window.h, pmb_stencil.cuh).  This file walks particles serially with
+// exactly those routines so that `pytest -m "not gpu"` can check, in a container without a GPU,
+// that the arithmetic the kernels execute is bit-identical to the oracle (g++ -ffp-contract=off
+// mirrors nvcc -fmad=false).  It is not part of libpmesh_b200.so and is never used by the product.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../pmesh_b200/csrc/pmb_stencil.cuh"
+
+static pmb_table g_tables[PMB_NKINDS];
+static std::vector<double> g_store[PMB_NKINDS];
+
+extern "C" int hh_set_table(int kind, const double *values, int n, double step, double hsupport)
+{
+    if (kind < 0 || kind >= PMB_NKINDS) return -1;
+    g_store[kind].assign(values, values + n);
+    g_tables[kind].d_values = g_store[kind].data();
+    g_tables[kind].n = n;
+    g_tables[kind].step = step;
+    g_tables[kind].hsupport = hsupport;
+    return 0;
+}
+
+static int resolve(const pmb_resample_args *a, PmbWindow *w)
+{
+    if (pmb_window_resolve(a->kind, a->support, a->ndim, a->order, w) != 0) return -1;
+    if (w->family == PMB_FAM_SYMTABLE || w->family == PMB_FAM_WAVELET) {
+        if (!g_tables[a->kind].d_values) return -2;
+        w->table = g_tables[a->kind].d_values;
+        w->tablesize = g_tables[a->kind].n;
+        w->step = g_tables[a->kind].step;
+        w->hsupport = g_tables[a->kind].hsupport;
+    }
+    return 0;
+}
+
+static void geom(const pmb_resample_args *a, PmbGeom *g)
+{
+    memset(g, 0, sizeof(*g));
+    g->ndim = a->ndim;
+    for (int d = 0; d < a->ndim; d++) {
+        g->order[d] = a->order[d]; g->scale[d] = a->scale[d]; g->translate[d] = a->translate[d];
+        g->period[d] = a->period[d]; g->size[d] = a->size[d]; g->strides[d] = a->strides[d];
+    }
+}
+
+static void parts(const pmb_resample_args *a, PmbParticles *p)
+{
+    p->pos = a->pos; p->pos_elsize = a->pos_elsize; p->ps0 = a->pos_stride0; p->ps1 = a->pos_stride1;
+    p->mass = a->mass; p->mass_elsize = a->mass_elsize; p->ms = a->mass_stride; p->mass_scalar = a->mass_scalar;
+    p->hsml = a->hsml; p->hsml_elsize = a->hsml_elsize; p->hs = a->hsml_stride; p->hsml_scalar = a->hsml_scalar;
+}
+
+static int fixed_family(const PmbWindow &w, const pmb_resample_args *a)
+{
+    if (!w.tuned || a->hsml) return 0;
+    PmbWinInfo info;
+    pmb_window_info(w.nativesupport, w.support * a->hsml_scalar, &info);
+    return info.support == w.tuned ? w.tuned : 0;
+}
+
+// visit the stencil of particle i the way the kernels do: f(ordinal, off, value_for_paint, weightprod)
+template <int NDIM, int FAM, class F>
+static void visit_fixed(const PmbGeom &g, const PmbParticles &p, int64_t i, int pcsfix, F &&f)
+{
+    double x[NDIM];
+    pmb_load_pos<NDIM>(p, i, x);
+    const double m = pmb_load_mass(p, i);
+    PmbAxes<NDIM, FAM> A;
+    pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+    pmb_for_points_fixed<NDIM, FAM>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+        f(ord, off, pmb_paint_value(true, m, v0, v1, v2), (v0 * v1) * v2);
+    });
+}
+
+template <int NDIM, class F>
+static void visit_dyn(const PmbGeom &g, const PmbWindow &w, const PmbParticles &p, int64_t i, int pcsfix, F &&f)
+{
+    double x[NDIM];
+    pmb_load_pos<NDIM>(p, i, x);
+    const double m = pmb_load_mass(p, i);
+    const double h = pmb_load_hsml(p, i);
+    PmbWinInfo info;
+    pmb_window_info(w.nativesupport, w.support * h, &info);
+    if (info.support <= PMB_MAX_SUPPORT) {
+        PmbAxes<NDIM, PMB_MAX_SUPPORT> A;
+        pmb_axes_dyn<NDIM>(g, w, info, g.order, x, pcsfix, A);
+        const bool tuned = A.tuned;
+        pmb_for_points_dyn<NDIM, PMB_MAX_SUPPORT>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+            f(ord, off, pmb_paint_value(tuned, m, v0, v1, v2), (v0 * v1) * v2);
+        });
+    } else {
+        pmb_for_points_wide<NDIM>(g, w, info, g.order, x, [&](int ord, int64_t off, double v0, double v1, double v2) {
+            f(ord, off, pmb_paint_value(false, m, v0, v1, v2), (v0 * v1) * v2);
+        });
+    }
+}
+
+template <int NDIM, class F>
+static void visit(const PmbGeom &g, const PmbWindow &w, int fam, const PmbParticles &p, int64_t i, int pcsfix, F &&f)
+{
+    switch (fam) {
+    case 0: visit_dyn<NDIM>(g, w, p, i, pcsfix, f); break;
+    case 1: visit_fixed<NDIM, 1>(g, p, i, pcsfix, f); break;
+    case 2: visit_fixed<NDIM, 2>(g, p, i, pcsfix, f); break;
+    case 3: visit_fixed<NDIM, 3>(g, p, i, pcsfix, f); break;
+    default: visit_fixed<NDIM, 4>(g, p, i, pcsfix, f); break;
+    }
+}
+
+template <int NDIM>
+static int paint_nd(const pmb_resample_args *a, const PmbWindow &w)
+{
+    PmbGeom g;
+    geom(a, &g);
+    PmbParticles p;
+    parts(a, &p);
+    const int fam = fixed_family(w, a);
+    char *mesh = (char *) a->mesh;
+    if (a->mode == PMB_MODE_ATOMIC) {
+        for (int64_t i = 0; i < a->npart; i++)
+            visit<NDIM>(g, w, fam, p, i, a->pcs_gradient_scale_fix, [&](int, int64_t off, double f, double) {
+                if (off == PMB_OFF_INVALID) return;
+                if (a->mesh_elsize == 8) *(double *) (mesh + off) += f;
+                else *(float *) (mesh + off) = *(float *) (mesh + off) + (float) f;   // red.global.add.f32 semantics
+            });
+        return 0;
+    }
+    // deterministic: (cell, value) pairs in particle/point order, stable sort by cell, sequential sums
+    PmbGeom gd = g;
+    int64_t acc = 1;
+    for (int d = NDIM - 1; d >= 0; d--) { gd.strides[d] = acc; acc *= gd.size[d]; }
+    std::vector<std::pair<int64_t, double>> pairs;
+    for (int64_t i = 0; i < a->npart; i++)
+        visit<NDIM>(gd, w, fam, p, i, a->pcs_gradient_scale_fix, [&](int, int64_t off, double f, double) {
+            if (off != PMB_OFF_INVALID) pairs.emplace_back(off, f);
+        });
+    std::stable_sort(pairs.begin(), pairs.end(),
+                     [](const std::pair<int64_t, double> &l, const std::pair<int64_t, double> &r) { return l.first < r.first; });
+    for (size_t s = 0; s < pairs.size();) {
+        int64_t lin = pairs[s].first, rem = lin;
+        int64_t off = 0;
+        for (int d = NDIM - 1; d >= 0; d--) { off += (rem % g.size[d]) * g.strides[d]; rem /= g.size[d]; }
+        size_t e = s;
+        if (a->mesh_elsize == 8) {
+            double c = *(double *) (mesh + off);
+            for (; e < pairs.size() && pairs[e].first == lin; e++) c = (double) ((double) c + pairs[e].second);
+            *(double *) (mesh + off) = c;
+        } else {
+            float c = *(float *) (mesh + off);
+            for (; e < pairs.size() && pairs[e].first == lin; e++) c = (float) ((double) c + pairs[e].second);
+            *(float *) (mesh + off) = c;
+        }
+        s = e;
+    }
+    return 0;
+}
+
+template <int NDIM>
+static int readout_nd(const pmb_resample_args *a, const PmbWindow &w)
+{
+    PmbGeom g;
+    geom(a, &g);
+    PmbParticles p;
+    parts(a, &p);
+    const int fam = fixed_family(w, a);
+    const char *mesh = (const char *) a->mesh;
+    for (int64_t i = 0; i < a->npart; i++) {
+        double value = 0;
+        visit<NDIM>(g, w, fam, p, i, a->pcs_gradient_scale_fix, [&](int, int64_t off, double, double wp) {
+            if (off == PMB_OFF_INVALID) return;
+            const double c = a->mesh_elsize == 8 ? *(const double *) (mesh + off) : (double) *(const float *) (mesh + off);
+            value += c * wp;
+        });
+        pmb_st_real(a->out, i * a->out_stride, a->out_elsize, value);
+    }
+    return 0;
+}
+
+extern "C" int hh_paint(const pmb_resample_args *a)
+{
+    PmbWindow w;
+    int rc = resolve(a, &w);
+    if (rc) return rc;
+    for (int d = 0; d < a->ndim; d++) if (a->size[d] == 0) return 0;
+    switch (a->ndim) {
+    case 1: return paint_nd<1>(a, w);
+    case 2: return paint_nd<2>(a, w);
+    case 3: return paint_nd<3>(a, w);
+    }
+    return -3;
+}
+
+extern "C" int hh_readout(const pmb_resample_args *a)
+{
+    PmbWindow w;
+    int rc = resolve(a, &w);
+    if (rc) return rc;
+    switch (a->ndim) {
+    case 1: return readout_nd<1>(a, w);
+    case 2: return readout_nd<2>(a, w);
+    case 3: return readout_nd<3>(a, w);
+    }
+    return -3;
+}
