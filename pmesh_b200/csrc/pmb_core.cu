@@ -344,6 +344,24 @@ __device__ __forceinline__ int64_t view_offset(const FieldView &v, int64_t i)
     return a * v.strides[0] + j * v.strides[1] + k * v.strides[2];
 }
 
+static bool view_is_dense(const FieldView &v, int elsize)
+{
+    int64_t acc = elsize;
+    for (int d = 2; d >= 0; d--) {
+        if (v.size[d] != 1 && v.strides[d] != acc) return false;
+        acc *= v.size[d];
+    }
+    return true;
+}
+
+template <typename T>
+__global__ void pmb_k_scale_flat(T *__restrict__ a, int64_t n, T factor)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) a[i] = (T) (a[i] * factor);
+}
+
 template <typename T>
 __global__ void pmb_k_fill(char *mesh, FieldView v, T value)
 {
@@ -371,6 +389,10 @@ extern "C" int pmb_field_fill(pmb_ctx *ctx, void *mesh, int elsize, int ndim, co
     FieldView v;
     PMB_CHECK(make_view(ndim, size, strides, &v));
     if (v.n == 0) return PMB_OK;
+    if (value == 0.0 && view_is_dense(v, elsize)) {
+        PMB_CUDA(cudaMemsetAsync(mesh, 0, (size_t) v.n * elsize, ctx->stream));
+        return PMB_OK;
+    }
     int grid = pmb_grid(ctx, v.n, 256, 8);
     if (elsize == 8) pmb_k_fill<double><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, value);
     else pmb_k_fill<float><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, (float) value);
@@ -404,7 +426,10 @@ extern "C" int pmb_field_scale(pmb_ctx *ctx, void *mesh, int elsize, int is_comp
     PMB_CHECK(make_view(ndim, sz, st, &v));
     if (v.n == 0) return PMB_OK;
     int grid = pmb_grid(ctx, v.n, 256, 8);
-    if (elsize == 8) pmb_k_scale<double><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, factor);
+    if (view_is_dense(v, elsize)) {
+        if (elsize == 8) pmb_k_scale_flat<double><<<grid, 256, 0, ctx->stream>>>((double *) mesh, v.n, factor);
+        else pmb_k_scale_flat<float><<<grid, 256, 0, ctx->stream>>>((float *) mesh, v.n, (float) factor);
+    } else if (elsize == 8) pmb_k_scale<double><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, factor);
     else pmb_k_scale<float><<<grid, 256, 0, ctx->stream>>>((char *) mesh, v, factor);
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;

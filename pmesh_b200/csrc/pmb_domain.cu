@@ -64,11 +64,25 @@ __device__ __forceinline__ int pmb_imod(int a, int n)
     return m < 0 ? m + n : m;
 }
 
+// c = x % box with numpy semantics; for 0 <= x < box fmod(x, box) == x exactly, so the (slow,
+// iterative) fmod is only taken by out-of-box coordinates.  -0.0 maps to +0.0 like npy_divmod.
+__device__ __forceinline__ double pmb_pymod_fast(double a, double b)
+{
+    if (a >= 0.0 && a < b) return a + 0.0;
+    return pmb_pymod(a, b);
+}
+
 // per-particle rank mask; ref: pmesh/domain.py:609-630 (sil/sir) + pmesh/_domain.pyx:62-100 (patch walk)
 __device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t i)
 {
     int sil[3], sir[3];
     for (int d = 0; d < g.ndim; d++) {
+        if (g.periodic && g.shape[d] == 1) {
+            // one periodic domain on this axis: sil = p - 1, sir = p, and the single patch cell wraps
+            // to domain 0 whatever the coordinate is (also for NaN: digitize gives len(edges))
+            sil[d] = 0; sir[d] = 1;
+            continue;
+        }
         const double x = g.scale[d] * pmb_ld_real(pos, i * ps0 + d * ps1, elsize);
         const double sm = g.smoothing[d];
         const double *e = g.edges[d];
@@ -76,9 +90,9 @@ __device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsi
         int l, r;
         if (g.periodic) {
             const double box = e[ne - 1];
-            const double c = pmb_pymod(x, box);
-            l = pmb_digitize(pmb_pymod(c - sm, box), e, ne);
-            r = pmb_digitize(pmb_pymod(c + sm, box), e, ne);
+            const double c = pmb_pymod_fast(x, box);
+            l = pmb_digitize(pmb_pymod_fast(c - sm, box), e, ne);
+            r = pmb_digitize(pmb_pymod_fast(c + sm, box), e, ne);
             const int p = pmb_digitize(c, e, ne);
             l = p - pmb_imod(p - l, g.shape[d]) - 1;
             r = p + pmb_imod(r - p, g.shape[d]);
@@ -333,15 +347,46 @@ extern "C" int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int
 }
 
 // ------------------------------------------------------------------ take (gather-pack)
-template <typename W>
-__global__ void pmb_k_take(const W *data, int64_t words, const int32_t *indices, int64_t n, W *out)
+// WORDS > 0: one thread per record of WORDS machine words (no integer division on the hot path);
+// WORDS == 0: generic, one thread per word.
+template <typename W, int WORDS>
+__global__ void __launch_bounds__(256)
+pmb_k_take(const W *__restrict__ data, int64_t words, const int32_t *__restrict__ indices, int64_t n, W *__restrict__ out)
 {
     int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    const int64_t total = n * words;
-    for (; t < total; t += stride) {
-        const int64_t j = t / words, w = t - j * words;
-        out[t] = data[(int64_t) indices[j] * words + w];
+    if (WORDS > 0) {
+        for (; t < n; t += stride) {
+            const W *src = data + (int64_t) __ldcs(indices + t) * WORDS;
+            W v[WORDS > 0 ? WORDS : 1];
+#pragma unroll
+            for (int w = 0; w < WORDS; w++) v[w] = __ldcs(src + w);
+#pragma unroll
+            for (int w = 0; w < WORDS; w++) __stcs(out + t * WORDS + w, v[w]);
+        }
+    } else {
+        const int64_t total = n * words;
+        for (; t < total; t += stride) {
+            const int64_t j = t / words, w = t - j * words;
+            out[t] = data[(int64_t) indices[j] * words + w];
+        }
+    }
+}
+
+template <typename W>
+static void take_launch(pmb_ctx *ctx, const void *data, int64_t words, const int32_t *indices, int64_t n, void *out)
+{
+    const W *d = (const W *) data;
+    W *o = (W *) out;
+    const int grid = pmb_grid(ctx, n, 256, 8);
+    switch (words) {
+    case 1: pmb_k_take<W, 1><<<grid, 256, 0, ctx->stream>>>(d, words, indices, n, o); break;
+    case 2: pmb_k_take<W, 2><<<grid, 256, 0, ctx->stream>>>(d, words, indices, n, o); break;
+    case 3: pmb_k_take<W, 3><<<grid, 256, 0, ctx->stream>>>(d, words, indices, n, o); break;
+    case 4: pmb_k_take<W, 4><<<grid, 256, 0, ctx->stream>>>(d, words, indices, n, o); break;
+    case 6: pmb_k_take<W, 6><<<grid, 256, 0, ctx->stream>>>(d, words, indices, n, o); break;
+    default:
+        pmb_k_take<W, 0><<<pmb_grid(ctx, n * words, 256, 8), 256, 0, ctx->stream>>>(d, words, indices, n, o);
     }
 }
 
@@ -351,48 +396,39 @@ extern "C" int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const 
     if (n == 0) return PMB_OK;
     PMB_REQUIRE(data && indices && out, "null argument");
     const uintptr_t al = (uintptr_t) data | (uintptr_t) out | (uintptr_t) itemsize;
-    if ((al & 7) == 0) {
-        int64_t words = itemsize / 8;
-        pmb_k_take<uint64_t><<<pmb_grid(ctx, n * words, 256, 8), 256, 0, ctx->stream>>>((const uint64_t *) data, words, indices, n, (uint64_t *) out);
-    } else if ((al & 3) == 0) {
-        int64_t words = itemsize / 4;
-        pmb_k_take<uint32_t><<<pmb_grid(ctx, n * words, 256, 8), 256, 0, ctx->stream>>>((const uint32_t *) data, words, indices, n, (uint32_t *) out);
-    } else {
-        pmb_k_take<uint8_t><<<pmb_grid(ctx, n * itemsize, 256, 8), 256, 0, ctx->stream>>>((const uint8_t *) data, itemsize, indices, n, (uint8_t *) out);
-    }
+    if ((al & 7) == 0) take_launch<unsigned long long>(ctx, data, itemsize / 8, indices, n, out);
+    else if ((al & 3) == 0) take_launch<unsigned int>(ctx, data, itemsize / 4, indices, n, out);
+    else take_launch<unsigned char>(ctx, data, itemsize, indices, n, out);
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }
 
 // ------------------------------------------------------------------ ghost reduction (gather 'sum')
-struct GatherSegs {
-    int nranks;
-    int64_t off[ROUTE_MAXRANKS + 1];
-};
+// numpy.bincount(indices, weights) adds weights[j] into out[indices[j]] for ascending j, in float64,
+// starting from 0.0.  `indices` is grouped by rank and a particle appears at most once per rank
+// segment, so one streaming pass per segment (in rank order) performs exactly those additions in
+// exactly that order without atomics: acc[indices[j]] = acc[indices[j]] + data[j].
+__global__ void __launch_bounds__(256)
+pmb_k_gather_pass(const void *__restrict__ data, int data_elsize, int ncomp, const int32_t *__restrict__ indices,
+                  int64_t begin, int64_t end, double *__restrict__ acc)
+{
+    int64_t t = begin * ncomp + blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t total = end * ncomp;
+    for (; t < total; t += stride) {
+        const int64_t j = ncomp == 1 ? t : t / ncomp;
+        const int c = ncomp == 1 ? 0 : (int) (t - j * ncomp);
+        const int64_t o = (int64_t) __ldcs(indices + j) * ncomp + c;
+        const double v = data_elsize == 8 ? __ldcs((const double *) data + t) : (double) __ldcs((const float *) data + t);
+        acc[o] = acc[o] + v;
+    }
+}
 
-// out[i] = sum over ranks r (ascending) of data[j] where indices[j] == i inside segment r.
-// Each segment is sorted ascending by construction, and holds a particle at most once.
-__global__ void pmb_k_gather_sum(const void *data, int data_elsize, int ncomp, const int32_t *indices,
-                                 GatherSegs segs, int64_t nout, void *out, int out_elsize)
+__global__ void pmb_k_f64_to_f32(const double *__restrict__ in, float *__restrict__ out, int64_t n)
 {
     int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    const int64_t total = nout * ncomp;
-    for (; t < total; t += stride) {
-        const int64_t i = t / ncomp;
-        const int c = (int) (t - i * ncomp);
-        double acc = 0.0;
-        for (int r = 0; r < segs.nranks; r++) {
-            int64_t lo = segs.off[r], hi = segs.off[r + 1];
-            while (lo < hi) {
-                int64_t mid = (lo + hi) >> 1;
-                if (indices[mid] < i) lo = mid + 1; else hi = mid;
-            }
-            if (lo < segs.off[r + 1] && indices[lo] == i)
-                acc += pmb_ld_real(data, (lo * ncomp + c) * data_elsize, data_elsize);
-        }
-        pmb_st_real(out, t * out_elsize, out_elsize, acc);
-    }
+    for (; t < n; t += stride) out[t] = (float) in[t];
 }
 
 extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
@@ -403,12 +439,25 @@ extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, i
     PMB_REQUIRE((data_elsize == 4 || data_elsize == 8) && (out_elsize == 4 || out_elsize == 8), "float32/float64 only");
     if (nout == 0) return PMB_OK;
     PMB_REQUIRE(out, "null out");
-    GatherSegs segs;
-    segs.nranks = nranks;
-    for (int r = 0; r <= nranks; r++) segs.off[r] = offsets_h[r];
-    PMB_REQUIRE(segs.off[nranks] == 0 || (data && indices), "null data / indices");
-    pmb_k_gather_sum<<<pmb_grid(ctx, nout * ncomp, 256, 8), 256, 0, ctx->stream>>>(
-        data, data_elsize, ncomp, indices, segs, nout, out, out_elsize);
-    PMB_LAUNCH_CHECK(ctx);
+    PMB_REQUIRE(offsets_h[nranks] == 0 || (data && indices), "null data / indices");
+    const int64_t n = nout * ncomp;
+    double *acc = (double *) out;
+    if (out_elsize == 4) {
+        void *tmp;
+        PMB_CHECK(pmb_scratch(ctx, sizeof(double) * n, &tmp));
+        acc = (double *) tmp;
+    }
+    PMB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * n, ctx->stream));
+    for (int r = 0; r < nranks; r++) {
+        const int64_t b = offsets_h[r], e = offsets_h[r + 1];
+        if (e <= b) continue;
+        pmb_k_gather_pass<<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
+            data, data_elsize, ncomp, indices, b, e, acc);
+        PMB_LAUNCH_CHECK(ctx);
+    }
+    if (out_elsize == 4) {
+        pmb_k_f64_to_f32<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(acc, (float *) out, n);
+        PMB_LAUNCH_CHECK(ctx);
+    }
     return PMB_OK;
 }

@@ -13,6 +13,7 @@
 //   complex, P ranks: distributed along axis 1, memory order (1, 2, 0) = (n1_local, nc, n0)
 //                     -- the "transposed out" representation (TransposedComplexField, pm.py:1078-1086)
 #include <cufft.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "pmb_internal.h"
@@ -428,25 +429,28 @@ static int c2r_from_work(pmb_fft *f, void *real)
 }
 
 // ---- transfer functions -----------------------------------------------------------
+// Per-axis factors are tabulated on the host once per call (3 short tables: wavenumbers k_d[i], and
+// the direction multiplier m[i] = kfinite(k_dir[i]) / k_dir[i] / window factor ...), so the kernel is
+// a pure streaming multiply: one complex load, one complex store, no sin/div-mod per cell.
 struct TfArgs {
-    int kind, dir, ndim, P;
+    int kind, ndim, P;
     int64_t n[3], nc, s1, m1;
-    double box[3];
-    double p0, p1;
-    int win_p;          // sinc power of the compensated window (0: none)
-    double win_vfactor;
+    const double *ktab[3];   // wavenumber per global index of each (left-padded) axis
+    const double *mtab;      // per-index multiplier along the direction axis (or window factors, 3 axes)
+    int dd;                  // direction axis (left-padded index)
+    double p0;
 };
 
 // wavenumber of global index i on an axis of n points, box length L (ref: pm.py:1213-1219):
 // Nyquist and above map to negative frequencies.
-__device__ __forceinline__ double pmb_wavenumber(int64_t i, int64_t n, double L)
+static double host_wavenumber(int64_t i, int64_t n, double L)
 {
     double w = (double) (i >= n / 2 ? i - n : i);
     w = w * (2 * 3.141592653589793 / (double) n);
     return w * (double) n / L;
 }
 
-__device__ __forceinline__ double pmb_sinc_unnormed(double x)
+static double host_sinc_unnormed(double x)
 {
     if (x < 1e-5 && x > -1e-5) {
         double x2 = x * x;
@@ -456,75 +460,75 @@ __device__ __forceinline__ double pmb_sinc_unnormed(double x)
 }
 
 template <typename C>
-__global__ void pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t total, TfArgs a)
+__device__ __forceinline__ void pmb_tf_apply(const C *__restrict__ in, C *__restrict__ out, int64_t t,
+                                             const TfArgs &a, double k0, double k1, double k2v, int64_t idir,
+                                             int64_t i0, int64_t i1, int64_t i2)
 {
-    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (; t < total; t += stride) {
-        int64_t idx[3];
-        if (a.P == 1) {
-            idx[2] = t % a.nc;
-            int64_t r = t / a.nc;
-            idx[1] = r % a.n[1];
-            idx[0] = r / a.n[1];
-        } else {
-            idx[0] = t % a.n[0];
-            int64_t r = t / a.n[0];
-            idx[2] = r % a.nc;
-            idx[1] = a.s1 + r / a.nc;
+    double k2 = 0;
+    if (a.ndim > 2) k2 = k2 + k0 * k0;
+    if (a.ndim > 1) k2 = k2 + k1 * k1;
+    k2 = k2 + k2v * k2v;
+    double re = 1.0, im = 0.0;
+    switch (a.kind) {
+    case PMB_TF_SCALE: re = a.p0; break;
+    case PMB_TF_GRAVITY_FD4:
+    case PMB_TF_GRADIENT_K:
+        if (k2 == 0) k2 = 1.0;
+        re = 0; im = a.mtab[idir] / k2;
+        break;
+    case PMB_TF_INV_LAPLACE:
+        if (k2 == 0) k2 = 1.0;
+        re = -1. / k2;
+        break;
+    case PMB_TF_GAUSS_LOWPASS:
+        re = exp(-0.5 * k2 * (a.p0 * a.p0));
+        break;
+    case PMB_TF_COMPENSATE: {
+        double tf = 1.0;
+        if (a.ndim > 2) tf = tf * a.mtab[i0];
+        if (a.ndim > 1) tf = tf * a.mtab[a.n[0] + i1];
+        tf = tf * a.mtab[a.n[0] + a.n[1] + i2];
+        re = 1.0 / tf;
+    } break;
+    case PMB_TF_IK:
+        re = 0; im = a.mtab[idir];
+        break;
+    }
+    const C v = in[t];
+    C o;
+    o.x = (decltype(o.x)) ((double) v.x * re - (double) v.y * im);
+    o.y = (decltype(o.y)) ((double) v.x * im + (double) v.y * re);
+    out[t] = o;
+}
+
+// one block walks whole rows of the contiguous axis; the row -> (outer indices) split costs one
+// division per row, not per element
+template <typename C>
+__global__ void __launch_bounds__(256)
+pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int64_t rowlen, TfArgs a)
+{
+    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+        int64_t i0, i1, i2 = 0;
+        if (a.P == 1) {           // (n0, n1, nc): rows = (i0, i1), inner = i2
+            i1 = row % a.n[1];
+            i0 = row / a.n[1];
+        } else {                  // (m1, nc, n0): rows = (j, i2), inner = i0
+            i2 = row % a.nc;
+            i1 = a.s1 + row / a.nc;
+            i0 = 0;
         }
-        const int pad = 3 - a.ndim;
-        double k[3] = {0, 0, 0};
-        double k2 = 0;
-        for (int d = pad; d < 3; d++) {
-            k[d] = pmb_wavenumber(idx[d], a.n[d], a.box[d]);
-            k2 = k2 + k[d] * k[d];
-        }
-        const int dd = a.dir + pad;
-        double re = 1.0, im = 0.0;   // multiplier
-        switch (a.kind) {
-        case PMB_TF_SCALE: re = a.p0; break;
-        case PMB_TF_GRAVITY_FD4: {
-            if (k2 == 0) k2 = 1.0;
-            const double Cc = a.box[dd] / (double) a.n[dd];
-            const double w = k[dd] * Cc;
-            const double kfinite = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
-            re = 0; im = kfinite / k2;
-        } break;
-        case PMB_TF_GRADIENT_K:
-            if (k2 == 0) k2 = 1.0;
-            re = 0; im = k[dd] / k2;
-            break;
-        case PMB_TF_INV_LAPLACE:
-            if (k2 == 0) k2 = 1.0;
-            re = -1. / k2;
-            break;
-        case PMB_TF_GAUSS_LOWPASS:
-            re = exp(-0.5 * k2 * (a.p0 * a.p0));
-            break;
-        case PMB_TF_COMPENSATE: {
-            double tf = 1.0;
-            for (int d = pad; d < 3; d++) {
-                const double w = k[d] * a.box[d] / (double) a.n[d];
-                double s = 1.0;
-                if (a.win_p) {
-                    const double b = pmb_sinc_unnormed(0.5 * (w / a.win_vfactor));
-                    s = b;
-                    for (int j = 1; j < a.win_p; j++) s = s * b;
-                }
-                tf = tf * s;
+        const double kA = a.P == 1 ? a.ktab[0][i0] : a.ktab[2][i2];
+        const double kB = a.ktab[1][i1];
+        for (int64_t c = threadIdx.x; c < rowlen; c += blockDim.x) {
+            const int64_t t = row * rowlen + c;
+            if (a.P == 1) {
+                const int64_t idir = a.dd == 0 ? i0 : (a.dd == 1 ? i1 : c);
+                pmb_tf_apply<C>(in, out, t, a, kA, kB, a.ktab[2][c], idir, i0, i1, c);
+            } else {
+                const int64_t idir = a.dd == 0 ? c : (a.dd == 1 ? i1 : i2);
+                pmb_tf_apply<C>(in, out, t, a, a.ktab[0][c], kB, kA, idir, c, i1, i2);
             }
-            re = 1.0 / tf;
-        } break;
-        case PMB_TF_IK:
-            re = 0; im = k[dd];
-            break;
         }
-        const C v = in[t];
-        C o;
-        o.x = (decltype(o.x)) ((double) v.x * re - (double) v.y * im);
-        o.y = (decltype(o.y)) ((double) v.x * im + (double) v.y * re);
-        out[t] = o;
     }
 }
 
@@ -534,31 +538,75 @@ extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_
     PMB_REQUIRE(f && boxsize_h && in && out, "null argument");
     PMB_REQUIRE(kind >= PMB_TF_SCALE && kind <= PMB_TF_IK, "unknown transfer kind %d", kind);
     PMB_REQUIRE(dir >= 0 && dir < f->ndim, "bad direction %d", dir);
-    TfArgs a;
-    memset(&a, 0, sizeof(a));
-    a.kind = kind; a.dir = dir; a.ndim = f->ndim; a.P = f->P;
-    for (int d = 0; d < 3; d++) { a.n[d] = f->n[d]; a.box[d] = 1.0; }
-    for (int d = 0; d < f->ndim; d++) a.box[3 - f->ndim + d] = boxsize_h[d];
-    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1;
-    a.p0 = params_h ? params_h[0] : 0.0;
-    a.p1 = params_h ? params_h[1] : 0.0;
-    if (kind == PMB_TF_COMPENSATE) {
-        PMB_REQUIRE(params_h, "compensation needs params = {kind, support}");
+    pmb_ctx *ctx = f->ctx;
+    const int pad = 3 - f->ndim;
+    double box[3] = {1.0, 1.0, 1.0};
+    for (int d = 0; d < f->ndim; d++) box[pad + d] = boxsize_h[d];
+    const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
+    // host tables: [k0 | k1 | k2 | mult]
+    double *h = (double *) malloc(sizeof(double) * 2 * ntab);
+    if (!h) return PMB_ENOMEM;
+    int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
+    for (int d = 0; d < 3; d++)
+        for (int64_t i = 0; i < f->n[d]; i++) h[off[d] + i] = d < pad ? 0.0 : host_wavenumber(i, f->n[d], box[d]);
+    double *m = h + ntab;
+    const int dd = dir + pad;
+    int rc = PMB_OK;
+    if (kind == PMB_TF_GRAVITY_FD4) {
+        // kfinite = 1/C * 1/6 * (8 sin w - sin 2w), w = k C   (examples/nbody.py:166-168)
+        const double Cc = box[dd] / (double) f->n[dd];
+        for (int64_t i = 0; i < f->n[dd]; i++) {
+            const double w = h[off[dd] + i] * Cc;
+            m[i] = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
+        }
+    } else if (kind == PMB_TF_GRADIENT_K || kind == PMB_TF_IK) {
+        for (int64_t i = 0; i < f->n[dd]; i++) m[i] = h[off[dd] + i];
+    } else if (kind == PMB_TF_COMPENSATE) {
+        if (!params_h) { free(h); pmb_set_error("compensation needs params = {kind, support}"); return PMB_EINVAL; }
         PmbWindow w;
-        PMB_CHECK(pmb_resolve_window(NULL, (int) params_h[0], (int) params_h[1], 0, NULL, &w, 0));
+        rc = pmb_resolve_window(NULL, (int) params_h[0], (int) params_h[1], 0, NULL, &w, 0);
+        if (rc != PMB_OK) { free(h); return rc; }
         PmbWinInfo info;
         pmb_window_info(w.nativesupport, (double) (int) params_h[1], &info);
-        a.win_vfactor = info.vfactor;
-        a.win_p = w.family == PMB_FAM_NEAREST ? 1 : w.family == PMB_FAM_LINEAR ? 2
-                  : w.family == PMB_FAM_QUADRATIC ? 3 : w.family == PMB_FAM_CUBIC ? 4 : 0;
+        const int p = w.family == PMB_FAM_NEAREST ? 1 : w.family == PMB_FAM_LINEAR ? 2
+                      : w.family == PMB_FAM_QUADRATIC ? 3 : w.family == PMB_FAM_CUBIC ? 4 : 0;
+        for (int d = 0; d < 3; d++)
+            for (int64_t i = 0; i < f->n[d]; i++) {
+                double s = 1.0;
+                if (p && d >= pad) {
+                    const double wv = h[off[d] + i] * box[d] / (double) f->n[d];
+                    const double b = host_sinc_unnormed(0.5 * (wv / info.vfactor));
+                    s = b;
+                    for (int j = 1; j < p; j++) s = s * b;
+                }
+                m[off[d] + i] = s;
+            }
     }
-    const int64_t total = f->P == 1 ? f->n[0] * f->n[1] * f->nc : f->m1 * f->nc * f->n[0];
-    if (total == 0) return PMB_OK;
-    pmb_ctx *ctx = f->ctx;
+    void *dev;
+    rc = pmb_scratch(ctx, sizeof(double) * 2 * ntab, &dev);
+    if (rc != PMB_OK) { free(h); return rc; }
+    cudaError_t e = cudaMemcpyAsync(dev, h, sizeof(double) * 2 * ntab, cudaMemcpyHostToDevice, ctx->stream);
+    free(h);     // pageable source: the copy was staged before cudaMemcpyAsync returned
+    if (e != cudaSuccess) return pmb_cuda_fail(e, "transfer tables", __FILE__, __LINE__);
+
+    TfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kind = kind; a.ndim = f->ndim; a.P = f->P; a.dd = dd;
+    for (int d = 0; d < 3; d++) { a.n[d] = f->n[d]; a.ktab[d] = (const double *) dev + off[d]; }
+    a.mtab = (const double *) dev + ntab;
+    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1;
+    a.p0 = params_h ? params_h[0] : 0.0;
+    int64_t nrows, rowlen;
+    if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
+    else { nrows = f->m1 * f->nc; rowlen = f->n[0]; }
+    if (nrows == 0 || rowlen == 0) return PMB_OK;
+    int64_t grid = nrows;
+    const int64_t cap = (int64_t) ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
     if (f->elsize == 8)
-        pmb_k_transfer<double2><<<pmb_grid(ctx, total, 256, 8), 256, 0, ctx->stream>>>((const double2 *) in, (double2 *) out, total, a);
+        pmb_k_transfer<double2><<<(int) grid, 256, 0, ctx->stream>>>((const double2 *) in, (double2 *) out, nrows, rowlen, a);
     else
-        pmb_k_transfer<float2><<<pmb_grid(ctx, total, 256, 8), 256, 0, ctx->stream>>>((const float2 *) in, (float2 *) out, total, a);
+        pmb_k_transfer<float2><<<(int) grid, 256, 0, ctx->stream>>>((const float2 *) in, (float2 *) out, nrows, rowlen, a);
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }

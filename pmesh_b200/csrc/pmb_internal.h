@@ -100,3 +100,23 @@ PMB_HD void pmb_st_real(void *base, int64_t byteoff, int elsize, double v)
     char *p = (char *) base + byteoff;
     if (elsize == 8) *(double *) p = v; else *(float *) p = (float) v;
 }
+// streaming variants for per-particle columns that are touched exactly once per kernel: evict-first
+// in L2 so that the 3x larger particle stream does not push the mesh lines out (ld.global.cs / st.global.cs)
+PMB_HD double pmb_ld_real_stream(const void *base, int64_t byteoff, int elsize)
+{
+    const char *p = (const char *) base + byteoff;
+#ifdef __CUDA_ARCH__
+    return elsize == 8 ? __ldcs((const double *) p) : (double) __ldcs((const float *) p);
+#else
+    return elsize == 8 ? *(const double *) p : (double) *(const float *) p;
+#endif
+}
+PMB_HD void pmb_st_real_stream(void *base, int64_t byteoff, int elsize, double v)
+{
+    char *p = (char *) base + byteoff;
+#ifdef __CUDA_ARCH__
+    if (elsize == 8) __stcs((double *) p, v); else __stcs((float *) p, (float) v);
+#else
+    if (elsize == 8) *(double *) p = v; else *(float *) p = (float) v;
+#endif
+}

@@ -89,7 +89,7 @@ pmb_k_readout_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, 
         pmb_for_points_fixed<NDIM, FAM>(A, [&](int, int64_t off, double v0, double v1, double v2) {
             if (off != PMB_OFF_INVALID) value += pmb_mesh_ld<MeshT>(mesh, off) * ((v0 * v1) * v2);
         });
-        pmb_st_real(out, i * out_stride, out_elsize, value);
+        pmb_st_real_stream(out, i * out_stride, out_elsize, value);
     }
 }
 
@@ -117,7 +117,7 @@ pmb_k_readout_dyn(PmbGeom g, PmbWindow w, PmbParticles p, const char *mesh, int6
         } else {
             pmb_for_points_wide<NDIM>(g, w, info, g.order, x, acc);
         }
-        pmb_st_real(out, i * out_stride, out_elsize, value);
+        pmb_st_real_stream(out, i * out_stride, out_elsize, value);
     }
 }
 
@@ -165,9 +165,9 @@ pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t np
                 }
             }
         }
-        if (out) pmb_st_real(out, i * out_stride, out_elsize, value);
+        if (out) pmb_st_real_stream(out, i * out_stride, out_elsize, value);
 #pragma unroll
-        for (int d = 0; d < NDIM; d++) pmb_st_real(grad, i * gs0 + d * gs1, out_elsize, gr[d]);
+        for (int d = 0; d < NDIM; d++) pmb_st_real_stream(grad, i * gs0 + d * gs1, out_elsize, gr[d]);
     }
 }
 

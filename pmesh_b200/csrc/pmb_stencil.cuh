@@ -28,15 +28,15 @@ template <int NDIM>
 PMB_HD void pmb_load_pos(const PmbParticles &p, int64_t i, double *x)
 {
 #pragma unroll
-    for (int d = 0; d < NDIM; d++) x[d] = pmb_ld_real(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize);
+    for (int d = 0; d < NDIM; d++) x[d] = pmb_ld_real_stream(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize);
 }
 PMB_HD double pmb_load_mass(const PmbParticles &p, int64_t i)
 {
-    return p.mass ? pmb_ld_real(p.mass, i * p.ms, p.mass_elsize) : p.mass_scalar;
+    return p.mass ? pmb_ld_real_stream(p.mass, i * p.ms, p.mass_elsize) : p.mass_scalar;
 }
 PMB_HD double pmb_load_hsml(const PmbParticles &p, int64_t i)
 {
-    return p.hsml ? pmb_ld_real(p.hsml, i * p.hs, p.hsml_elsize) : p.hsml_scalar;
+    return p.hsml ? pmb_ld_real_stream(p.hsml, i * p.hs, p.hsml_elsize) : p.hsml_scalar;
 }
 
 template <int FAM>

@@ -187,6 +187,8 @@ class Field(NDArrayLike):
         self.start = numpy.array(start, dtype='intp')
         self._layout_strides = tuple(int(s) * self._dtype.itemsize for s in estrides)
         self.size = int(numpy.prod(self.shape, dtype='i8'))
+        # number of reals the padded real layout spans: shape[0] * (stride of axis 0)
+        self._padded_reals = int(self.shape[0]) * int(estrides[0]) if len(self.shape) > 1 else int(2 * (pm.Nmesh[-1] // 2 + 1))
         self._dev = DeviceArray(self.shape, self._dtype, ptr=base.dev.ptr, strides=self._layout_strides,
                                 base=base.dev, ctx=pm.ctx)
         # host mirror (lazily allocated); a fresh field is all zeros on the device
@@ -270,14 +272,15 @@ class Field(NDArrayLike):
     def fill(self, value=0.0):
         """set every value (device)"""
         ctx = self.pm.ctx
-        if isinstance(self, RealField):
+        if value == 0:
+            # the whole allocation, padding included: one memset
+            ctx.memset(self._base.dev.ptr, 0, self._base.dev.nbytes)
+        elif isinstance(self, RealField):
             sz = (ctypes.c_int64 * 3)(*self.shape)
             st = (ctypes.c_int64 * 3)(*self._layout_strides)
             _lib.check(ctx.lib.pmb_field_fill(ctx.handle, self._dev.ptr, self.pm.dtype.itemsize, self.ndim, sz, st, float(value)))
         else:
-            if value != 0:
-                raise NotImplementedError
-            ctx.memset(self._base.dev.ptr, 0, self._base.dev.nbytes)
+            raise NotImplementedError
         self._mark_device_written()
         return self
 
@@ -285,14 +288,12 @@ class Field(NDArrayLike):
         """value[...] *= factor on the device (the `rho[...] *= fac` step of the force, nbody.py:205-207)"""
         ctx = self.pm.ctx
         d = self._device()
-        if isinstance(self, RealField):
-            sz = (ctypes.c_int64 * 3)(*self.shape)
-            st = (ctypes.c_int64 * 3)(*self._layout_strides)
-            _lib.check(ctx.lib.pmb_field_scale(ctx.handle, d.ptr, self.pm.dtype.itemsize, 0, self.ndim, sz, st, float(factor)))
-        else:
-            n = (ctypes.c_int64 * 3)(2 * self.size)
-            st = (ctypes.c_int64 * 3)(self.pm.dtype.itemsize)
-            _lib.check(ctx.lib.pmb_field_scale(ctx.handle, d.ptr, self.pm.dtype.itemsize, 0, 1, n, st, float(factor)))
+        # flat over the dense storage (for real fields this includes the r2c padding, harmlessly)
+        es = self.pm.dtype.itemsize
+        nreal = self._padded_reals if isinstance(self, RealField) else 2 * self.size
+        n = (ctypes.c_int64 * 3)(nreal)
+        st = (ctypes.c_int64 * 3)(es)
+        _lib.check(ctx.lib.pmb_field_scale(ctx.handle, d.ptr, es, 0, 1, n, st, float(factor)))
         self._mark_device_written()
         return self
 

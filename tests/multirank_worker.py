@@ -1,0 +1,102 @@
+"""Worker of tests/test_gpu_multirank.py: run under torch.distributed.run with one process per GPU.
+
+Checks the NCCL legs (particle alltoallv, ghost reduction, slab FFT transposes) against the oracle's
+all-ranks simulation: every rank regenerates all ranks' inputs from seeds, computes what it should
+receive / hold with the oracle, and compares with what the library delivered.
+"""
+import os
+import sys
+
+import numpy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import oracle  # noqa: E402
+from pmesh_b200 import comm as C, transfer as T  # noqa: E402
+from pmesh_b200.device import DeviceArray  # noqa: E402
+from pmesh_b200.pm import ParticleMesh  # noqa: E402
+
+
+def rel(a, b):
+    return abs(numpy.asarray(a) - numpy.asarray(b)).max() / max(abs(numpy.asarray(b)).max(), 1e-300)
+
+
+def main():
+    comm = C.world()
+    P, r = comm.size, comm.rank
+    assert P > 1
+    for n, res, dtype in ((16, "cic", "f8"), (24, "tsc", "f8"), (16, "cic", "f4"), (20, "pcs", "f8")):
+        L = 100.0
+        pm = ParticleMesh(BoxSize=L, Nmesh=[n, n, n], dtype=dtype, resampler=res, comm=comm)
+        tol = 1e-6 if dtype == "f8" else 2e-4
+        start, shape = pm._layout["i_start"], pm._layout["i_shape"]
+        edges = pm.domain.edges
+        # every rank's particles, reproducible everywhere
+        allpos = [numpy.random.default_rng(100 + q).uniform(-0.2 * L, 1.2 * L, (3000 + 100 * q, 3)) for q in range(P)]
+        allmass = [numpy.random.default_rng(200 + q).uniform(0.5, 2.0, len(allpos[q])) for q in range(P)]
+        sm = 0.5 * pm.resampler.support
+        lays = [oracle.decompose(allpos[q], edges, P, smoothing=sm, assign=pm.domain.DomainAssign, scale=n / L)
+                for q in range(P)]
+
+        # 1. routing + exchange over NCCL, bit exact
+        layout = pm.decompose(allpos[r])
+        assert numpy.array_equal(layout.sendcounts, lays[r][0]) and numpy.array_equal(layout.indices, lays[r][1])
+        want_pos = oracle.exchange_all(allpos, lays)[r]
+        want_mass = oracle.exchange_all(allmass, lays)[r]
+        lpos, lmass = layout.exchange(allpos[r], allmass[r])
+        assert numpy.array_equal(lpos, want_pos) and numpy.array_equal(lmass, want_mass)
+        dl = layout.exchange(DeviceArray.from_host(allpos[r]))
+        assert numpy.array_equal(dl.to_host(), want_pos)
+
+        # 2. decomposed deterministic paint == oracle paint of the received particles into the slab
+        rho = pm.paint(allpos[r], mass=allmass[r], layout=layout, mode="deterministic")
+        slab = numpy.zeros(tuple(shape), dtype)
+        oracle.paint(slab, want_pos, res, mass=want_mass, scale=n / L, translate=-start, period=[n] * 3)
+        assert numpy.array_equal(rho.value, slab), "decomposed paint differs"
+        full = numpy.concatenate(comm.allgather(slab), axis=0)
+        serial = numpy.zeros((n, n, n), dtype)
+        oracle.paint(serial, numpy.concatenate(allpos), res, mass=numpy.concatenate(allmass), scale=n / L, period=[n] * 3)
+        assert rel(full, serial) < (1e-12 if dtype == "f8" else 1e-5)          # not bit-equal by design
+
+        # 3. distributed r2c / c2r against numpy on the gathered field
+        ck_full = oracle.r2c(full.astype("f8"))
+        rhok = rho.r2c()
+        s1, m1 = rhok.start[1], rhok.shape[1]
+        assert rhok.shape == (n, m1, n // 2 + 1)
+        assert rel(rhok.value, ck_full[:, s1:s1 + m1, :]) < tol
+        back = rhok.c2r()
+        assert rel(back.value, slab) < tol
+        assert rel(rhok.value, ck_full[:, s1:s1 + m1, :]) < tol          # input preserved
+        rip = pm.create("real", value=slab)
+        cip = rip.r2c(out=Ellipsis)
+        assert rel(cip.value, ck_full[:, s1:s1 + m1, :]) < tol
+        assert rel(cip.c2r(out=Ellipsis).value, slab) < tol
+
+        # 4. transfer + c2r + readout with ghost reduction == serial oracle pipeline
+        for d in range(3):
+            fr_full = oracle.c2r(oracle.transfer(ck_full, [n] * 3, [L] * 3, "gravity_fd4", d), [n] * 3)
+            f = rhok.apply(T.GravityFD4(d)).c2r()
+            assert rel(f.value, fr_full[start[0]:start[0] + shape[0]]) < tol
+            got = f.readout(allpos[r], layout=layout)
+            want = oracle.readout(fr_full.astype(dtype), allpos[r], res, scale=n / L, period=[n] * 3)
+            assert rel(got, want) < tol, rel(got, want)
+            gd = f.readout(DeviceArray.from_host(allpos[r]), layout=layout)
+            assert numpy.array_equal(gd.to_host(), got)
+
+        # 5. gather modes on real ghosts (tests/test_domain.py:229-266 semantics)
+        ones = numpy.ones(layout.recvlength)
+        nghost = layout.gather(ones, mode="sum")
+        assert nghost.min() >= 1 and abs(nghost.sum() - lays[r][0].sum()) < 1e-9
+        assert numpy.array_equal(layout.gather(lpos, mode="any"), allpos[r])
+        assert numpy.allclose(layout.gather(lpos, mode="mean"), allpos[r])
+        comm.Barrier()
+        if r == 0:
+            print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
+    comm.Barrier()
+    print("rank %d done" % r)
+
+
+if __name__ == "__main__":
+    main()
