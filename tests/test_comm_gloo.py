@@ -64,7 +64,7 @@ WORKER = textwrap.dedent("""
     oracle.paint(serial, numpy.concatenate([allpos[0], allpos[1]]), "cic", period=[n, n, n])
     assert abs(full - serial).max() < 1e-13, abs(full - serial).max()
     assert abs(full.sum() - 800) < 1e-9
-    sys.stdout.write("rank%d-ok\n" % r); sys.stdout.flush()
+    sys.stdout.write("rank%%d-ok\\n" %% r); sys.stdout.flush()
 """)
 
 
