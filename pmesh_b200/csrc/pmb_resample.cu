@@ -14,26 +14,55 @@
 #include "pmb_stencil.cuh"
 
 // ------------------------------------------------------------------ atomic paint
-template <typename MeshT>
-__device__ __forceinline__ void pmb_red_add(char *mesh, int64_t off, double f)
+// L2 residency control: mesh cells are re-touched by particles of neighbouring lattice rows /
+// planes, the particle columns are touched once.  Mesh accesses carry an evict_last policy, the
+// particle stream is loaded with ld.global.cs (evict-first), so the stream cannot push the mesh
+// working set out of L2.  PMB_CACHE_MODE=0 disables the mesh policy (for A/B measurements).
+static int pmb_cache_mode(void)
 {
-    atomicAdd((MeshT *) (mesh + off), (MeshT) f);
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("PMB_CACHE_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
 }
 
-template <typename MeshT, int NDIM, int FAM>
+__device__ __forceinline__ uint64_t pmb_policy_evict_last(void)
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+template <typename MeshT>
+__device__ __forceinline__ void pmb_red_add(char *mesh, int64_t off, double f, uint64_t policy, int hint)
+{
+    if (hint) {
+        if (sizeof(MeshT) == 8)
+            asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(mesh + off), "d"(f), "l"(policy) : "memory");
+        else
+            asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(mesh + off), "f"((float) f), "l"(policy) : "memory");
+    } else {
+        atomicAdd((MeshT *) (mesh + off), (MeshT) f);
+    }
+}
+
+template <typename MeshT, int NDIM, int FAM, bool CHECK>
 __global__ void __launch_bounds__(256)
-pmb_k_paint_tuned(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix)
+pmb_k_paint_tuned(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix, int hint)
 {
     int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const uint64_t policy = pmb_policy_evict_last();
     for (; i < npart; i += stride) {
         double x[NDIM];
         pmb_load_pos<NDIM>(p, i, x);
         const double m = pmb_load_mass(p, i);
         PmbAxes<NDIM, FAM> A;
-        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
-        pmb_for_points_fixed<NDIM, FAM>(A, [&](int, int64_t off, double v0, double v1, double v2) {
-            if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(true, m, v0, v1, v2));
+        pmb_axes_tuned<NDIM, FAM, CHECK>(g, g.order, x, pcsfix, A);
+        pmb_for_points_fixed<NDIM, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+            if (!CHECK || off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(true, m, v0, v1, v2), policy, hint);
         });
     }
 }
@@ -56,11 +85,11 @@ pmb_k_paint_dyn(PmbGeom g, PmbWindow w, PmbParticles p, char *mesh, int64_t npar
             pmb_axes_dyn<NDIM>(g, w, info, g.order, x, pcsfix, A);
             const bool tuned = A.tuned;
             pmb_for_points_dyn<NDIM, PMB_MAX_SUPPORT>(A, [&](int, int64_t off, double v0, double v1, double v2) {
-                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(tuned, m, v0, v1, v2));
+                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(tuned, m, v0, v1, v2), 0, 0);
             });
         } else {
             pmb_for_points_wide<NDIM>(g, w, info, g.order, x, [&](int, int64_t off, double v0, double v1, double v2) {
-                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(false, m, v0, v1, v2));
+                if (off != PMB_OFF_INVALID) pmb_red_add<MeshT>(mesh, off, pmb_paint_value(false, m, v0, v1, v2), 0, 0);
             });
         }
     }
@@ -73,21 +102,37 @@ __device__ __forceinline__ double pmb_mesh_ld(const char *mesh, int64_t off)
     return (double) __ldg((const MeshT *) (mesh + off));
 }
 
-template <typename MeshT, int NDIM, int FAM>
+template <typename MeshT>
+__device__ __forceinline__ double pmb_mesh_ld_hint(const char *mesh, int64_t off, uint64_t policy, int hint)
+{
+    if (!hint) return (double) __ldg((const MeshT *) (mesh + off));
+    if (sizeof(MeshT) == 8) {
+        double v;
+        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(mesh + off), "l"(policy));
+        return v;
+    } else {
+        float v;
+        asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(mesh + off), "l"(policy));
+        return (double) v;
+    }
+}
+
+template <typename MeshT, int NDIM, int FAM, bool CHECK>
 __global__ void __launch_bounds__(256)
 pmb_k_readout_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
-                    void *out, int out_elsize, int64_t out_stride)
+                    void *out, int out_elsize, int64_t out_stride, int hint)
 {
     int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const uint64_t policy = pmb_policy_evict_last();
     for (; i < npart; i += stride) {
         double x[NDIM];
         pmb_load_pos<NDIM>(p, i, x);
         PmbAxes<NDIM, FAM> A;
-        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+        pmb_axes_tuned<NDIM, FAM, CHECK>(g, g.order, x, pcsfix, A);
         double value = 0;
-        pmb_for_points_fixed<NDIM, FAM>(A, [&](int, int64_t off, double v0, double v1, double v2) {
-            if (off != PMB_OFF_INVALID) value += pmb_mesh_ld<MeshT>(mesh, off) * ((v0 * v1) * v2);
+        pmb_for_points_fixed<NDIM, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+            if (!CHECK || off != PMB_OFF_INVALID) value += pmb_mesh_ld_hint<MeshT>(mesh, off, policy, hint) * ((v0 * v1) * v2);
         });
         pmb_st_real_stream(out, i * out_stride, out_elsize, value);
     }
@@ -123,7 +168,7 @@ pmb_k_readout_dyn(PmbGeom g, PmbWindow w, PmbParticles p, const char *mesh, int6
 
 // fused value + NDIM gradients: one sweep over the neighbourhood, four accumulators.  Each
 // accumulator sees the same addends in the same order as a separate readout(gradient=d) would.
-template <typename MeshT, int NDIM, int FAM>
+template <typename MeshT, int NDIM, int FAM, bool CHECK>
 __global__ void __launch_bounds__(256)
 pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
                          void *out, int out_elsize, int64_t out_stride,
@@ -137,8 +182,8 @@ pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t np
         double x[NDIM];
         pmb_load_pos<NDIM>(p, i, x);
         PmbAxes<NDIM, FAM> A, D;
-        pmb_axes_tuned<NDIM, FAM>(g, zero, x, pcsfix, A);
-        pmb_axes_tuned<NDIM, FAM>(g, one, x, pcsfix, D);
+        pmb_axes_tuned<NDIM, FAM, CHECK>(g, zero, x, pcsfix, A);
+        pmb_axes_tuned<NDIM, FAM, CHECK>(g, one, x, pcsfix, D);
         double value = 0, gr[3] = {0, 0, 0};
         // walk the stencil by ordinal to address both weight sets
         int ord = 0;
@@ -151,7 +196,7 @@ pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t np
                     int64_t o0 = A.off[0][a];
                     int64_t o1 = NDIM > 1 ? A.off[NDIM > 1 ? 1 : 0][b] : 0;
                     int64_t o2 = NDIM > 2 ? A.off[NDIM > 2 ? 2 : 0][c] : 0;
-                    if (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID || o2 == PMB_OFF_INVALID) continue;
+                    if (CHECK && (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID || o2 == PMB_OFF_INVALID)) continue;
                     const double mval = pmb_mesh_ld<MeshT>(mesh, o0 + o1 + o2);
                     const double v0 = A.V[0][a], d0 = D.V[0][a];
                     const double v1 = NDIM > 1 ? A.V[NDIM > 1 ? 1 : 0][b] : 1.0;
@@ -192,10 +237,10 @@ pmb_k_expand_tuned(PmbGeom g, PmbParticles p, int64_t first, int64_t count, int 
         pmb_load_pos<NDIM>(p, i, x);
         const double m = pmb_load_mass(p, i);
         PmbAxes<NDIM, FAM> A;
-        pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
+        pmb_axes_tuned<NDIM, FAM, true>(g, g.order, x, pcsfix, A);
         KeyT *kk = keys + j * npts;
         double *vv = vals + j * npts;
-        pmb_for_points_fixed<NDIM, FAM>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+        pmb_for_points_fixed<NDIM, FAM, true>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
             kk[ord] = off == PMB_OFF_INVALID ? (KeyT) ~(KeyT) 0 : (KeyT) off;
             vv[ord] = pmb_paint_value(true, m, v0, v1, v2);
         });
@@ -298,6 +343,7 @@ static int check_args(pmb_ctx *ctx, const pmb_resample_args *a, int need_out)
         PMB_REQUIRE(a->out_elsize == 4 || a->out_elsize == 8, "out must be float32 or float64");
     }
     for (int d = 0; d < a->ndim; d++) {
+        PMB_REQUIRE(a->size[d] < ((int64_t) 1 << 31) && a->period[d] < ((int64_t) 1 << 31), "canvas extent / period must be < 2^31");
         PMB_REQUIRE(a->size[d] >= 0, "negative canvas size");
         PMB_REQUIRE(a->order[d] >= 0, "negative order");
     }
@@ -343,6 +389,10 @@ static int fixed_family(const PmbWindow &w, const pmb_resample_args *a)
     default: { constexpr int FAM = 4; CALL; } break;        \
     }
 
+#define PMB_DISPATCH_CHECK(CHECKV, CALL)                    \
+    if (CHECKV) { constexpr bool CHECK = true; CALL; }      \
+    else { constexpr bool CHECK = false; CALL; }
+
 #define PMB_DISPATCH_NDIM(NDIMV, CALL)                      \
     switch (NDIMV) {                                        \
     case 1: { constexpr int NDIM = 1; CALL; } break;        \
@@ -358,8 +408,9 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
     char *mesh = (char *) a->mesh;
     if (fam) {
         int grid = pmb_grid(ctx, a->npart, 256, 8);
-        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
-            (pmb_k_paint_tuned<MeshT, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix))));
+        const bool chk = pmb_geom_needs_check(g);
+        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_paint_tuned<MeshT, NDIM, FAM, CHECK><<<grid, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix, pmb_cache_mode() & 1)))));
     } else {
         int grid = pmb_grid(ctx, a->npart, 128, 8);
         PMB_DISPATCH_NDIM(a->ndim,
@@ -504,9 +555,10 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
     const char *mesh = (const char *) a->mesh;
     if (fam) {
         int grid = pmb_grid(ctx, a->npart, 256, 8);
-        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
-            (pmb_k_readout_tuned<MeshT, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
-                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride))));
+        const bool chk = pmb_geom_needs_check(g);
+        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_tuned<MeshT, NDIM, FAM, CHECK><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, pmb_cache_mode() & 1)))));
     } else {
         int grid = pmb_grid(ctx, a->npart, 128, 8);
         PMB_DISPATCH_NDIM(a->ndim,
@@ -563,14 +615,15 @@ extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *
     }
     const char *mesh = (const char *) a->mesh;
     int grid = pmb_grid(ctx, a->npart, 256, 8);
+    const bool chk = pmb_geom_needs_check(g);
     if (a->mesh_elsize == 8) {
-        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
-            (pmb_k_readout_grad_tuned<double, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
-                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1))));
+        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_grad_tuned<double, NDIM, FAM, CHECK><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1)))));
     } else {
-        PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
-            (pmb_k_readout_grad_tuned<float, NDIM, FAM><<<grid, 256, 0, ctx->stream>>>(
-                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1))));
+        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_NDIM(a->ndim, PMB_DISPATCH_FAM(fam, NDIM,
+            (pmb_k_readout_grad_tuned<float, NDIM, FAM, CHECK><<<grid, 256, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1)))));
     }
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;

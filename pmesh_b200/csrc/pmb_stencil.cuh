@@ -48,10 +48,21 @@ PMB_HD void pmb_axis_tuned(double X, int order, double scale, int pcsfix, int *I
     else pmb_axis_pcs(X, order, scale, I, V, pcsfix);
 }
 
-// tuned stencil with compile-time support FAM (1 nnb, 2 cic, 3 tsc, 4 pcs)
-template <int NDIM, int FAM>
+// true when some stencil point can fall outside the local canvas: a non-periodic axis, or a canvas
+// that is a slab of the periodic mesh.  Otherwise (single-rank periodic mesh) the kernels skip
+// every bounds test.
+static inline bool pmb_geom_needs_check(const PmbGeom &g)
+{
+    for (int d = 0; d < g.ndim; d++)
+        if (g.period[d] <= 0 || g.size[d] != g.period[d]) return true;
+    return false;
+}
+
+// tuned stencil with compile-time support FAM (1 nnb, 2 cic, 3 tsc, 4 pcs).  The FAM mesh indices
+// of an axis are consecutive: wrap the first, then step with a compare (no division).
+template <int NDIM, int FAM, bool CHECK>
 PMB_HD void pmb_axes_tuned(const PmbGeom &g, const int *order, const double *x, int pcsfix,
-                                               PmbAxes<NDIM, FAM> &A)
+                           PmbAxes<NDIM, FAM> &A)
 {
     A.S = FAM;
     A.tuned = true;
@@ -60,10 +71,16 @@ PMB_HD void pmb_axes_tuned(const PmbGeom &g, const int *order, const double *x, 
         double X = pmb_gridpos(x[d], g.scale[d], g.translate[d]);
         int I[FAM];
         pmb_axis_tuned<FAM>(X, order[d], g.scale[d], pcsfix, I, A.V[d]);
+        const int per = (int) g.period[d];
+        const int sz = (int) g.size[d];
+        int t = I[0];
+        if (per > 0) t = pmb_wrap32(t, per);
 #pragma unroll
         for (int s = 0; s < FAM; s++) {
-            int64_t t = pmb_wrap_clip(I[s], g.period[d], g.size[d]);
-            A.off[d][s] = t < 0 ? PMB_OFF_INVALID : t * g.strides[d];
+            const bool ok = !CHECK || (t >= 0 && t < sz);
+            A.off[d][s] = ok ? (int64_t) t * g.strides[d] : PMB_OFF_INVALID;
+            t += 1;
+            if (per > 0 && t == per) t = 0;
         }
     }
 }
@@ -109,7 +126,7 @@ PMB_HD void pmb_axes_dyn(const PmbGeom &g, const PmbWindow &w, const PmbWinInfo 
 
 // visit all S^NDIM points in C order: f(ordinal, offset_or_INVALID, v0, v1, v2)
 // FIXED: compile-time support SMAX, fully unrolled (tuned kernels).
-template <int NDIM, int SMAX, class F>
+template <int NDIM, int SMAX, bool CHECK, class F>
 PMB_HD void pmb_for_points_fixed(const PmbAxes<NDIM, SMAX> &A, F &&f)
 {
     int ord = 0;
@@ -122,14 +139,14 @@ PMB_HD void pmb_for_points_fixed(const PmbAxes<NDIM, SMAX> &A, F &&f)
 #pragma unroll
             for (int b = 0; b < SMAX; b++) {
                 const int64_t o1 = A.off[NDIM > 1 ? 1 : 0][b];
-                const bool bad01 = (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID);
+                const bool bad01 = CHECK && (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID);
                 if (NDIM == 2) {
                     f(ord++, bad01 ? PMB_OFF_INVALID : o0 + o1, A.V[0][a], A.V[NDIM > 1 ? 1 : 0][b], 1.0);
                 } else {
 #pragma unroll
                     for (int c = 0; c < SMAX; c++) {
                         const int64_t o2 = A.off[NDIM > 2 ? 2 : 0][c];
-                        const int64_t o = (bad01 || o2 == PMB_OFF_INVALID) ? PMB_OFF_INVALID : o0 + o1 + o2;
+                        const int64_t o = (CHECK && (bad01 || o2 == PMB_OFF_INVALID)) ? PMB_OFF_INVALID : o0 + o1 + o2;
                         f(ord++, o, A.V[0][a], A.V[NDIM > 1 ? 1 : 0][b], A.V[NDIM > 2 ? 2 : 0][c]);
                     }
                 }

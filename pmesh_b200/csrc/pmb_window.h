@@ -318,13 +318,32 @@ PMB_HD double pmb_axis_generic_weight(const PmbWindow &w, const PmbWinInfo &info
 }
 
 // periodic wrap then local bounds test (ref: _window_generics.h:42-55, _window_tuned_cic.h:24-31)
-// returns the wrapped index, or -1 when the point falls outside the local canvas.
+// returns the wrapped index, or -1 when the point falls outside the local canvas.  The common
+// case (at most one period away) costs a compare and an add; no integer division.
 PMB_HD int64_t pmb_wrap_clip(int64_t t, int64_t period, int64_t size)
 {
     if (period > 0) {
-        t %= period;
-        if (t < 0) t += period;
+        if (t >= period) {
+            t -= period;
+            if (t >= period) t %= period;
+        } else if (t < 0) {
+            t += period;
+            if (t < 0) { t %= period; if (t < 0) t += period; }
+        }
     }
     if (t < 0 || t >= size) return -1;
+    return t;
+}
+
+// 32-bit variant used by the tuned kernels (canvas extents are checked to be < 2^31)
+PMB_HD int pmb_wrap32(int t, int period)
+{
+    if (t >= period) {
+        t -= period;
+        if (t >= period) t %= period;
+    } else if (t < 0) {
+        t += period;
+        if (t < 0) { t %= period; if (t < 0) t += period; }
+    }
     return t;
 }

@@ -72,10 +72,16 @@ static void visit_fixed(const PmbGeom &g, const PmbParticles &p, int64_t i, int 
     pmb_load_pos<NDIM>(p, i, x);
     const double m = pmb_load_mass(p, i);
     PmbAxes<NDIM, FAM> A;
-    pmb_axes_tuned<NDIM, FAM>(g, g.order, x, pcsfix, A);
-    pmb_for_points_fixed<NDIM, FAM>(A, [&](int ord, int64_t off, double v0, double v1, double v2) {
+    auto cb = [&](int ord, int64_t off, double v0, double v1, double v2) {
         f(ord, off, pmb_paint_value(true, m, v0, v1, v2), (v0 * v1) * v2);
-    });
+    };
+    if (pmb_geom_needs_check(g)) {          // the same CHECK dispatch as the kernels
+        pmb_axes_tuned<NDIM, FAM, true>(g, g.order, x, pcsfix, A);
+        pmb_for_points_fixed<NDIM, FAM, true>(A, cb);
+    } else {
+        pmb_axes_tuned<NDIM, FAM, false>(g, g.order, x, pcsfix, A);
+        pmb_for_points_fixed<NDIM, FAM, false>(A, cb);
+    }
 }
 
 template <int NDIM, class F>
