@@ -78,6 +78,7 @@ extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->route_masks) cudaFree(ctx->route_masks);
     if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
+    if (ctx->sched_buf) cudaFree(ctx->sched_buf);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
     return PMB_OK;

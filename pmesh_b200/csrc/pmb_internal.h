@@ -44,6 +44,12 @@ struct pmb_ctx {
     int route_nblocks;
     int64_t route_per_block;
     size_t det_chunk_bytes;  // workspace budget of the deterministic paint
+    // chunk schedule of the tuned 3-D paint / readout kernels (see pmb_resample.cu)
+    void *sched_buf;
+    size_t sched_bytes;
+    int64_t sched_nchunks;
+    uint64_t sched_sig;
+    int sched_uses;
 };
 
 void pmb_set_error(const char *fmt, ...);

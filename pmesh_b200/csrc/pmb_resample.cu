@@ -11,7 +11,7 @@
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
-#include "pmb_stencil.cuh"
+#include "pmb_sched.cuh"
 
 // ------------------------------------------------------------------ atomic paint
 // L2 residency control: mesh cells are re-touched by particles of neighbouring lattice rows /
@@ -406,6 +406,21 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
 {
     const int fam = fixed_family(w, a);
     char *mesh = (char *) a->mesh;
+    if (fam && a->ndim == 3 && a->npart >= ((int64_t) 1 << 18) && pmb_env_flag("PMB_SCHED_KERNELS", 1)) {
+        // large 3-D problems: locality-scheduled chunks + warp-aggregated atomics (pmb_sched.cuh)
+        const uint32_t *order;
+        int64_t nchunks;
+        PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks));
+        const int grid = (int) (nchunks < (int64_t) ctx->sm_count * 8 ? nchunks : (int64_t) ctx->sm_count * 8);
+        const bool chk = pmb_geom_needs_check(g);
+        const bool merge = fam > 1 && pmb_env_flag("PMB_MERGE", 1);
+#define PMB_SCHED_PAINT(MERGEV) PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3, \
+            (pmb_k_paint_sched<MeshT, FAM, CHECK, MERGEV><<<grid, PMB_CHUNK, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix, order, nchunks))))
+        if (merge) { PMB_SCHED_PAINT(true); } else { PMB_SCHED_PAINT(false); }
+#undef PMB_SCHED_PAINT
+        PMB_LAUNCH_CHECK(ctx);
+        return PMB_OK;
+    }
     if (fam) {
         int grid = pmb_grid(ctx, a->npart, 256, 8);
         const bool chk = pmb_geom_needs_check(g);
@@ -553,6 +568,20 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
 {
     const int fam = fixed_family(w, a);
     const char *mesh = (const char *) a->mesh;
+    // measured on B200 (1024^3 CIC): the plain grid-stride gather (14.4 ms) beats the chunk-scheduled
+    // one (16.6 ms) -- reads do not thrash L2 the way the atomics do -- so it stays opt-in
+    if (fam && a->ndim == 3 && a->npart >= ((int64_t) 1 << 18) && pmb_env_flag("PMB_SCHED_READOUT", 0)) {
+        const uint32_t *order;
+        int64_t nchunks;
+        PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks));
+        const int grid = (int) (nchunks < (int64_t) ctx->sm_count * 8 ? nchunks : (int64_t) ctx->sm_count * 8);
+        const bool chk = pmb_geom_needs_check(g);
+        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3,
+            (pmb_k_readout_sched<MeshT, FAM, CHECK><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, order, nchunks))));
+        PMB_LAUNCH_CHECK(ctx);
+        return PMB_OK;
+    }
     if (fam) {
         int grid = pmb_grid(ctx, a->npart, 256, 8);
         const bool chk = pmb_geom_needs_check(g);

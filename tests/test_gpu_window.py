@@ -298,3 +298,32 @@ def test_large_cic_properties_and_device_arrays(W, oracle):
         assert abs(got.sum() - N ** 3) < 1e-6 * N ** 3
     r = W.CIC.readout(DeviceArray.from_host(want), dpos, transform=tr)
     assert_array_equal(r.to_host(), oracle.readout(want, pos, "cic", scale=N / 100.0, period=[N] * 3))
+
+
+@pytest.mark.parametrize("name", ["nnb", "cic", "tsc", "pcs"])
+@pytest.mark.parametrize("order", ["lattice", "random"])
+def test_scheduled_kernels_large_inputs(W, oracle, name, order):
+    """>= 2^18 particles on a 3-D mesh take the locality-scheduled kernels with warp-aggregated
+    atomics (pmb_sched.cuh): full periodic canvas and a slab (size[0] < period, translated) canvas,
+    lattice-ordered (merging lanes) and shuffled (no merging) particles, f8 and f4."""
+    from pmesh_b200.device import DeviceArray
+    N = 72
+    rng = numpy.random.default_rng(17)
+    q = numpy.indices((N, N, N)).reshape(3, -1).T + 0.5
+    pos = (q + 2.5 * numpy.sin(2 * numpy.pi * q[:, ::-1] / N) + rng.uniform(-0.2, 0.2, q.shape)) % N
+    if order == "random":
+        pos = pos[rng.permutation(len(pos))]
+    mass = rng.uniform(0.5, 2.0, len(pos))
+    dpos, dmass = DeviceArray.from_host(pos), DeviceArray.from_host(mass)
+    for shape, translate in (((N, N, N), [0.0, 0.0, 0.0]), ((20, N, N), [-30.0, 0.0, 0.0])):
+        tr = W.Affine(3, scale=1.0, translate=translate, period=N)
+        for dtype, tol in (("f8", 1e-6), ("f4", 1e-4)):
+            want = numpy.zeros(shape, dtype)
+            oracle.paint(want, pos, name, mass=mass, translate=translate, period=[N] * 3)
+            mesh = DeviceArray.zeros(shape, dtype)
+            W.windows[name].paint(mesh, dpos, mass=dmass, transform=tr, mode="atomic")
+            got = mesh.to_host()
+            assert_allclose(got, want, rtol=tol, atol=tol * abs(want).max())
+            field = rng.uniform(-1, 1, shape).astype(dtype)
+            r = W.windows[name].readout(DeviceArray.from_host(field), dpos, transform=tr)
+            assert_array_equal(r.to_host(), oracle.readout(field, pos, name, translate=translate, period=[N] * 3))
