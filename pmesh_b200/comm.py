@@ -102,10 +102,18 @@ class TorchComm(object):
         return box[0]
 
     def Alltoall(self, send, recv):
-        send = numpy.asarray(send)
-        rows = self.allgather(send.copy())
-        for r in range(self.size):
-            recv[r] = rows[r][self.rank]
+        """one item per rank (the sendcounts -> recvcounts transpose of Layout)"""
+        import torch
+        send = numpy.ascontiguousarray(send)
+        try:
+            tin = torch.from_numpy(send.astype("int64") if send.dtype.kind in "iu" else send.astype("float64"))
+            tout = torch.empty_like(tin)
+            self._dist.all_to_all_single(tout, tin, group=self._group)
+            recv[...] = tout.numpy().astype(recv.dtype)
+        except (RuntimeError, NotImplementedError):
+            rows = self.allgather(send.copy())
+            for r in range(self.size):
+                recv[r] = rows[r][self.rank]
 
     def Allreduce_inplace(self, array, op=SUM):
         array[...] = self.allreduce(numpy.array(array), op)

@@ -74,9 +74,9 @@ class Layout(object):
         self.recvoffsets = numpy.zeros_like(self.recvcounts, order='C')
 
         if recvcounts is None:
-            self.comm.Barrier()
+            # the reference brackets this Alltoall with Barriers (domain.py:112-114); the exchange of
+            # counts is itself synchronising, so they are dropped here
             self.comm.Alltoall(self.sendcounts, self.recvcounts)
-            self.comm.Barrier()
         else:
             self.recvcounts = numpy.asarray(recvcounts)
         self.sendoffsets[1:] = self.sendcounts.cumsum()[:-1]
@@ -131,7 +131,8 @@ class Layout(object):
     def _to_device_records(self, data, length, what):
         """-> (DeviceArray view as (N, itemsize) bytes, record dtype, trailing shape, was_host)"""
         if is_device(data):
-            if any(self.comm.allgather(data.shape[0] != length)):
+            # device-resident columns: local length check only (no host collective on the hot path)
+            if data.shape[0] != length:
                 raise ValueError(what)
             assert data.is_contiguous
             return data, data.dtype, data.shape[1:], False
