@@ -20,7 +20,11 @@ from pmesh_b200.pm import ParticleMesh  # noqa: E402
 
 
 def rel(a, b):
-    return abs(numpy.asarray(a) - numpy.asarray(b)).max() / max(abs(numpy.asarray(b)).max(), 1e-300)
+    a, b = numpy.asarray(a), numpy.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:          # a rank may own no mesh planes (e.g. 20 planes over 8 ranks)
+        return 0.0
+    return abs(a - b).max() / max(abs(b).max(), 1e-300)
 
 
 def main():
@@ -99,4 +103,17 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        msg = "WORKER-ERROR rank %s\n%s" % (os.environ.get("RANK"), traceback.format_exc())
+        sys.stderr.write(msg)
+        sys.stderr.flush()
+        try:        # keep the first failure readable even if the launcher truncates the output
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "multirank_error_rank%s.txt" % os.environ.get("RANK")), "w") as f:
+                f.write(msg)
+        except OSError:
+            pass
+        os._exit(1)
