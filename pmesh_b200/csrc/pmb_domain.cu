@@ -408,6 +408,7 @@ extern "C" int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const 
 // starting from 0.0.  `indices` is grouped by rank and a particle appears at most once per rank
 // segment, so one streaming pass per segment (in rank order) performs exactly those additions in
 // exactly that order without atomics: acc[indices[j]] = acc[indices[j]] + data[j].
+template <bool ASSIGN>
 __global__ void __launch_bounds__(256)
 pmb_k_gather_pass(const void *__restrict__ data, int data_elsize, int ncomp, const int32_t *__restrict__ indices,
                   int64_t begin, int64_t end, double *__restrict__ acc)
@@ -420,7 +421,7 @@ pmb_k_gather_pass(const void *__restrict__ data, int data_elsize, int ncomp, con
         const int c = ncomp == 1 ? 0 : (int) (t - j * ncomp);
         const int64_t o = (int64_t) __ldcs(indices + j) * ncomp + c;
         const double v = data_elsize == 8 ? __ldcs((const double *) data + t) : (double) __ldcs((const float *) data + t);
-        acc[o] = acc[o] + v;
+        acc[o] = ASSIGN ? 0.0 + v : acc[o] + v;
     }
 }
 
@@ -447,14 +448,24 @@ extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, i
         PMB_CHECK(pmb_scratch(ctx, sizeof(double) * n, &tmp));
         acc = (double *) tmp;
     }
-    PMB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * n, ctx->stream));
+    // A first segment that holds nout entries lists every particle exactly once (ascending, unique,
+    // < nout): it can assign `0.0 + data[j]` instead of read-modify-write, and no memset is needed.
+    bool first = true;
     for (int r = 0; r < nranks; r++) {
         const int64_t b = offsets_h[r], e = offsets_h[r + 1];
         if (e <= b) continue;
-        pmb_k_gather_pass<<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
-            data, data_elsize, ncomp, indices, b, e, acc);
+        const bool assign = first && (e - b) == nout;
+        if (first && !assign) PMB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * n, ctx->stream));
+        first = false;
+        if (assign)
+            pmb_k_gather_pass<true><<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
+                data, data_elsize, ncomp, indices, b, e, acc);
+        else
+            pmb_k_gather_pass<false><<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
+                data, data_elsize, ncomp, indices, b, e, acc);
         PMB_LAUNCH_CHECK(ctx);
     }
+    if (first) PMB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * n, ctx->stream));
     if (out_elsize == 4) {
         pmb_k_f64_to_f32<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(acc, (float *) out, n);
         PMB_LAUNCH_CHECK(ctx);

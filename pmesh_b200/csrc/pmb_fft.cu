@@ -501,13 +501,14 @@ __device__ __forceinline__ void pmb_tf_apply(const C *__restrict__ in, C *__rest
     out[t] = o;
 }
 
-// one block walks whole rows of the contiguous axis; the row -> (outer indices) split costs one
-// division per row, not per element
+// one WARP walks a whole row of the contiguous axis (512-byte coalesced accesses, at most one
+// partially filled iteration per row); the row -> (outer indices) split costs one division per row
 template <typename C>
 __global__ void __launch_bounds__(256)
 pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int64_t rowlen, TfArgs a)
 {
-    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t row = (int64_t) blockIdx.x * 8 + warp; row < nrows; row += (int64_t) gridDim.x * 8) {
         int64_t i0, i1, i2 = 0;
         if (a.P == 1) {           // (n0, n1, nc): rows = (i0, i1), inner = i2
             i1 = row % a.n[1];
@@ -519,7 +520,7 @@ pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int
         }
         const double kA = a.P == 1 ? a.ktab[0][i0] : a.ktab[2][i2];
         const double kB = a.ktab[1][i1];
-        for (int64_t c = threadIdx.x; c < rowlen; c += blockDim.x) {
+        for (int64_t c = lane; c < rowlen; c += 32) {
             const int64_t t = row * rowlen + c;
             if (a.P == 1) {
                 const int64_t idir = a.dd == 0 ? i0 : (a.dd == 1 ? i1 : c);
@@ -600,7 +601,7 @@ extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_
     if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
     else { nrows = f->m1 * f->nc; rowlen = f->n[0]; }
     if (nrows == 0 || rowlen == 0) return PMB_OK;
-    int64_t grid = nrows;
+    int64_t grid = (nrows + 7) / 8;
     const int64_t cap = (int64_t) ctx->sm_count * 8;
     if (grid > cap) grid = cap;
     if (f->elsize == 8)

@@ -1,19 +1,30 @@
-// pmb_sched.cuh -- locality-scheduled paint / readout kernels for the tuned windows on 3-D meshes.
+// pmb_sched.cuh -- chunk-scheduled paint / readout kernels for the tuned windows on 3-D meshes.
 //
-// Why: one thread per particle in memory order is only as cache-friendly as the particle order.
-// PM simulations keep particles in (displaced) lattice order, so a 256-particle chunk is a compact
-// z-segment, but two chunks that touch the SAME mesh rows (lattice planes x and x+1) are a whole
-// plane of particles apart in memory.  At 1024^3 that reuse distance (~40 MB of traffic) no longer
-// fits L2: ncu showed every mesh sector fetched ~4x and written back ~3.8x by the atomic paint.
+// Why: one thread per particle in a grid-stride loop is only as cache-friendly as the particle
+// order AND as the lock-step of the CTAs.  PM simulations keep particles in (displaced) lattice
+// order, so a 256-particle chunk is a compact z-segment, but chunks that touch the SAME mesh rows
+// (lattice planes x and x+1) are a whole plane of particles apart in memory, and a CTA that lags one
+// grid-stride iteration lags by 300k particles.  ncu at 1024^3 (profiles/): the atomic paint
+// re-fetched every mesh sector ~4x and wrote it back ~3.8x (93 GB of DRAM traffic for 34 GB of
+// algorithmic bytes); the gather re-read the mesh 2.5x.
 //
-// What: (1) a CHUNK SCHEDULE -- each 256-particle chunk gets a spatial key from its first particle,
-// (y-block, x, y, z), the ~Np/256 keys are radix sorted (library: cub, a few hundred microseconds)
-// and CTAs walk chunks in key order, so chunks that are neighbours in space are neighbours in time
-// (reuse distance: 32 rows instead of a plane).  The schedule is only a traversal order: any
-// permutation of the chunks is correct, so a stale schedule costs speed, never correctness.
-// (2) WARP-AGGREGATED ATOMICS along the contiguous mesh axis -- lanes whose stencils are shifted by
-// c cells hand their overlapping contributions to the lane that owns the cell (shuffle), which
-// issues ONE red.global.add per cell of the warp instead of one per (particle, stencil point).
+// What:
+// (1) CHUNKS + DYNAMIC TICKETS.  Work is handed out in 256-particle chunks through a global ticket
+//     counter, so the chunks in flight are always one compact window of the traversal order however
+//     unevenly CTAs progress; the next ticket is drawn at the top of an iteration and resolved at
+//     its end, off the critical path.  For the READOUT this brings DRAM traffic down to the
+//     algorithmic 43 GB and is the fastest variant (12.4 ms at 1024^3).
+// (2) SPATIAL SCHEDULE.  Each chunk gets a key (y-block, x, y, z) from its middle particle; keys are
+//     radix sorted (cub, library, ~4M keys) and chunks are walked in key order.  Any permutation is
+//     correct, so a stale schedule costs speed, never correctness (it is rebuilt every 8 uses).
+// (3) WARP-AGGREGATED ATOMICS.  Lanes whose stencils are shifted by c cells along the contiguous
+//     axis pass their overlapping contributions to the owning lane by shuffle: one red.global.add
+//     per cell of the warp instead of one per (particle, point): 8 -> ~4.5 per CIC particle.  The
+//     paint is bound by red issue (~0.8 clk per active lane per SM, measured) so this is the lever.
+// Measured trade-off for the PAINT (1024^3 CIC f8, ms / DRAM GB): tickets give the ideal 43.6 GB
+// but 23.0 ms -- neighbouring chunks run concurrently and their reds serialise on the same L2
+// lines; a static chunk stride over the spatial schedule lets CTAs drift apart just enough:
+// 16.1 ms / 63 GB.  The paint therefore uses (2)+(3) with a static stride, the readout (1).
 #pragma once
 #include <cub/cub.cuh>
 
@@ -52,6 +63,19 @@ __global__ void pmb_k_chunk_keys(PmbGeom g, PmbParticles p, int64_t npart, int64
 }
 
 // returns the device array of chunk ids in traversal order (NULL: natural order)
+static int pmb_sched_ticket(pmb_ctx *ctx, unsigned long long **ticket)
+{
+    // a tiny dedicated allocation (first 256 bytes of sched_buf are reserved for it)
+    if (!ctx->sched_buf) {
+        PMB_CUDA(cudaMalloc(&ctx->sched_buf, 4096));
+        ctx->sched_bytes = 4096;
+        ctx->sched_sig = 0;
+    }
+    *ticket = (unsigned long long *) ctx->sched_buf;
+    PMB_CUDA(cudaMemsetAsync(*ticket, 0, sizeof(unsigned long long), ctx->stream));
+    return PMB_OK;
+}
+
 static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart,
                              const uint32_t **order, int64_t *nchunks_out)
 {
@@ -69,14 +93,14 @@ static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles 
     size_t temp = 0;
     PMB_CUDA(cub::DeviceRadixSort::SortPairs(NULL, temp, (uint64_t *) NULL, (uint64_t *) NULL, (uint32_t *) NULL,
                                              (uint32_t *) NULL, (int) nchunks, 0, 64, ctx->stream));
-    const size_t need = 2 * b_keys + 2 * b_ids + temp + 256;
+    const size_t need = 256 + 2 * b_keys + 2 * b_ids + temp + 256;
     if (need > ctx->sched_bytes) {
         if (ctx->sched_buf) { PMB_CUDA(cudaStreamSynchronize(ctx->stream)); PMB_CUDA(cudaFree(ctx->sched_buf)); ctx->sched_buf = NULL; }
         PMB_CUDA(cudaMalloc(&ctx->sched_buf, need + need / 8));
         ctx->sched_bytes = need + need / 8;
         ctx->sched_sig = 0;
     }
-    char *b = (char *) ctx->sched_buf;
+    char *b = (char *) ctx->sched_buf + 256;     // the first 256 bytes hold the ticket counter
     uint32_t *sorted_ids = (uint32_t *) (b + 2 * b_keys + b_ids);
     // a schedule stays useful while the particles move slowly: rebuild every few uses
     if (ctx->sched_sig == sig && ctx->sched_nchunks == nchunks && ctx->sched_uses < 8) {
@@ -96,6 +120,17 @@ static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles 
     ctx->sched_uses = 1;
     *order = sorted_ids;
     return PMB_OK;
+}
+
+// ---- dynamic chunk tickets ----------------------------------------------------------------------
+__device__ __forceinline__ long long pmb_resolve_chunk(unsigned long long tk, const uint32_t *order, int64_t nchunks)
+{
+    if ((int64_t) tk >= nchunks) return -1;
+    return order ? (long long) order[tk] : (long long) tk;
+}
+__device__ __forceinline__ long long pmb_next_chunk(unsigned long long *ticket, const uint32_t *order, int64_t nchunks)
+{
+    return pmb_resolve_chunk(atomicAdd(ticket, 1ull), order, nchunks);
 }
 
 // ---- paint -------------------------------------------------------------------------------------
@@ -123,19 +158,35 @@ __device__ __forceinline__ void pmb_red(char *mesh, int64_t off, double f, uint6
 template <typename MeshT, int FAM, bool CHECK, bool MERGE>
 __global__ void __launch_bounds__(PMB_CHUNK)
 pmb_k_paint_sched(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix,
-                  const uint32_t *__restrict__ order, int64_t nchunks)
+                  const uint32_t *__restrict__ order, int64_t nchunks, int dbg, unsigned long long *ticket)
 {
     uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    if ((dbg & 3) == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    else if ((dbg & 3) == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+    const int pos_stream = (dbg >> 2) & 1;
     const int lane = threadIdx.x & 31;
-    for (int64_t cb = blockIdx.x; cb < nchunks; cb += gridDim.x) {
-        const int64_t chunk = order ? (int64_t) order[cb] : cb;
+    // dynamic tickets: chunks are handed out strictly in schedule order, so the set of chunks in
+    // flight is always one compact window of the schedule however unevenly the CTAs progress (with
+    // a static stride, a CTA that lags by one iteration lags by a whole window).  The ticket of the
+    // NEXT iteration is drawn at the top of the current one and resolved at its end, off the
+    // critical path.
+    __shared__ long long s_chunk[2];
+    const bool dynamic = (dbg >> 3) & 1;
+    if (threadIdx.x == 0)
+        s_chunk[0] = dynamic ? pmb_next_chunk(ticket, order, nchunks) : pmb_resolve_chunk(blockIdx.x, order, nchunks);
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int64_t chunk = s_chunk[it & 1];
+        if (chunk < 0) break;
+        unsigned long long tk = 0;
+        if (threadIdx.x == 0) tk = dynamic ? atomicAdd(ticket, 1ull) : (unsigned long long) blockIdx.x + (unsigned long long) (it + 1) * gridDim.x;
         const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
         const bool active = i < npart;
         double x[3] = {0, 0, 0};
         double m = 0;
         if (active) {
-            pmb_load_pos<3>(p, i, x);
+            pmb_load_pos<3>(p, i, x, pos_stream);
             m = pmb_load_mass(p, i);
         }
         PmbAxes<3, FAM> A;
@@ -145,8 +196,7 @@ pmb_k_paint_sched(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsf
                 pmb_for_points_fixed<3, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
                     if (!CHECK || off != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, off, pmb_paint_value(true, m, v0, v1, v2), policy);
                 });
-            continue;
-        }
+        } else {
         // cell (0,0,c) of my stencil as a byte offset; invalid -> a value no other lane can equal
         int64_t base[FAM];
 #pragma unroll
@@ -190,6 +240,9 @@ pmb_k_paint_sched(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsf
                 }
             }
         }
+        }
+        if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = pmb_resolve_chunk(tk, order, nchunks);
+        __syncthreads();
     }
 }
 
@@ -198,14 +251,20 @@ template <typename MeshT, int FAM, bool CHECK>
 __global__ void __launch_bounds__(PMB_CHUNK)
 pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
                     void *out, int out_elsize, int64_t out_stride,
-                    const uint32_t *__restrict__ order, int64_t nchunks)
+                    const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
 {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    for (int64_t cb = blockIdx.x; cb < nchunks; cb += gridDim.x) {
-        const int64_t chunk = order ? (int64_t) order[cb] : cb;
+    __shared__ long long s_chunk[2];
+    if (threadIdx.x == 0) s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int64_t chunk = s_chunk[it & 1];
+        if (chunk < 0) break;
+        unsigned long long tk = 0;
+        if (threadIdx.x == 0) tk = atomicAdd(ticket, 1ull);
         const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
-        if (i >= npart) continue;
+        if (i < npart) {
         double x[3];
         pmb_load_pos<3>(p, i, x);
         PmbAxes<3, FAM> A;
@@ -225,5 +284,8 @@ pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, 
             }
         });
         pmb_st_real_stream(out, i * out_stride, out_elsize, value);
+        }
+        if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = pmb_resolve_chunk(tk, order, nchunks);
+        __syncthreads();
     }
 }

@@ -25,10 +25,12 @@ struct PmbAxes {
 };
 
 template <int NDIM>
-PMB_HD void pmb_load_pos(const PmbParticles &p, int64_t i, double *x)
+PMB_HD void pmb_load_pos(const PmbParticles &p, int64_t i, double *x, int stream = 1)
 {
 #pragma unroll
-    for (int d = 0; d < NDIM; d++) x[d] = pmb_ld_real_stream(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize);
+    for (int d = 0; d < NDIM; d++)
+        x[d] = stream ? pmb_ld_real_stream(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize)
+                      : pmb_ld_real(p.pos, i * p.ps0 + d * p.ps1, p.pos_elsize);
 }
 PMB_HD double pmb_load_mass(const PmbParticles &p, int64_t i)
 {
