@@ -410,12 +410,24 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         // large 3-D problems: locality-scheduled chunks + warp-aggregated atomics (pmb_sched.cuh)
         const uint32_t *order;
         int64_t nchunks;
+        const bool chk = pmb_geom_needs_check(g);
+        const int unit = pmb_env_flag("PMB_CARRY_UNIT", 128);
+        if (fam == 2 && unit > 0 && !(a->order[0] | a->order[1] | a->order[2])) {
+            // CIC: y-carry in registers + z aggregation in the warp (pmb_k_paint_cic_carry)
+            PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks, 1));
+            const int64_t nunits = (nchunks + unit - 1) / unit;
+            const int64_t capu = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
+            const int gridu = (int) (nunits < capu ? nunits : capu);
+            PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry<MeshT, CHECK><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                g, p, mesh, a->npart, order, nchunks, unit)));
+            PMB_LAUNCH_CHECK(ctx);
+            return PMB_OK;
+        }
         PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks));
         unsigned long long *ticket;
         PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
         const int64_t cap = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
         const int grid = (int) (nchunks < cap ? nchunks : cap);
-        const bool chk = pmb_geom_needs_check(g);
         const bool merge = fam > 1 && pmb_env_flag("PMB_MERGE", 1);
         // bits 0-1: mesh L2 policy (1 evict_last), bit 2: streaming pos loads, bit 3: dynamic tickets
         const int dbg = pmb_env_flag("PMB_DBG", 1 | 4);

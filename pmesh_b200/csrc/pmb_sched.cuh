@@ -40,7 +40,7 @@ static int pmb_env_flag(const char *name, int dflt)
 
 // ---- schedule ---------------------------------------------------------------------------------
 __global__ void pmb_k_chunk_keys(PmbGeom g, PmbParticles p, int64_t npart, int64_t nchunks,
-                                 uint64_t *keys, uint32_t *ids)
+                                 uint64_t *keys, uint32_t *ids, int keymode)
 {
     int64_t c = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
@@ -58,7 +58,10 @@ __global__ void pmb_k_chunk_keys(PmbGeom g, PmbParticles p, int64_t npart, int64
         cell[d] = (uint64_t) t;
     }
     // (y-block of 32 rows, x, y within the block, z / 64): 16 bits per field is plenty
-    keys[c] = ((cell[1] >> 5) << 48) | (cell[0] << 26) | ((cell[1] & 31) << 21) | (cell[2] >> 6);
+    if (keymode == 0)     // (y-block, x, y, z/64): spatial neighbours close in the order
+        keys[c] = ((cell[1] >> 5) << 48) | (cell[0] << 26) | ((cell[1] & 31) << 21) | (cell[2] >> 6);
+    else                  // (y-block, x, z/256, y): consecutive chunks are y-neighbours at the same z range
+        keys[c] = ((cell[1] >> 5) << 48) | (cell[0] << 26) | ((cell[2] >> 8) << 5) | (cell[1] & 31);
     ids[c] = (uint32_t) c;
 }
 
@@ -77,7 +80,7 @@ static int pmb_sched_ticket(pmb_ctx *ctx, unsigned long long **ticket)
 }
 
 static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart,
-                             const uint32_t **order, int64_t *nchunks_out)
+                             const uint32_t **order, int64_t *nchunks_out, int keymode = 0)
 {
     const int64_t nchunks = (npart + PMB_CHUNK - 1) / PMB_CHUNK;
     *nchunks_out = nchunks;
@@ -88,6 +91,7 @@ static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles 
     uint64_t tr;
     memcpy(&tr, &g.translate[0], sizeof(tr));
     sig ^= tr * 0x94D049BB133111EBull;
+    sig += (uint64_t) keymode;
     const size_t b_keys = (sizeof(uint64_t) * nchunks + 255) & ~(size_t) 255;
     const size_t b_ids = (sizeof(uint32_t) * nchunks + 255) & ~(size_t) 255;
     size_t temp = 0;
@@ -110,7 +114,7 @@ static int pmb_sched_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles 
     }
     uint64_t *keys = (uint64_t *) b, *keys2 = (uint64_t *) (b + b_keys);
     uint32_t *ids = (uint32_t *) (b + 2 * b_keys);
-    pmb_k_chunk_keys<<<(int) ((nchunks + 255) / 256), 256, 0, ctx->stream>>>(g, p, npart, nchunks, keys, ids);
+    pmb_k_chunk_keys<<<(int) ((nchunks + 255) / 256), 256, 0, ctx->stream>>>(g, p, npart, nchunks, keys, ids, keymode);
     PMB_LAUNCH_CHECK(ctx);
     PMB_CUDA(cub::DeviceRadixSort::SortPairs(b + 2 * b_keys + 2 * b_ids, temp, keys, keys2, ids, sorted_ids,
                                              (int) nchunks, 0, 64, ctx->stream));
@@ -243,6 +247,100 @@ pmb_k_paint_sched(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsf
         }
         if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = pmb_resolve_chunk(tk, order, nchunks);
         __syncthreads();
+    }
+}
+
+// ---- CIC paint with a register carry along y ------------------------------------------------------
+// With the (y-block, x, z/256, y) schedule a CTA that walks a run of consecutive chunks sees, in
+// thread t, the particles (x', y', k), (x', y'+1, k), (x', y'+2, k), ... of the lattice: the b = 1
+// row of one particle's stencil is the b = 0 row of the next.  That row is CARRIED in registers to
+// the next iteration and merged there, so only the b = 0 rows are ever written: with the warp
+// aggregation along z this is ~2.2 red.global.add per particle instead of 8.  A carry whose target
+// row does not match (row ends, displaced neighbours, end of a run) is flushed with plain reds.
+// CTAs own whole runs of UNIT chunks (static stride over runs), so concurrently running CTAs work
+// on different mesh rows and their reds do not serialise on the same L2 lines.
+template <typename MeshT, bool CHECK>
+__global__ void __launch_bounds__(PMB_CHUNK)
+pmb_k_paint_cic_carry(PmbGeom g, PmbParticles p, char *mesh, int64_t npart,
+                      const uint32_t *__restrict__ order, int64_t nchunks, int unit)
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    const int lane = threadIdx.x & 31;
+    const int64_t nunits = (nchunks + unit - 1) / unit;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        // carry: values of the (a, b = 1, c) points of the previous particle and where they go
+        double cv[2][2] = {{0, 0}, {0, 0}};
+        int64_t coff[2][2] = {{PMB_OFF_INVALID, PMB_OFF_INVALID}, {PMB_OFF_INVALID, PMB_OFF_INVALID}};
+        int64_t ckey = PMB_OFF_INVALID;
+        const int64_t cend = min((u + 1) * (int64_t) unit, nchunks);
+        uint32_t next = order ? order[u * unit] : (uint32_t) (u * unit);
+        for (int64_t cb = u * unit; cb < cend; cb++) {
+            const int64_t chunk = next;
+            if (cb + 1 < cend) next = order ? order[cb + 1] : (uint32_t) (cb + 1);
+            const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
+            const bool active = i < npart;
+            double x[3] = {0, 0, 0};
+            double m = 0;
+            if (active) {
+                pmb_load_pos<3>(p, i, x);
+                m = pmb_load_mass(p, i);
+            }
+            PmbAxes<3, 2> A;
+            pmb_axes_tuned<3, 2, CHECK>(g, g.order, x, 0, A);
+            // this particle's values: ((V0 * m) * V1) * V2
+            double v[2][2][2];
+            int64_t off[2][2][2];
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        v[a][b][c] = ((A.V[0][a] * m) * A.V[1][b]) * A.V[2][c];
+                        const bool ok = active && (!CHECK || (A.off[0][a] != PMB_OFF_INVALID && A.off[1][b] != PMB_OFF_INVALID &&
+                                                              A.off[2][c] != PMB_OFF_INVALID));
+                        off[a][b][c] = ok ? A.off[0][a] + A.off[1][b] + A.off[2][c] : PMB_OFF_INVALID;
+                    }
+            // merge the carried row into my b = 0 row, or flush it
+            if (ckey != PMB_OFF_INVALID && ckey == off[0][0][0] && coff[0][1] == off[0][0][1] &&
+                coff[1][0] == off[1][0][0] && coff[1][1] == off[1][0][1]) {
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) v[a][0][c] += cv[a][c];
+            } else {
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++)
+                        if (coff[a][c] != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, coff[a][c], cv[a][c], policy);
+            }
+            // new carry = my b = 1 row
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) { cv[a][c] = v[a][1][c]; coff[a][c] = off[a][1][c]; }
+            ckey = off[0][1][0];
+            // b = 0 row: warp aggregation along z, then one red per owned cell
+            const int64_t theirs = pmb_shfl_up_i64(off[0][0][1], 1);
+            const bool accept = lane >= 1 && off[0][0][0] != PMB_OFF_INVALID && theirs == off[0][0][0];
+            const bool taken = __shfl_down_sync(0xffffffffu, (int) accept, 1) != 0 && lane < 31;
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const double r = pmb_shfl_up_f64(v[a][0][1], 1);
+                double acc = v[a][0][0];
+                if (accept) acc += r;
+                if (off[a][0][0] != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, off[a][0][0], acc, policy);
+                if (!taken && off[a][0][1] != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, off[a][0][1], v[a][0][1], policy);
+            }
+        }
+        // end of the run: whatever is still carried goes out
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+                if (coff[a][c] != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, coff[a][c], cv[a][c], policy);
     }
 }
 
