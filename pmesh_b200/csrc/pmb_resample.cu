@@ -108,11 +108,11 @@ __device__ __forceinline__ double pmb_mesh_ld_hint(const char *mesh, int64_t off
     if (!hint) return (double) __ldg((const MeshT *) (mesh + off));
     if (sizeof(MeshT) == 8) {
         double v;
-        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(mesh + off), "l"(policy));
+        asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(mesh + off), "l"(policy));
         return v;
     } else {
         float v;
-        asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(mesh + off), "l"(policy));
+        asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(mesh + off), "l"(policy));
         return (double) v;
     }
 }
@@ -418,8 +418,13 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
             const int64_t nunits = (nchunks + unit - 1) / unit;
             const int64_t capu = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
             const int gridu = (int) (nunits < capu ? nunits : capu);
-            PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry<MeshT, CHECK><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
-                g, p, mesh, a->npart, order, nchunks, unit)));
+            if (pmb_env_flag("PMB_PAINT_PREFETCH", 1)) {
+                PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry<MeshT, CHECK, true><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                    g, p, mesh, a->npart, order, nchunks, unit)));
+            } else {
+                PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry<MeshT, CHECK, false><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                    g, p, mesh, a->npart, order, nchunks, unit)));
+            }
             PMB_LAUNCH_CHECK(ctx);
             return PMB_OK;
         }
@@ -599,9 +604,12 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         const int64_t cap = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
         const int grid = (int) (nchunks < cap ? nchunks : cap);
         const bool chk = pmb_geom_needs_check(g);
-        PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3,
-            (pmb_k_readout_sched<MeshT, FAM, CHECK><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
-                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket))));
+        const int variant = pmb_env_flag("PMB_READOUT_VARIANT", 2);
+#define PMB_SCHED_READOUT(V) PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3, \
+            (pmb_k_readout_sched<MeshT, FAM, CHECK, V><<<grid, PMB_CHUNK, 0, ctx->stream>>>( \
+                g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket))))
+        if (variant == 0) { PMB_SCHED_READOUT(0); } else if (variant == 1) { PMB_SCHED_READOUT(1); } else { PMB_SCHED_READOUT(2); }
+#undef PMB_SCHED_READOUT
         PMB_LAUNCH_CHECK(ctx);
         return PMB_OK;
     }

@@ -259,8 +259,8 @@ pmb_k_paint_sched(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsf
 // row does not match (row ends, displaced neighbours, end of a run) is flushed with plain reds.
 // CTAs own whole runs of UNIT chunks (static stride over runs), so concurrently running CTAs work
 // on different mesh rows and their reds do not serialise on the same L2 lines.
-template <typename MeshT, bool CHECK>
-__global__ void __launch_bounds__(PMB_CHUNK)
+template <typename MeshT, bool CHECK, bool PREFETCH>
+__global__ void __launch_bounds__(PMB_CHUNK, 4)
 pmb_k_paint_cic_carry(PmbGeom g, PmbParticles p, char *mesh, int64_t npart,
                       const uint32_t *__restrict__ order, int64_t nchunks, int unit)
 {
@@ -274,17 +274,30 @@ pmb_k_paint_cic_carry(PmbGeom g, PmbParticles p, char *mesh, int64_t npart,
         int64_t coff[2][2] = {{PMB_OFF_INVALID, PMB_OFF_INVALID}, {PMB_OFF_INVALID, PMB_OFF_INVALID}};
         int64_t ckey = PMB_OFF_INVALID;
         const int64_t cend = min((u + 1) * (int64_t) unit, nchunks);
-        uint32_t next = order ? order[u * unit] : (uint32_t) (u * unit);
+        int64_t chunk = order ? (int64_t) order[u * unit] : u * unit;
+        // software pipeline: the positions of the next chunk are loaded while this one is deposited
+        double xn[3] = {0, 0, 0};
+        double mn = 0;
+        if (PREFETCH && chunk * PMB_CHUNK + threadIdx.x < npart) {
+            pmb_load_pos<3>(p, chunk * PMB_CHUNK + threadIdx.x, xn);
+            mn = pmb_load_mass(p, chunk * PMB_CHUNK + threadIdx.x);
+        }
         for (int64_t cb = u * unit; cb < cend; cb++) {
-            const int64_t chunk = next;
-            if (cb + 1 < cend) next = order ? order[cb + 1] : (uint32_t) (cb + 1);
             const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
             const bool active = i < npart;
-            double x[3] = {0, 0, 0};
-            double m = 0;
-            if (active) {
-                pmb_load_pos<3>(p, i, x);
-                m = pmb_load_mass(p, i);
+            if (!PREFETCH && active) {
+                pmb_load_pos<3>(p, i, xn);
+                mn = pmb_load_mass(p, i);
+            }
+            const double x[3] = {xn[0], xn[1], xn[2]};
+            const double m = mn;
+            if (cb + 1 < cend) {
+                chunk = order ? (int64_t) order[cb + 1] : cb + 1;
+                const int64_t in = chunk * PMB_CHUNK + threadIdx.x;
+                if (PREFETCH && in < npart) {
+                    pmb_load_pos<3>(p, in, xn);
+                    mn = pmb_load_mass(p, in);
+                }
             }
             PmbAxes<3, 2> A;
             pmb_axes_tuned<3, 2, CHECK>(g, g.order, x, 0, A);
@@ -345,45 +358,64 @@ pmb_k_paint_cic_carry(PmbGeom g, PmbParticles p, char *mesh, int64_t npart,
 }
 
 // ---- readout -----------------------------------------------------------------------------------
-template <typename MeshT, int FAM, bool CHECK>
-__global__ void __launch_bounds__(PMB_CHUNK)
+template <typename MeshT, bool VOL>
+__device__ __forceinline__ double pmb_mesh_load(const char *mesh, int64_t off, uint64_t policy)
+{
+    if (sizeof(MeshT) == 8) {
+        double v;
+        if (VOL) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(mesh + off), "l"(policy));
+        else asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(mesh + off), "l"(policy));
+        return v;
+    } else {
+        float v;
+        if (VOL) asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(mesh + off), "l"(policy));
+        else asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(mesh + off), "l"(policy));
+        return (double) v;
+    }
+}
+
+// Chunks come from the dynamic ticket counter; the positions of the NEXT chunk are loaded while the
+// current one is gathered (software pipeline: the DRAM latency of the particle stream is hidden
+// behind the mesh gathers of the previous chunk).
+template <typename MeshT, int FAM, bool CHECK, int VARIANT>
+__global__ void __launch_bounds__(PMB_CHUNK, (VARIANT == 2 ? 5 : 1))
 pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
                     void *out, int out_elsize, int64_t out_stride,
                     const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
 {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    __shared__ long long s_chunk[2];
-    if (threadIdx.x == 0) s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
+    __shared__ long long s_chunk[3];
+    if (threadIdx.x == 0) {
+        s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
+        s_chunk[1] = pmb_next_chunk(ticket, order, nchunks);
+    }
     __syncthreads();
-    for (int it = 0;; it++) {
-        const int64_t chunk = s_chunk[it & 1];
-        if (chunk < 0) break;
+    int64_t cur = s_chunk[0], nxt = s_chunk[1];
+    double x[3] = {0, 0, 0};
+    if (VARIANT >= 2 && cur >= 0 && cur * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos<3>(p, cur * PMB_CHUNK + threadIdx.x, x);
+    for (int it = 0; cur >= 0; it++) {
         unsigned long long tk = 0;
         if (threadIdx.x == 0) tk = atomicAdd(ticket, 1ull);
-        const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
+        // prefetch the next chunk's positions
+        double xn[3] = {0, 0, 0};
+        const int64_t in = nxt * PMB_CHUNK + threadIdx.x;
+        if (VARIANT >= 2 && nxt >= 0 && in < npart) pmb_load_pos<3>(p, in, xn);
+        const int64_t i = cur * PMB_CHUNK + threadIdx.x;
+        if (VARIANT < 2 && i < npart) pmb_load_pos<3>(p, i, x);
         if (i < npart) {
-        double x[3];
-        pmb_load_pos<3>(p, i, x);
-        PmbAxes<3, FAM> A;
-        pmb_axes_tuned<3, FAM, CHECK>(g, g.order, x, pcsfix, A);
-        double value = 0;
-        pmb_for_points_fixed<3, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
-            if (!CHECK || off != PMB_OFF_INVALID) {
-                double mv;
-                if (sizeof(MeshT) == 8) {
-                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(mv) : "l"(mesh + off), "l"(policy));
-                } else {
-                    float fv;
-                    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(fv) : "l"(mesh + off), "l"(policy));
-                    mv = (double) fv;
-                }
-                value += mv * ((v0 * v1) * v2);
-            }
-        });
-        pmb_st_real_stream(out, i * out_stride, out_elsize, value);
+            PmbAxes<3, FAM> A;
+            pmb_axes_tuned<3, FAM, CHECK>(g, g.order, x, pcsfix, A);
+            double value = 0;
+            pmb_for_points_fixed<3, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
+                if (!CHECK || off != PMB_OFF_INVALID) value += pmb_mesh_load<MeshT, VARIANT == 0>(mesh, off, policy) * ((v0 * v1) * v2);
+            });
+            pmb_st_real_stream(out, i * out_stride, out_elsize, value);
         }
-        if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = pmb_resolve_chunk(tk, order, nchunks);
+        if (threadIdx.x == 0) s_chunk[(it + 2) % 3] = pmb_resolve_chunk(tk, order, nchunks);
         __syncthreads();
+        cur = nxt;
+        nxt = s_chunk[(it + 2) % 3];
+        x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
     }
 }
