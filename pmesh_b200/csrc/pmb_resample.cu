@@ -418,6 +418,31 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
             const int64_t nunits = (nchunks + unit - 1) / unit;
             const int64_t capu = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
             const int gridu = (int) (nunits < capu ? nunits : capu);
+            // 32-bit element indices when the canvas spans < 2^31 elements and strides are whole elements
+            bool idx32 = pmb_env_flag("PMB_CARRY32", 1) != 0;
+            int64_t span = 0;
+            for (int d = 0; d < 3; d++) {
+                if (a->strides[d] < 0 || a->strides[d] % (int64_t) sizeof(MeshT)) idx32 = false;
+                span += (a->size[d] - 1) * (a->strides[d] / (int64_t) sizeof(MeshT));
+            }
+            if (span >= ((int64_t) 1 << 31) - 1) idx32 = false;
+            if (idx32) {
+                PmbGeom32 g32;
+                for (int d = 0; d < 3; d++) {
+                    g32.scale[d] = g.scale[d]; g32.translate[d] = g.translate[d];
+                    g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
+                    g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
+                }
+                if (pmb_pos_is_f8_rows(p)) {
+                    PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, true><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                        g32, p, (MeshT *) mesh, a->npart, order, nchunks, unit)));
+                } else {
+                    PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, false><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                        g32, p, (MeshT *) mesh, a->npart, order, nchunks, unit)));
+                }
+                PMB_LAUNCH_CHECK(ctx);
+                return PMB_OK;
+            }
             if (pmb_env_flag("PMB_PAINT_PREFETCH", 1)) {
                 PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry<MeshT, CHECK, true><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
                     g, p, mesh, a->npart, order, nchunks, unit)));
@@ -604,6 +629,32 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         const int64_t cap = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
         const int grid = (int) (nchunks < cap ? nchunks : cap);
         const bool chk = pmb_geom_needs_check(g);
+        if (fam == 2 && !(a->order[0] | a->order[1] | a->order[2]) && pmb_env_flag("PMB_READOUT32", 1)) {
+            bool idx32 = true;
+            int64_t span = 0;
+            for (int d = 0; d < 3; d++) {
+                if (a->strides[d] < 0 || a->strides[d] % (int64_t) sizeof(MeshT)) idx32 = false;
+                span += (a->size[d] - 1) * (a->strides[d] / (int64_t) sizeof(MeshT));
+            }
+            if (span >= ((int64_t) 1 << 31) - 1) idx32 = false;
+            if (idx32) {
+                PmbGeom32 g32;
+                for (int d = 0; d < 3; d++) {
+                    g32.scale[d] = g.scale[d]; g32.translate[d] = g.translate[d];
+                    g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
+                    g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
+                }
+                if (pmb_pos_is_f8_rows(p)) {
+                    PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, true><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                        g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                } else {
+                    PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, false><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                        g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                }
+                PMB_LAUNCH_CHECK(ctx);
+                return PMB_OK;
+            }
+        }
         const int variant = pmb_env_flag("PMB_READOUT_VARIANT", 2);
 #define PMB_SCHED_READOUT(V) PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3, \
             (pmb_k_readout_sched<MeshT, FAM, CHECK, V><<<grid, PMB_CHUNK, 0, ctx->stream>>>( \

@@ -357,6 +357,134 @@ pmb_k_paint_cic_carry(PmbGeom g, PmbParticles p, char *mesh, int64_t npart,
     }
 }
 
+// ---- the same kernel with 32-bit element indices ---------------------------------------------------
+// ncu (profiles/) showed the 64-bit version issue-bound: 428 warp instructions per 32 particles, 29 %
+// IMAD + 14 % ISETP from 64-bit byte-offset arithmetic and compares.  When the canvas has fewer than
+// 2^31 elements (1024^3 padded has 1.08e9) every cell is a 32-bit element index: one IMAD per axis
+// point, 32-bit adds / compares / shuffles, and a single IMAD.WIDE per red for the address.
+struct PmbGeom32 {
+    double scale[3], translate[3];
+    int period[3], size[3], estride[3];
+};
+
+// positions of particle i; POS8: contiguous (N, 3) float64 rows (the common case) -- no stride
+// arithmetic, no element-size branch
+template <bool POS8>
+__device__ __forceinline__ void pmb_load_pos3(const PmbParticles &p, int64_t i, double &x0, double &x1, double &x2)
+{
+    if (POS8) {
+        const double *pp = (const double *) p.pos + 3 * i;
+        x0 = __ldcs(pp); x1 = __ldcs(pp + 1); x2 = __ldcs(pp + 2);
+    } else {
+        double t[3];
+        pmb_load_pos<3>(p, i, t);
+        x0 = t[0]; x1 = t[1]; x2 = t[2];
+    }
+}
+static inline bool pmb_pos_is_f8_rows(const PmbParticles &p)
+{
+    return p.pos_elsize == 8 && p.ps1 == 8 && p.ps0 == 24 && ((uintptr_t) p.pos & 7) == 0;
+}
+
+template <bool CHECK>
+__device__ __forceinline__ void pmb_cic_axis32(double xin, double scale, double translate, int per, int sz, int es,
+                                               double &V0, double &V1, int &e0, int &e1)
+{
+    const double X = pmb_gridpos(xin, scale, translate);
+    const int I0 = (int) floor(X);
+    V1 = X - I0;
+    V0 = 1. - V1;
+    int t0 = I0;
+    if (per > 0) t0 = pmb_wrap32(t0, per);
+    int t1 = t0 + 1;
+    if (per > 0 && t1 == per) t1 = 0;
+    e0 = (!CHECK || (unsigned) t0 < (unsigned) sz) ? t0 * es : -1;
+    e1 = (!CHECK || (unsigned) t1 < (unsigned) sz) ? t1 * es : -1;
+}
+
+template <typename MeshT, bool CHECK, bool POS8>
+__global__ void __launch_bounds__(PMB_CHUNK, 4)
+pmb_k_paint_cic_carry32(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart,
+                        const uint32_t *__restrict__ order, int64_t nchunks, int unit)
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    const int lane = threadIdx.x & 31;
+    const int64_t nunits = (nchunks + unit - 1) / unit;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        double cv00 = 0, cv01 = 0, cv10 = 0, cv11 = 0;     // carried (a, b = 1, c) values
+        int co00 = -1, co01 = -1, co10 = -1, co11 = -1;     // and their element indices (-1: none)
+        const int64_t cend = min((u + 1) * (int64_t) unit, nchunks);
+        int64_t chunk = order ? (int64_t) order[u * unit] : u * unit;
+        double xn0 = 0, xn1 = 0, xn2 = 0, mn = 0;
+        {
+            const int64_t i0 = chunk * PMB_CHUNK + threadIdx.x;
+            if (i0 < npart) {
+                pmb_load_pos3<POS8>(p, i0, xn0, xn1, xn2);
+                mn = pmb_load_mass(p, i0);
+            }
+        }
+        for (int64_t cb = u * unit; cb < cend; cb++) {
+            const bool active = chunk * PMB_CHUNK + threadIdx.x < npart;
+            const double x0 = xn0, x1 = xn1, x2 = xn2, m = mn;
+            if (cb + 1 < cend) {
+                chunk = order ? (int64_t) order[cb + 1] : cb + 1;
+                const int64_t in = chunk * PMB_CHUNK + threadIdx.x;
+                if (in < npart) {
+                    pmb_load_pos3<POS8>(p, in, xn0, xn1, xn2);
+                    mn = pmb_load_mass(p, in);
+                }
+            }
+            double Vx0, Vx1, Vy0, Vy1, Vz0, Vz1;
+            int ex0, ex1, ey0, ey1, ez0, ez1;
+            pmb_cic_axis32<CHECK>(x0, g.scale[0], g.translate[0], g.period[0], g.size[0], g.estride[0], Vx0, Vx1, ex0, ex1);
+            pmb_cic_axis32<CHECK>(x1, g.scale[1], g.translate[1], g.period[1], g.size[1], g.estride[1], Vy0, Vy1, ey0, ey1);
+            pmb_cic_axis32<CHECK>(x2, g.scale[2], g.translate[2], g.period[2], g.size[2], g.estride[2], Vz0, Vz1, ez0, ez1);
+            // element index of point (a, b, c); -1 when outside the canvas or the lane is idle
+            auto idx = [&](int ea, int eb, int ec) -> int {
+                if (CHECK) return (active && ea >= 0 && eb >= 0 && ec >= 0) ? ea + eb + ec : -1;
+                return active ? ea + eb + ec : -1;
+            };
+            const int o000 = idx(ex0, ey0, ez0), o001 = idx(ex0, ey0, ez1), o100 = idx(ex1, ey0, ez0), o101 = idx(ex1, ey0, ez1);
+            const int o010 = idx(ex0, ey1, ez0), o011 = idx(ex0, ey1, ez1), o110 = idx(ex1, ey1, ez0), o111 = idx(ex1, ey1, ez1);
+            // ((V0 * m) * V1) * V2, the tuned routine's order
+            const double wx0 = Vx0 * m, wx1 = Vx1 * m;
+            const double w00 = wx0 * Vy0, w01 = wx0 * Vy1, w10 = wx1 * Vy0, w11 = wx1 * Vy1;
+            double v000 = w00 * Vz0, v001 = w00 * Vz1, v100 = w10 * Vz0, v101 = w10 * Vz1;
+            const double v010 = w01 * Vz0, v011 = w01 * Vz1, v110 = w11 * Vz0, v111 = w11 * Vz1;
+            // carried row: merge into my b = 0 row when it is the same mesh row, else flush it
+            const bool same = co00 >= 0 && co00 == o000 && co01 == o001 && co10 == o100 && (!CHECK || co11 == o101);
+            if (same) {
+                v000 += cv00; v001 += cv01; v100 += cv10; v101 += cv11;
+            } else {
+                if (co00 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co00 * sizeof(MeshT), cv00, policy);
+                if (co01 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co01 * sizeof(MeshT), cv01, policy);
+                if (co10 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co10 * sizeof(MeshT), cv10, policy);
+                if (co11 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co11 * sizeof(MeshT), cv11, policy);
+            }
+            cv00 = v010; cv01 = v011; cv10 = v110; cv11 = v111;
+            co00 = o010; co01 = o011; co10 = o110; co11 = o111;
+            // b = 0 row: aggregate along z inside the warp, one red per owned cell
+            const int theirs = __shfl_up_sync(0xffffffffu, o001, 1);
+            const bool accept = lane >= 1 && o000 >= 0 && theirs == o000;
+            const bool taken = __shfl_down_sync(0xffffffffu, (int) accept, 1) != 0 && lane < 31;
+            const double r0 = __shfl_up_sync(0xffffffffu, v001, 1);
+            const double r1 = __shfl_up_sync(0xffffffffu, v101, 1);
+            if (accept) { v000 += r0; v100 += r1; }
+            if (o000 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) o000 * sizeof(MeshT), v000, policy);
+            if (o100 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) o100 * sizeof(MeshT), v100, policy);
+            if (!taken) {
+                if (o001 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) o001 * sizeof(MeshT), v001, policy);
+                if (o101 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) o101 * sizeof(MeshT), v101, policy);
+            }
+        }
+        if (co00 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co00 * sizeof(MeshT), cv00, policy);
+        if (co01 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co01 * sizeof(MeshT), cv01, policy);
+        if (co10 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co10 * sizeof(MeshT), cv10, policy);
+        if (co11 >= 0) pmb_red<MeshT>((char *) mesh, (int64_t) co11 * sizeof(MeshT), cv11, policy);
+    }
+}
+
 // ---- readout -----------------------------------------------------------------------------------
 template <typename MeshT, bool VOL>
 __device__ __forceinline__ double pmb_mesh_load(const char *mesh, int64_t off, uint64_t policy)
@@ -417,5 +545,71 @@ pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, 
         cur = nxt;
         nxt = s_chunk[(it + 2) % 3];
         x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
+    }
+}
+
+// ---- CIC gather with 32-bit element indices ---------------------------------------------------------
+// Same pipeline as pmb_k_readout_sched (dynamic tickets, positions of the next chunk prefetched) with
+// the lean index arithmetic of pmb_k_paint_cic_carry32.  Sums in the reference's point order:
+// bit-identical results.
+template <typename MeshT, bool CHECK, bool POS8>
+__global__ void __launch_bounds__(PMB_CHUNK, 5)
+pmb_k_readout_cic32(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh, int64_t npart,
+                    void *out, int out_elsize, int64_t out_stride,
+                    const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    __shared__ long long s_chunk[3];
+    if (threadIdx.x == 0) {
+        s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
+        s_chunk[1] = pmb_next_chunk(ticket, order, nchunks);
+    }
+    __syncthreads();
+    int64_t cur = s_chunk[0], nxt = s_chunk[1];
+    double x0 = 0, x1 = 0, x2 = 0;
+    if (cur >= 0 && cur * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, cur * PMB_CHUNK + threadIdx.x, x0, x1, x2);
+    for (int it = 0; cur >= 0; it++) {
+        unsigned long long tk = 0;
+        if (threadIdx.x == 0) tk = atomicAdd(ticket, 1ull);
+        double xn0 = 0, xn1 = 0, xn2 = 0;
+        const int64_t in = nxt * PMB_CHUNK + threadIdx.x;
+        if (nxt >= 0 && in < npart) pmb_load_pos3<POS8>(p, in, xn0, xn1, xn2);
+        const int64_t i = cur * PMB_CHUNK + threadIdx.x;
+        if (i < npart) {
+            double Vx[2], Vy[2], Vz[2];
+            int ex[2], ey[2], ez[2];
+            pmb_cic_axis32<CHECK>(x0, g.scale[0], g.translate[0], g.period[0], g.size[0], g.estride[0], Vx[0], Vx[1], ex[0], ex[1]);
+            pmb_cic_axis32<CHECK>(x1, g.scale[1], g.translate[1], g.period[1], g.size[1], g.estride[1], Vy[0], Vy[1], ey[0], ey[1]);
+            pmb_cic_axis32<CHECK>(x2, g.scale[2], g.translate[2], g.period[2], g.size[2], g.estride[2], Vz[0], Vz[1], ez[0], ez[1]);
+            double mv[2][2][2];
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const bool ok = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0);
+                        mv[a][b][c] = ok ? pmb_mesh_load<MeshT, false>((const char *) mesh,
+                                                                       (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), policy)
+                                         : 0.0;
+                    }
+            double value = 0;
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const bool ok = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0);
+                        if (ok) value += mv[a][b][c] * ((Vx[a] * Vy[b]) * Vz[c]);
+                    }
+            pmb_st_real_stream(out, i * out_stride, out_elsize, value);
+        }
+        if (threadIdx.x == 0) s_chunk[(it + 2) % 3] = pmb_resolve_chunk(tk, order, nchunks);
+        __syncthreads();
+        cur = nxt;
+        nxt = s_chunk[(it + 2) % 3];
+        x0 = xn0; x1 = xn1; x2 = xn2;
     }
 }

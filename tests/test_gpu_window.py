@@ -314,6 +314,8 @@ def test_scheduled_kernels_large_inputs(W, oracle, name, order):
     if order == "random":
         pos = pos[rng.permutation(len(pos))]
     mass = rng.uniform(0.5, 2.0, len(pos))
+    if name == "cic" and order == "random":
+        pos = pos.astype("f4")          # the strided / float32 position loader of the lean CIC kernels
     dpos, dmass = DeviceArray.from_host(pos), DeviceArray.from_host(mass)
     for shape, translate in (((N, N, N), [0.0, 0.0, 0.0]), ((20, N, N), [-30.0, 0.0, 0.0])):
         tr = W.Affine(3, scale=1.0, translate=translate, period=N)
