@@ -228,9 +228,25 @@ def run_ours(args):
     gp_s = comm.allreduce(nl, op=C.SUM) / ((comm.allreduce(t_paint, op=C.MAX) + comm.allreduce(t_read, op=C.MAX)) * 1e-3) / 1e9
     dom = ("paint", t_paint, ab_paint) if t_paint >= t_read else ("readout", t_read, ab_read)
     achieved = dom[2] / (dom[1] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pmb_k_%s_tuned<%s>" % (dom[0], args.window), "achieved": round(achieved, 1),
+    # which kernel that is (dispatch of pmb_resample.cu) and its DRAM traffic per launch from the
+    # committed ncu --set full capture of the same launch (profiles/traffic_r1.json), when there is one
+    big = nl >= (1 << 18)
+    if args.window == "cic" and big:
+        kname = {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32"}[dom[0]]
+    elif args.window in ("nnb", "cic", "tsc", "pcs"):
+        kname = {"paint": "pmb_k_paint_sched" if big else "pmb_k_paint_tuned",
+                 "readout": "pmb_k_readout_sched" if big else "pmb_k_readout_tuned"}[dom[0]]
+    else:
+        kname = "pmb_k_%s_dyn" % dom[0]
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        traffic = tj.get("%s:%s:%d:%d:%s" % (kname, args.window, M, comm.size, args.particles))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "ms_per_launch": round(dom[1], 4),
+                "traffic": traffic, "ms_per_launch": round(dom[1], 4),
                 "algorithmic_bytes_per_launch": dom[2],
                 "paint_ms": round(t_paint, 4), "readout_ms": round(t_read, 4),
                 "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),

@@ -30,6 +30,8 @@ struct RouteGeom {
     int nedges[3];
     const int32_t *assign;       // device [ndomains]
     const int16_t *degenerate;   // device [ndomains]
+    int all_trivial;             // every axis is a single periodic domain: the mask is a constant
+    uint64_t const_mask;
 };
 
 // numpy floored modulo for doubles (npy_divmod): result has the sign of b, may round up to b itself
@@ -114,7 +116,11 @@ __device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsi
         int target = 0;
         for (int d = 0; d < g.ndim; d++) {
             int t = p[d];
-            if (g.periodic) t = pmb_imod(t, g.shape[d]);
+            if (g.periodic) {      // sil >= -shape - 1 and sir <= 2 shape: a few conditional steps, no division
+                const int n = g.shape[d];
+                if (t >= n) { t -= n; if (t >= n) t = pmb_imod(t, n); }
+                else if (t < 0) { t += n; if (t < 0) t = pmb_imod(t, n); }
+            }
             target += t * g.dstride[d];
         }
         if (target >= 0 && target < g.ndomains) {
@@ -146,7 +152,7 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
         const int64_t i = base + threadIdx.x;
         uint64_t mask = 0;
         if (i < end) {
-            mask = pmb_route_mask(g, pos, elsize, ps0, ps1, i);
+            mask = g.all_trivial ? g.const_mask : pmb_route_mask(g, pos, elsize, ps0, ps1, i);
             masks[i] = mask;
         }
         for (int r = 0; r < g.nranks; r++) {
@@ -258,6 +264,14 @@ static int route_setup(pmb_ctx *ctx, const pmb_decompose_args *a, RouteGeom *g, 
     if (e != cudaSuccess) { cudaFree(dev); return pmb_cuda_fail(e, "route tables", __FILE__, __LINE__); }
     int o = 0;
     for (int d = 0; d < a->ndim; d++) { g->edges[d] = (const double *) dev + o; o += a->nedges[d]; }
+    // one periodic domain on every axis (a single rank): every particle goes to the rank of domain 0
+    g->all_trivial = a->periodic ? 1 : 0;
+    for (int d = 0; d < a->ndim; d++) if (g->shape[d] != 1) g->all_trivial = 0;
+    if (g->all_trivial) {
+        const int rank = a->domain_assign_h[0];
+        const int deg = (rank >= 0 && rank < ndomains) ? a->domain_degenerate_h[rank] : 0;
+        g->const_mask = (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) ? ((uint64_t) 1 << rank) : 0;
+    }
     g->assign = (const int32_t *) (dev + b_edges);
     g->degenerate = (const int16_t *) (dev + b_edges + b_assign);
     *dev_tables = dev;
