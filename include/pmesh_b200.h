@@ -160,12 +160,18 @@ typedef struct pmb_decompose_args {
  * Both phases must be called with the same args on the same ctx, back to back. */
 int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *counts_h, int64_t *ntotal);
 int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *indices);
+/* *flag = 1 when the last pmb_decompose_count found the IDENTITY layout: a single periodic domain on
+ * every axis, so every particle goes exactly once, in order, to one rank (indices = arange(npart)).
+ * Callers may then skip pmb_decompose_fill and pass indices = NULL to pmb_take / pmb_gather_sum. */
+int pmb_decompose_identity(pmb_ctx *ctx, int *flag);
 
-/* out[j] = data[indices[j]]  (records of itemsize bytes) <- ndarray.take(indices, axis=0), domain.py:188 */
+/* out[j] = data[indices[j]]  (records of itemsize bytes) <- ndarray.take(indices, axis=0), domain.py:188
+ * indices == NULL: the identity layout (a copy). */
 int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const int32_t *indices, int64_t n, void *out);
 /* out[i] = sum_j { data[j] : indices[j] == i } accumulated in ascending j, in float64, cast to out
  * <- bincountv(indices, recv, minlength=sendlength), domain.py:26-48,300. ncomp values per record.
- * offsets_h[nranks+1] delimit the per-rank sorted segments of indices. */
+ * offsets_h[nranks+1] delimit the per-rank sorted segments of indices.
+ * indices == NULL: the identity layout, out[i] = 0.0 + data[i]. */
 int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
                    const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize);
 
@@ -210,6 +216,11 @@ int pmb_fft_library_ms(pmb_fft *plan, float *ms, int reset);
 #define PMB_TF_IK 6               /* i*k_d (plain gradient) */
 int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
                  const void *in, void *out);
+/* out = prefactor * T(k) * in: the same kernel with a scalar folded into the multiplier, so that a
+ * pending normalisation of `in` (the 1/prod(Nmesh) of r2c, pm.py:692, or a `rho *= fac` before it)
+ * costs no pass of its own. */
+int pmb_transfer_scaled(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
+                        double prefactor, const void *in, void *out);
 
 #ifdef __cplusplus
 }

@@ -64,11 +64,11 @@ SYMBOLS = [
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
     "pmb_paint", "pmb_readout", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum",
     "pmb_particles_uniform", "pmb_particles_lattice",
-    "pmb_decompose_count", "pmb_decompose_fill", "pmb_take", "pmb_gather_sum",
+    "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
     "pmb_fft_create", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_library_ms",
-    "pmb_transfer",
+    "pmb_transfer", "pmb_transfer_scaled",
 ]
 
 _P = ctypes.c_void_p
@@ -92,6 +92,7 @@ _ARGTYPES = {
     "pmb_particles_uniform": [_P, _P, _I, _L, _I, _P, ctypes.c_uint64, _L],
     "pmb_particles_lattice": [_P, _P, _I, _L, _I, _P, _P, _D, _D, ctypes.c_uint64, _L],
     "pmb_decompose_count": [_P, _P, _P, _P], "pmb_decompose_fill": [_P, _P, _P],
+    "pmb_decompose_identity": [_P, _P],
     "pmb_take": [_P, _P, _L, _P, _L, _P],
     "pmb_gather_sum": [_P, _P, _I, _I, _P, _P, _I, _L, _P, _I],
     "pmb_comm_unique_id": [_P], "pmb_comm_init_rank": [_P, _P, _I, _I], "pmb_comm_destroy": [_P],
@@ -102,6 +103,7 @@ _ARGTYPES = {
     "pmb_fft_layout": [_P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pmb_fft_r2c": [_P, _P, _P, _D], "pmb_fft_c2r": [_P, _P, _P], "pmb_fft_library_ms": [_P, _P, _I],
     "pmb_transfer": [_P, _I, _I, _P, _P, _P, _P],
+    "pmb_transfer_scaled": [_P, _I, _I, _P, _P, _D, _P, _P],
 }
 
 _lib = None

@@ -298,7 +298,24 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
     *ntotal = 0;
     ctx->route_npart = a->npart;
     ctx->route_nblocks = 0;
+    ctx->route_identity = 0;
     if (a->npart == 0) { cudaFree(tables); return PMB_OK; }
+    if (g.all_trivial) {
+        // one periodic domain on every axis: every particle goes, once and in order, to the rank of
+        // domain 0 (or nowhere if that domain is flagged degenerate): counts are known without
+        // looking at a single position and indices = arange(npart)
+        cudaFree(tables);
+        if (g.const_mask) {
+            int rank = 0;
+            while (!((g.const_mask >> rank) & 1)) rank++;
+            if (rank < a->nranks) {
+                counts_h[rank] = (int32_t) a->npart;
+                *ntotal = a->npart;
+                ctx->route_identity = 1;
+            }
+        }
+        return PMB_OK;
+    }
 
     int64_t nblocks = (a->npart + ROUTE_BLOCK - 1) / ROUTE_BLOCK;
     const int64_t cap = (int64_t) ctx->sm_count * 8;
@@ -346,10 +363,30 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
     return PMB_OK;
 }
 
+__global__ void __launch_bounds__(256) pmb_k_iota(int32_t *out, int64_t n)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; t < n; t += stride) __stcs(out + t, (int32_t) t);
+}
+
+extern "C" int pmb_decompose_identity(pmb_ctx *ctx, int *flag)
+{
+    PMB_REQUIRE(ctx && flag, "null argument");
+    *flag = ctx->route_identity;
+    return PMB_OK;
+}
+
 extern "C" int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int32_t *indices)
 {
     PMB_REQUIRE(ctx && a, "null argument");
     PMB_REQUIRE(ctx->route_npart == a->npart, "pmb_decompose_fill must follow pmb_decompose_count with the same particles");
+    if (ctx->route_identity) {
+        PMB_REQUIRE(indices, "null indices");
+        pmb_k_iota<<<pmb_grid(ctx, a->npart, 256, 8), 256, 0, ctx->stream>>>(indices, a->npart);
+        PMB_LAUNCH_CHECK(ctx);
+        return PMB_OK;
+    }
     if (a->npart == 0 || ctx->route_nblocks == 0) return PMB_OK;
     PMB_REQUIRE(indices, "null indices");
     const int64_t per_block = ctx->route_per_block;
@@ -408,7 +445,11 @@ extern "C" int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const 
 {
     PMB_REQUIRE(ctx && itemsize > 0 && n >= 0, "bad take arguments");
     if (n == 0) return PMB_OK;
-    PMB_REQUIRE(data && indices && out, "null argument");
+    PMB_REQUIRE(data && out, "null argument");
+    if (!indices) {   // identity layout: take(arange(n)) is a copy
+        PMB_CUDA(cudaMemcpyAsync(out, data, (size_t) n * itemsize, cudaMemcpyDeviceToDevice, ctx->stream));
+        return PMB_OK;
+    }
     const uintptr_t al = (uintptr_t) data | (uintptr_t) out | (uintptr_t) itemsize;
     if ((al & 7) == 0) take_launch<unsigned long long>(ctx, data, itemsize / 8, indices, n, out);
     else if ((al & 3) == 0) take_launch<unsigned int>(ctx, data, itemsize / 4, indices, n, out);
@@ -446,6 +487,15 @@ __global__ void pmb_k_f64_to_f32(const double *__restrict__ in, float *__restric
     for (; t < n; t += stride) out[t] = (float) in[t];
 }
 
+// identity layout (indices = arange): bincount degenerates to out[j] = 0.0 + data[j]
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) pmb_k_gather_identity(const Tin *__restrict__ in, Tout *__restrict__ out, int64_t n)
+{
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; t < n; t += stride) __stcs(out + t, (Tout) (0.0 + (double) __ldcs(in + t)));
+}
+
 extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
                               const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize)
 {
@@ -454,8 +504,22 @@ extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, i
     PMB_REQUIRE((data_elsize == 4 || data_elsize == 8) && (out_elsize == 4 || out_elsize == 8), "float32/float64 only");
     if (nout == 0) return PMB_OK;
     PMB_REQUIRE(out, "null out");
-    PMB_REQUIRE(offsets_h[nranks] == 0 || (data && indices), "null data / indices");
+    PMB_REQUIRE(offsets_h[nranks] == 0 || data, "null data");
     const int64_t n = nout * ncomp;
+    if (!indices && offsets_h[nranks] != 0) {
+        PMB_REQUIRE(offsets_h[nranks] == nout, "identity gather needs exactly one record per output row");
+        const int grid = pmb_grid(ctx, n, 256, 8);
+        if (data_elsize == 8 && out_elsize == 8)
+            pmb_k_gather_identity<<<grid, 256, 0, ctx->stream>>>((const double *) data, (double *) out, n);
+        else if (data_elsize == 8)
+            pmb_k_gather_identity<<<grid, 256, 0, ctx->stream>>>((const double *) data, (float *) out, n);
+        else if (out_elsize == 8)
+            pmb_k_gather_identity<<<grid, 256, 0, ctx->stream>>>((const float *) data, (double *) out, n);
+        else
+            pmb_k_gather_identity<<<grid, 256, 0, ctx->stream>>>((const float *) data, (float *) out, n);
+        PMB_LAUNCH_CHECK(ctx);
+        return PMB_OK;
+    }
     double *acc = (double *) out;
     if (out_elsize == 4) {
         void *tmp;

@@ -438,6 +438,7 @@ struct TfArgs {
     const double *ktab[3];   // wavenumber per global index of each (left-padded) axis
     const double *mtab;      // per-index multiplier along the direction axis (or window factors, 3 axes)
     int dd;                  // direction axis (left-padded index)
+    double pre;              // scalar folded into the multiplier (a pending normalisation of the input)
     double p0;
 };
 
@@ -494,6 +495,8 @@ __device__ __forceinline__ void pmb_tf_apply(const C *__restrict__ in, C *__rest
         re = 0; im = a.mtab[idir];
         break;
     }
+    re = re * a.pre;
+    im = im * a.pre;
     const C v = in[t];
     C o;
     o.x = (decltype(o.x)) ((double) v.x * re - (double) v.y * im);
@@ -535,6 +538,12 @@ pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int
 
 extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_h, const double *boxsize_h,
                             const void *in, void *out)
+{
+    return pmb_transfer_scaled(f, kind, dir, params_h, boxsize_h, 1.0, in, out);
+}
+
+extern "C" int pmb_transfer_scaled(pmb_fft *f, int kind, int dir, const double *params_h, const double *boxsize_h,
+                                   double prefactor, const void *in, void *out)
 {
     PMB_REQUIRE(f && boxsize_h && in && out, "null argument");
     PMB_REQUIRE(kind >= PMB_TF_SCALE && kind <= PMB_TF_IK, "unknown transfer kind %d", kind);
@@ -597,6 +606,7 @@ extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_
     a.mtab = (const double *) dev + ntab;
     a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1;
     a.p0 = params_h ? params_h[0] : 0.0;
+    a.pre = prefactor;
     int64_t nrows, rowlen;
     if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
     else { nrows = f->m1 * f->nc; rowlen = f->n[0]; }

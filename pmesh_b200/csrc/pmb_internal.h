@@ -43,6 +43,7 @@ struct pmb_ctx {
     int64_t route_npart;
     int route_nblocks;
     int64_t route_per_block;
+    int route_identity;      // the last pmb_decompose_count found indices = arange(npart) to a single rank
     size_t det_chunk_bytes;  // workspace budget of the deterministic paint
     // chunk schedule of the tuned 3-D paint / readout kernels (see pmb_resample.cu)
     void *sched_buf;

@@ -63,8 +63,12 @@ class Layout(object):
     Do not create a Layout directly; use :py:meth:`GridND.decompose`.
     Useful methods are :py:meth:`exchange` and :py:meth:`gather`.
     """
-    def __init__(self, comm, sendlength, sendcounts, indices, recvcounts=None):
+    def __init__(self, comm, sendlength, sendcounts, indices, recvcounts=None, identity=False):
         self.comm = comm
+        # identity: every particle is sent exactly once, in order (indices = arange(sendlength));
+        # found by the routing for a single periodic domain.  `indices` is then built only on demand
+        # and exchange / gather skip the index indirection.
+        self.identity = bool(identity)
         sendcounts = numpy.asarray(sendcounts)
         assert self.comm.size == sendcounts.shape[0]
 
@@ -85,7 +89,11 @@ class Layout(object):
         self.sendlength = sendlength
         self.recvlength = self.recvcounts.sum()
 
-        if is_device(indices):
+        if indices is None:
+            assert self.identity
+            self._indices_dev = None
+            self._indices_host = None
+        elif is_device(indices):
             self._indices_dev = indices
             self._indices_host = None
         else:
@@ -96,14 +104,21 @@ class Layout(object):
     @property
     def indices(self):
         if self._indices_host is None:
-            self._indices_host = self._indices_dev.to_host()
+            if self._indices_dev is None:
+                self._indices_host = numpy.arange(self.sendlength, dtype='int32')
+            else:
+                self._indices_host = self._indices_dev.to_host()
         return self._indices_host
 
     @property
     def indices_device(self):
         if self._indices_dev is None:
-            self._indices_dev = DeviceArray.from_host(self._indices_host)
+            self._indices_dev = DeviceArray.from_host(self.indices)
         return self._indices_dev
+
+    def _indices_ptr(self):
+        """device pointer of indices, or NULL for the identity layout (the library then skips the indirection)"""
+        return None if self.identity else self.indices_device.ptr
 
     def get_exchange_cost(self):
         """ exchange cost of every rank: items sent to ranks other than itself (domain.py:125-136) """
@@ -162,9 +177,14 @@ class Layout(object):
         ctx = ddata.ctx
         itemsize = int(numpy.prod(trailing, dtype='i8')) * dtype.itemsize
         nsend = int(self.sendcounts.sum())
-        send = DeviceArray.empty((nsend, itemsize), 'u1')
-        # buffer = data.take(indices, axis=0)  (domain.py:188)
-        _lib.check(ctx.lib.pmb_take(ctx.handle, ddata.ptr, itemsize, self.indices_device.ptr, nsend, send.ptr))
+        if self.identity:
+            # take(arange) is the data itself: device arrays are handed on without a copy (a host
+            # input was copied to the device just above, so the caller's array is never aliased)
+            send = ddata
+        else:
+            send = DeviceArray.empty((nsend, itemsize), 'u1')
+            # buffer = data.take(indices, axis=0)  (domain.py:188)
+            _lib.check(ctx.lib.pmb_take(ctx.handle, ddata.ptr, itemsize, self.indices_device.ptr, nsend, send.ptr))
         recv = self._alltoallv(ctx, send, self.sendcounts, self.sendoffsets, self.recvlength,
                                self.recvcounts, self.recvoffsets, itemsize)
         out = DeviceArray((int(self.recvlength),) + tuple(trailing), dtype, ptr=recv.ptr, base=recv, ctx=ctx)
@@ -221,7 +241,7 @@ class Layout(object):
                 dout = DeviceArray.empty((int(self.sendlength),) + tuple(trailing), odt)
             offs = numpy.zeros(self.comm.size + 1, dtype='i8')
             offs[1:] = numpy.cumsum(self.sendcounts)
-            _lib.check(ctx.lib.pmb_gather_sum(ctx.handle, back.ptr, dtype.itemsize, ncomp, self.indices_device.ptr,
+            _lib.check(ctx.lib.pmb_gather_sum(ctx.handle, back.ptr, dtype.itemsize, ncomp, self._indices_ptr(),
                                               offs.ctypes.data, self.comm.size, int(self.sendlength),
                                               dout.ptr, dout.dtype.itemsize))
             if is_device(out):
@@ -471,6 +491,10 @@ class GridND(object):
         counts = numpy.zeros(self.comm.size, dtype='int32')
         ntotal = ctypes.c_int64(0)
         _lib.check(ctx.lib.pmb_decompose_count(ctx.handle, ctypes.byref(a), counts.ctypes.data, ctypes.byref(ntotal)))
+        ident = ctypes.c_int(0)
+        _lib.check(ctx.lib.pmb_decompose_identity(ctx.handle, ctypes.byref(ident)))
+        if ident.value:
+            return Layout(comm=self.comm, sendlength=Npoint, sendcounts=counts, indices=None, identity=True)
         indices = DeviceArray.empty((int(ntotal.value),), 'int32')
         _lib.check(ctx.lib.pmb_decompose_fill(ctx.handle, ctypes.byref(a), indices.ptr))
 

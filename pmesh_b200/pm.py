@@ -153,7 +153,7 @@ class Field(NDArrayLike):
         r = self.pm.create(_gettype(self))
         if self._dev_valid:
             self.pm.ctx.d2d(r._base.dev.ptr, self._base.dev.ptr, self._base.dev.nbytes)
-            r._mark_device_written()
+            r._mark_device_written(pending=self._pending)
         else:
             r._host[...] = self._host
             r._dev_valid = False
@@ -195,6 +195,10 @@ class Field(NDArrayLike):
         self._host_arr = None
         self._host_valid = False
         self._dev_valid = True
+        # a scalar factor not yet multiplied into the device values (value == _pending * memory).
+        # scale() and the 1/prod(Nmesh) of r2c only update it; the linear consumers that multiply
+        # anyway (r2c, c2r, the transfer kernels) fold it in, everything else materialises it first.
+        self._pending = 1.0
 
         self.x = pm.create_coords(type(self), return_indices=False)
         self.i = pm.create_coords(type(self), return_indices=True)
@@ -213,8 +217,21 @@ class Field(NDArrayLike):
             self._host_arr = numpy.zeros(self.shape, dtype=self._dtype)
         return self._host_arr
 
+    def _materialize(self):
+        """multiply a pending scalar factor into the device values"""
+        if self._pending != 1.0:
+            factor, self._pending = self._pending, 1.0
+            ctx = self.pm.ctx
+            es = self.pm.dtype.itemsize
+            # flat over the dense storage (for real fields this includes the r2c padding, harmlessly)
+            nreal = self._padded_reals if isinstance(self, RealField) else 2 * self.size
+            n = (ctypes.c_int64 * 3)(nreal)
+            st = (ctypes.c_int64 * 3)(es)
+            _lib.check(ctx.lib.pmb_field_scale(ctx.handle, self._dev.ptr, es, 0, 1, n, st, float(factor)))
+
     def _sync_host(self):
         if not self._host_valid:
+            self._materialize()
             self._host[...] = self._dev.to_host()
             self._host_valid = True
 
@@ -231,6 +248,7 @@ class Field(NDArrayLike):
         self._host[...] = v
         self._host_valid = True
         self._dev_valid = False
+        self._pending = 1.0
 
     def readonly_value(self):
         """host copy of the values without invalidating the device copy"""
@@ -239,9 +257,12 @@ class Field(NDArrayLike):
         r.flags.writeable = False
         return r
 
-    def _device(self):
-        """DeviceArray view of the field, uploading the host mirror if it is authoritative"""
+    def _device(self, absorb=False):
+        """DeviceArray view of the field, uploading the host mirror if it is authoritative.
+        absorb=True: the caller folds ``self._pending`` into its own arithmetic; otherwise the pending
+        factor is multiplied in first."""
         if not self._dev_valid:
+            assert self._pending == 1.0
             h = self._host
             if self.size:
                 extent = sum((n - 1) * s for n, s in zip(self.shape, self._layout_strides)) + self._dtype.itemsize
@@ -249,11 +270,14 @@ class Field(NDArrayLike):
                 numpy.ndarray(self.shape, self._dtype, buffer=hull, strides=self._layout_strides)[...] = h
                 self.pm.ctx.h2d(self._dev.ptr, hull, extent)
             self._dev_valid = True
+        if not absorb:
+            self._materialize()
         return self._dev
 
-    def _mark_device_written(self):
+    def _mark_device_written(self, pending=1.0):
         self._dev_valid = True
         self._host_valid = False
+        self._pending = float(pending)
 
     @property
     def flat(self):
@@ -286,15 +310,10 @@ class Field(NDArrayLike):
 
     def scale(self, factor):
         """value[...] *= factor on the device (the `rho[...] *= fac` step of the force, nbody.py:205-207)"""
-        ctx = self.pm.ctx
-        d = self._device()
-        # flat over the dense storage (for real fields this includes the r2c padding, harmlessly)
-        es = self.pm.dtype.itemsize
-        nreal = self._padded_reals if isinstance(self, RealField) else 2 * self.size
-        n = (ctypes.c_int64 * 3)(nreal)
-        st = (ctypes.c_int64 * 3)(es)
-        _lib.check(ctx.lib.pmb_field_scale(ctx.handle, d.ptr, es, 0, 1, n, st, float(factor)))
-        self._mark_device_written()
+        # lazy: the factor is carried along and folded into the next r2c / transfer kernel (or
+        # multiplied in by one streaming pass as soon as anything else looks at the values)
+        self._device(absorb=True)
+        self._mark_device_written(pending=self._pending * float(factor))
         return self
 
     # ------------------------------------------------------------------ collective indexing (host-side, not hot)
@@ -411,10 +430,11 @@ class Field(NDArrayLike):
         if tf is not None and isinstance(self, BaseComplexField) and isinstance(out, BaseComplexField) \
                 and kind == tf.apply_kind:
             ctx = self.pm.ctx
-            src = self._device()
+            src = self._device(absorb=True)
             params = (ctypes.c_double * 4)(*tf.params())
             box = (ctypes.c_double * 3)(*[float(b) for b in self.BoxSize])
-            _lib.check(ctx.lib.pmb_transfer(self.pm._plan, tf.kind, int(tf.direction), params, box, src.ptr, out._dev.ptr))
+            _lib.check(ctx.lib.pmb_transfer_scaled(self.pm._plan, tf.kind, int(tf.direction), params, box,
+                                                   float(self._pending), src.ptr, out._dev.ptr))
             out._mark_device_written()
             return out
 
@@ -460,11 +480,13 @@ class RealField(Field):
             out = TransposedComplexField(self.pm, base=self._base)
         assert isinstance(out, (BaseComplexField,))
         ctx = self.pm.ctx
-        src = self._device()
-        # PFFT normalization, same as FastPM
+        src = self._device(absorb=True)
+        # PFFT normalization, same as FastPM (pm.py:692) -- carried as the pending factor of the
+        # result together with whatever was pending on the input (the transform is linear)
         scale = float(numpy.prod(self.Nmesh ** -1.0))
-        _lib.check(ctx.lib.pmb_fft_r2c(self.pm._plan, src.ptr, out._dev.ptr, scale))
-        out._mark_device_written()
+        pending = self._pending * scale
+        _lib.check(ctx.lib.pmb_fft_r2c(self.pm._plan, src.ptr, out._dev.ptr, 1.0))
+        out._mark_device_written(pending=pending)
         if out._base is self._base:
             self._host_valid = False     # the real values are gone
         return out
@@ -636,9 +658,10 @@ class BaseComplexField(Field):
             out = RealField(self.pm, self._base)
         assert isinstance(out, RealField)
         ctx = self.pm.ctx
-        src = self._device()
+        src = self._device(absorb=True)
+        pending = self._pending
         _lib.check(ctx.lib.pmb_fft_c2r(self.pm._plan, src.ptr, out._dev.ptr))
-        out._mark_device_written()
+        out._mark_device_written(pending=pending)
         if out._base is self._base:
             self._host_valid = False
         return out

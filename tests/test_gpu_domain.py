@@ -140,6 +140,50 @@ def test_single_rank_exchange_gather(D, oracle):
         layout.exchange(pos[:10])
 
 
+def test_identity_layout_fast_path(D, oracle):
+    """a single periodic domain: the routing never looks at the positions (indices = arange, built on
+    demand), exchange hands device arrays on without a copy and gather('sum') is out = 0.0 + data;
+    counts / indices still equal the oracle's, also when the one domain belongs to a P-rank job"""
+    from pmesh_b200.device import DeviceArray
+    rng = numpy.random.default_rng(11)
+    pos = rng.uniform(-8, 16, (3000, 3))                   # out-of-box positions wrap into the one domain
+    for P in (1, 3):
+        g = D.GridND([numpy.array([0, 8.])] * 3, comm=FakeComm(0, P))
+        layout = g.decompose(pos, smoothing=1.0)
+        assert layout.identity
+        counts, indices = oracle.decompose(pos, g.edges, P, smoothing=1.0)
+        assert_array_equal(layout.sendcounts, counts)
+        assert_array_equal(layout.indices, indices)
+        assert layout.indices.dtype == numpy.dtype("int32")
+        assert_array_equal(layout.indices_device.to_host(), indices)
+    g = D.GridND([numpy.array([0, 8.])] * 3)
+    layout = g.decompose(pos, smoothing=1.0)
+    dpos = DeviceArray.from_host(pos)
+    lpos = layout.exchange(dpos)
+    assert lpos.ptr == dpos.ptr                            # no copy for device-resident columns
+    assert_array_equal(lpos.to_host(), pos)
+    hp = layout.exchange(pos)
+    assert hp is not pos and not numpy.shares_memory(hp, pos)
+    assert_array_equal(hp, pos)
+    for dt, odt in (("f8", "f8"), ("f4", "f4"), ("f8", "f4"), ("f4", "f8")):
+        v = rng.uniform(-1, 1, 3000).astype(dt)
+        v[:4] = [-0.0, 0.0, numpy.inf, -1e-300]
+        out = DeviceArray.empty((3000,), odt)
+        layout.gather(DeviceArray.from_host(v), mode="sum", out=out)
+        want = numpy.bincount(numpy.arange(3000), weights=v, minlength=3000).astype(odt)
+        got = out.to_host()
+        assert_array_equal(got, want)
+        assert_array_equal(numpy.signbit(got), numpy.signbit(want))   # 0.0 + -0.0 == +0.0, as bincount
+    v3 = rng.uniform(-1, 1, (3000, 3))
+    assert_array_equal(layout.gather(v3, mode="sum"), v3)
+    # a non-periodic single domain is NOT the identity (particles outside are dropped)
+    gn = D.GridND([numpy.array([0, 8.])] * 3, periodic=False)
+    ln = gn.decompose(pos, smoothing=1.0)
+    counts, indices = oracle.decompose(pos, gn.edges, 1, smoothing=1.0, periodic=False)
+    assert_array_equal(ln.sendcounts, counts)
+    assert_array_equal(ln.indices, indices)
+
+
 def test_gather_sum_matches_bincount(D, oracle):
     """the ghost reduction kernel against numpy.bincount on a fabricated multi-rank layout"""
     from pmesh_b200.device import DeviceArray
