@@ -174,6 +174,12 @@ int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const int32_t *in
  * indices == NULL: the identity layout, out[i] = 0.0 + data[i]. */
 int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
                    const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize);
+/* the same reduction with one device pointer per rank segment (segments_h[r] = first record of the
+ * segment of rank r; host array of nranks device pointers): lets the caller leave its own ghosts where
+ * they are instead of copying them through the reverse alltoallv (domain.py:274-281 self block). */
+int pmb_gather_sum_segments(pmb_ctx *ctx, const void *const *segments_h, int data_elsize, int ncomp,
+                            const int32_t *indices, const int64_t *offsets_h, int nranks, int64_t nout,
+                            void *out, int out_elsize);
 
 /* ---- communicator (NCCL over NVLink), one rank per process ------------------------ */
 int pmb_comm_unique_id(char *id128_h);                      /* 128 bytes */

@@ -64,7 +64,7 @@ SYMBOLS = [
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
     "pmb_paint", "pmb_readout", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum",
     "pmb_particles_uniform", "pmb_particles_lattice",
-    "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum",
+    "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
     "pmb_fft_create", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_library_ms",
@@ -95,6 +95,7 @@ _ARGTYPES = {
     "pmb_decompose_identity": [_P, _P],
     "pmb_take": [_P, _P, _L, _P, _L, _P],
     "pmb_gather_sum": [_P, _P, _I, _I, _P, _P, _I, _L, _P, _I],
+    "pmb_gather_sum_segments": [_P, _P, _I, _I, _P, _P, _I, _L, _P, _I],
     "pmb_comm_unique_id": [_P], "pmb_comm_init_rank": [_P, _P, _I, _I], "pmb_comm_destroy": [_P],
     "pmb_comm_rank": [_P, _P, _P],
     "pmb_alltoallv": [_P, _P, _P, _P, _P, _P, _P, _L],

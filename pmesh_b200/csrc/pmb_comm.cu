@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pmb_internal.h"
 
@@ -182,6 +183,36 @@ extern "C" int pmb_barrier(pmb_ctx *ctx)
         PMB_CUDA(cudaMemsetAsync(token, 0, 8, ctx->stream));
         PMB_NCCL(g_nccl.AllReduce(token, token, 1, ncclDouble, ncclSum, (ncclComm_t) ctx->comm, ctx->stream));
     }
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMB_OK;
+}
+
+// ---- internal helpers (pmb_internal.h) ---------------------------------------------------------
+// in-stream barrier: every rank's stream has reached this point when the allreduce completes; the
+// host does not wait.  Used to order direct peer-memory writes (pmb_fft.cu) between GPUs.
+int pmb_stream_barrier(pmb_ctx *ctx)
+{
+    if (ctx->nranks <= 1) return PMB_OK;
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    if (!ctx->barrier_token) {
+        PMB_CUDA(cudaMalloc(&ctx->barrier_token, 256));
+        PMB_CUDA(cudaMemsetAsync(ctx->barrier_token, 0, 256, ctx->stream));
+    }
+    PMB_NCCL(g_nccl.AllReduce(ctx->barrier_token, ctx->barrier_token, 1, ncclInt, ncclMax, (ncclComm_t) ctx->comm, ctx->stream));
+    return PMB_OK;
+}
+
+// allgather of small host records (setup paths only): staged through device scratch, synchronous
+int pmb_allgather_host(pmb_ctx *ctx, const void *send_h, void *recv_h, size_t nbytes)
+{
+    if (ctx->nranks <= 1) { memcpy(recv_h, send_h, nbytes); return PMB_OK; }
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    void *dev;
+    PMB_CHECK(pmb_scratch(ctx, nbytes * (size_t) (ctx->nranks + 1), &dev));
+    char *dsend = (char *) dev, *drecv = (char *) dev + nbytes;
+    PMB_CUDA(cudaMemcpyAsync(dsend, send_h, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    PMB_NCCL(g_nccl.AllGather(dsend, drecv, nbytes, ncclChar, (ncclComm_t) ctx->comm, ctx->stream));
+    PMB_CUDA(cudaMemcpyAsync(recv_h, drecv, nbytes * (size_t) ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
     PMB_CUDA(cudaStreamSynchronize(ctx->stream));
     return PMB_OK;
 }

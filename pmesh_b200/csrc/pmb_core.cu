@@ -76,6 +76,7 @@ extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
         if (ctx->tables[k].d_values) cudaFree(ctx->tables[k].d_values);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->barrier_token) cudaFree(ctx->barrier_token);
     if (ctx->route_masks) cudaFree(ctx->route_masks);
     if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
     if (ctx->sched_buf) cudaFree(ctx->sched_buf);

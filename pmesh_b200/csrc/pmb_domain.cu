@@ -75,19 +75,24 @@ __device__ __forceinline__ double pmb_pymod_fast(double a, double b)
 }
 
 // per-particle rank mask; ref: pmesh/domain.py:609-630 (sil/sir) + pmesh/_domain.pyx:62-100 (patch walk)
-__device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t i)
+// NDIM is a compile-time constant so that sil / sir / the patch odometer live in registers; `edges`
+// point into shared memory (the binary searches of digitize never leave the SM).
+template <int NDIM>
+__device__ __forceinline__ uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, const void *pos,
+                                                   int elsize, int64_t ps0, int64_t ps1, int64_t i)
 {
-    int sil[3], sir[3];
-    for (int d = 0; d < g.ndim; d++) {
+    int sil[NDIM], sir[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
         if (g.periodic && g.shape[d] == 1) {
             // one periodic domain on this axis: sil = p - 1, sir = p, and the single patch cell wraps
             // to domain 0 whatever the coordinate is (also for NaN: digitize gives len(edges))
             sil[d] = 0; sir[d] = 1;
             continue;
         }
-        const double x = g.scale[d] * pmb_ld_real(pos, i * ps0 + d * ps1, elsize);
+        const double x = g.scale[d] * pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize);
         const double sm = g.smoothing[d];
-        const double *e = g.edges[d];
+        const double *e = edges[d];
         const int ne = g.nedges[d];
         int l, r;
         if (g.periodic) {
@@ -109,12 +114,14 @@ __device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsi
         sir[d] = (int) (int16_t) r;
     }
     long long patch = 1;
-    int p[3];
-    for (int d = 0; d < g.ndim; d++) { patch *= (sir[d] - sil[d]); p[d] = sil[d]; }
+    int p[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) { patch *= (sir[d] - sil[d]); p[d] = sil[d]; }
     uint64_t mask = 0;
     for (long long q = 0; q < patch; q++) {
         int target = 0;
-        for (int d = 0; d < g.ndim; d++) {
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) {
             int t = p[d];
             if (g.periodic) {      // sil >= -shape - 1 and sir <= 2 shape: a few conditional steps, no division
                 const int n = g.shape[d];
@@ -129,20 +136,34 @@ __device__ uint64_t pmb_route_mask(const RouteGeom &g, const void *pos, int elsi
             const int deg = (rank >= 0 && rank < g.ndomains) ? g.degenerate[rank] : 0;
             if (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) mask |= (uint64_t) 1 << rank;
         }
-        p[g.ndim - 1] += 1;
-        for (int d = g.ndim - 1; d > 0; d--) {
-            if (p[d] == sir[d]) { p[d] = sil[d]; p[d - 1] += 1; } else break;
+        p[NDIM - 1] += 1;
+#pragma unroll
+        for (int d = NDIM - 1; d > 0; d--) {
+            if (p[d] == sir[d]) { p[d] = sil[d]; p[d - 1] += 1; }
         }
     }
     return mask;
 }
 
-// block b owns particles [b*per_block, (b+1)*per_block)
+// block b owns particles [b*per_block, (b+1)*per_block).  MaskT: the narrowest unsigned type that
+// holds one bit per rank (1 byte per particle up to 8 ranks instead of 8).
+template <int NDIM, typename MaskT>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t npart,
-                  int64_t per_block, uint64_t *masks, int32_t *blockhist)
+                  int64_t per_block, MaskT *masks, int32_t *blockhist)
 {
     __shared__ int hist[ROUTE_MAXRANKS];
+    extern __shared__ double s_edges[];
+    const double *edges[NDIM];
+    {
+        int o = 0;
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) {
+            for (int k = threadIdx.x; k < g.nedges[d]; k += ROUTE_BLOCK) s_edges[o + k] = g.edges[d][k];
+            edges[d] = s_edges + o;
+            o += g.nedges[d];
+        }
+    }
     if (threadIdx.x < ROUTE_MAXRANKS) hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t begin = blockIdx.x * per_block;
@@ -152,8 +173,8 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
         const int64_t i = base + threadIdx.x;
         uint64_t mask = 0;
         if (i < end) {
-            mask = g.all_trivial ? g.const_mask : pmb_route_mask(g, pos, elsize, ps0, ps1, i);
-            masks[i] = mask;
+            mask = pmb_route_mask<NDIM>(g, edges, pos, elsize, ps0, ps1, i);
+            __stcs(masks + i, (MaskT) mask);
         }
         for (int r = 0; r < g.nranks; r++) {
             unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
@@ -187,8 +208,9 @@ __global__ void pmb_k_route_cursors(int32_t *blockhist, int nblocks, int nranks,
     }
 }
 
+template <typename MaskT>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
-pmb_k_route_fill(int nranks, int64_t npart, int64_t per_block, const uint64_t *masks,
+pmb_k_route_fill(int nranks, int64_t npart, int64_t per_block, const MaskT *masks,
                  const int32_t *blockcursor, int32_t *indices)
 {
     __shared__ int cursor[ROUTE_MAXRANKS];
@@ -201,7 +223,7 @@ pmb_k_route_fill(int nranks, int64_t npart, int64_t per_block, const uint64_t *m
     const unsigned lt = (1u << lane) - 1u;
     for (int64_t base = begin; base < end; base += ROUTE_BLOCK) {
         const int64_t i = base + threadIdx.x;
-        const uint64_t mask = i < end ? masks[i] : 0;
+        const uint64_t mask = i < end ? (uint64_t) __ldcs(masks + i) : 0;
         for (int r = 0; r < nranks; r++) {
             unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
             if (lane == 0) warpcount[warp][r] = __popc(b);
@@ -336,9 +358,22 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
         pmb_set_error("internal: routing scratch too small");
         return PMB_EINVAL;
     }
-    pmb_k_route_count<<<(int) nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
-        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_block,
-        (uint64_t *) ctx->route_masks, hist);
+    int tot_edges = 0;
+    for (int d = 0; d < a->ndim; d++) tot_edges += a->nedges[d];
+    const size_t smem = sizeof(double) * tot_edges;
+    ctx->route_maskbytes = a->nranks <= 8 ? 1 : (a->nranks <= 16 ? 2 : 8);
+#define ROUTE_COUNT(ND, MT)                                                                          \
+    pmb_k_route_count<ND, MT><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(                     \
+        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_block, (MT *) ctx->route_masks, hist)
+#define ROUTE_COUNT_ND(MT)                                                                           \
+    do {                                                                                             \
+        if (a->ndim == 1) ROUTE_COUNT(1, MT); else if (a->ndim == 2) ROUTE_COUNT(2, MT); else ROUTE_COUNT(3, MT); \
+    } while (0)
+    if (ctx->route_maskbytes == 1) ROUTE_COUNT_ND(uint8_t);
+    else if (ctx->route_maskbytes == 2) ROUTE_COUNT_ND(uint16_t);
+    else ROUTE_COUNT_ND(unsigned long long);
+#undef ROUTE_COUNT_ND
+#undef ROUTE_COUNT
     ctx->launches++;
     pmb_k_route_scan<<<1, ROUTE_MAXRANKS, 0, ctx->stream>>>(hist, (int) nblocks, a->nranks, totals);
     ctx->launches++;
@@ -390,9 +425,15 @@ extern "C" int pmb_decompose_fill(pmb_ctx *ctx, const pmb_decompose_args *a, int
     if (a->npart == 0 || ctx->route_nblocks == 0) return PMB_OK;
     PMB_REQUIRE(indices, "null indices");
     const int64_t per_block = ctx->route_per_block;
-    pmb_k_route_fill<<<ctx->route_nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
-        a->nranks, a->npart, per_block, (const uint64_t *) ctx->route_masks,
-        (const int32_t *) ctx->route_blockhist, indices);
+    if (ctx->route_maskbytes == 1)
+        pmb_k_route_fill<uint8_t><<<ctx->route_nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
+            a->nranks, a->npart, per_block, (const uint8_t *) ctx->route_masks, (const int32_t *) ctx->route_blockhist, indices);
+    else if (ctx->route_maskbytes == 2)
+        pmb_k_route_fill<uint16_t><<<ctx->route_nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
+            a->nranks, a->npart, per_block, (const uint16_t *) ctx->route_masks, (const int32_t *) ctx->route_blockhist, indices);
+    else
+        pmb_k_route_fill<unsigned long long><<<ctx->route_nblocks, ROUTE_BLOCK, 0, ctx->stream>>>(
+            a->nranks, a->npart, per_block, (const unsigned long long *) ctx->route_masks, (const int32_t *) ctx->route_blockhist, indices);
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }
@@ -465,17 +506,18 @@ extern "C" int pmb_take(pmb_ctx *ctx, const void *data, int64_t itemsize, const 
 // exactly that order without atomics: acc[indices[j]] = acc[indices[j]] + data[j].
 template <bool ASSIGN>
 __global__ void __launch_bounds__(256)
-pmb_k_gather_pass(const void *__restrict__ data, int data_elsize, int ncomp, const int32_t *__restrict__ indices,
+pmb_k_gather_pass(const void *__restrict__ seg, int data_elsize, int ncomp, const int32_t *__restrict__ indices,
                   int64_t begin, int64_t end, double *__restrict__ acc)
 {
-    int64_t t = begin * ncomp + blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    // seg points at the first record of the segment [begin, end) of `indices`
+    int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    const int64_t total = end * ncomp;
+    const int64_t total = (end - begin) * ncomp;
     for (; t < total; t += stride) {
         const int64_t j = ncomp == 1 ? t : t / ncomp;
         const int c = ncomp == 1 ? 0 : (int) (t - j * ncomp);
-        const int64_t o = (int64_t) __ldcs(indices + j) * ncomp + c;
-        const double v = data_elsize == 8 ? __ldcs((const double *) data + t) : (double) __ldcs((const float *) data + t);
+        const int64_t o = (int64_t) __ldcs(indices + begin + j) * ncomp + c;
+        const double v = data_elsize == 8 ? __ldcs((const double *) seg + t) : (double) __ldcs((const float *) seg + t);
         acc[o] = ASSIGN ? 0.0 + v : acc[o] + v;
     }
 }
@@ -499,15 +541,34 @@ __global__ void __launch_bounds__(256) pmb_k_gather_identity(const Tin *__restri
 extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, const int32_t *indices,
                               const int64_t *offsets_h, int nranks, int64_t nout, void *out, int out_elsize)
 {
-    PMB_REQUIRE(ctx && offsets_h && ncomp >= 1 && nout >= 0, "bad gather arguments");
+    PMB_REQUIRE(ctx && offsets_h && ncomp >= 1, "bad gather arguments");
+    PMB_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXRANKS, "gather supports 1..%d ranks", ROUTE_MAXRANKS);
+    PMB_REQUIRE(data_elsize == 4 || data_elsize == 8, "float32/float64 only");
+    PMB_REQUIRE(offsets_h[nranks] == 0 || data, "null data");
+    const void *segs[ROUTE_MAXRANKS];
+    for (int r = 0; r < nranks; r++) segs[r] = (const char *) data + offsets_h[r] * ncomp * data_elsize;
+    return pmb_gather_sum_segments(ctx, segs, data_elsize, ncomp, indices, offsets_h, nranks, nout, out, out_elsize);
+}
+
+extern "C" int pmb_gather_sum_segments(pmb_ctx *ctx, const void *const *segments_h, int data_elsize, int ncomp,
+                                       const int32_t *indices, const int64_t *offsets_h, int nranks, int64_t nout,
+                                       void *out, int out_elsize)
+{
+    PMB_REQUIRE(ctx && offsets_h && segments_h && ncomp >= 1 && nout >= 0, "bad gather arguments");
     PMB_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXRANKS, "gather supports 1..%d ranks", ROUTE_MAXRANKS);
     PMB_REQUIRE((data_elsize == 4 || data_elsize == 8) && (out_elsize == 4 || out_elsize == 8), "float32/float64 only");
     if (nout == 0) return PMB_OK;
     PMB_REQUIRE(out, "null out");
-    PMB_REQUIRE(offsets_h[nranks] == 0 || data, "null data");
+    for (int r = 0; r < nranks; r++)
+        PMB_REQUIRE(offsets_h[r + 1] <= offsets_h[r] || segments_h[r], "null data segment %d", r);
     const int64_t n = nout * ncomp;
     if (!indices && offsets_h[nranks] != 0) {
+        // identity layout: one segment that lists every row once, in order
+        int only = -1;
+        for (int r = 0; r < nranks; r++)
+            if (offsets_h[r + 1] > offsets_h[r]) { PMB_REQUIRE(only < 0, "identity gather needs a single segment"); only = r; }
         PMB_REQUIRE(offsets_h[nranks] == nout, "identity gather needs exactly one record per output row");
+        const void *data = segments_h[only];
         const int grid = pmb_grid(ctx, n, 256, 8);
         if (data_elsize == 8 && out_elsize == 8)
             pmb_k_gather_identity<<<grid, 256, 0, ctx->stream>>>((const double *) data, (double *) out, n);
@@ -520,6 +581,7 @@ extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, i
         PMB_LAUNCH_CHECK(ctx);
         return PMB_OK;
     }
+    PMB_REQUIRE(offsets_h[nranks] == 0 || indices, "null indices");
     double *acc = (double *) out;
     if (out_elsize == 4) {
         void *tmp;
@@ -537,10 +599,10 @@ extern "C" int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, i
         first = false;
         if (assign)
             pmb_k_gather_pass<true><<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
-                data, data_elsize, ncomp, indices, b, e, acc);
+                segments_h[r], data_elsize, ncomp, indices, b, e, acc);
         else
             pmb_k_gather_pass<false><<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
-                data, data_elsize, ncomp, indices, b, e, acc);
+                segments_h[r], data_elsize, ncomp, indices, b, e, acc);
         PMB_LAUNCH_CHECK(ctx);
     }
     if (first) PMB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * n, ctx->stream));

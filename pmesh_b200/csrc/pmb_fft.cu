@@ -15,6 +15,7 @@
 #include <cufft.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pmb_internal.h"
 
@@ -35,6 +36,12 @@ struct pmb_fft {
     bool have_full, have_slab;
     void *work0, *work1;
     size_t work_bytes;
+    // direct peer-memory global transpose (P > 1): every rank exposes two landing buffers through
+    // CUDA IPC; the transpose kernels of the other ranks store straight into them over NVLink
+    int p2p;                      // 1: peer path armed, 0: NCCL send/recv path
+    int xcur;                     // landing buffer used by the next transform (they alternate)
+    void *xbuf[2];                // my landing buffers (cudaMalloc, IPC-exported)
+    void *peer_x[64][2];          // the same buffers of every rank, mapped into this process
     cudaEvent_t ev[FFT_NEV][2];
     int nev;
     float lib_ms;
@@ -70,6 +77,72 @@ static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long lo
     PMB_CUFFT(cufftMakePlanMany64(*h, rank, n, inembed, 1, idist, onembed, 1, odist, type, batch, &ws));
     PMB_CUFFT(cufftSetStream(*h, f->ctx->stream));
     return PMB_OK;
+}
+
+// ---- peer-memory landing buffers -------------------------------------------------------------------
+// One process per GPU: the buffers are shared with cudaIpc handles, exchanged once per plan over the
+// communicator.  Any failure (IPC not permitted in the container, no peer access) leaves p2p = 0 on
+// EVERY rank -- the decision is agreed with an allgather -- and the transforms use NCCL send/recv.
+static int p2p_setup(pmb_fft *f)
+{
+    pmb_ctx *ctx = f->ctx;
+    f->p2p = 0;
+    f->xcur = 0;
+    const char *env = getenv("PMB_FFT_P2P");
+    const int want = env ? atoi(env) : 1;
+    struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad; } mine, all[64];
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = want && f->P <= 64;
+    if (mine.ok) {
+        for (int b = 0; b < 2 && mine.ok; b++) {
+            if (cudaMalloc(&f->xbuf[b], f->work_bytes) != cudaSuccess) { f->xbuf[b] = NULL; mine.ok = 0; break; }
+            if (cudaIpcGetMemHandle(&mine.h[b], f->xbuf[b]) != cudaSuccess) mine.ok = 0;
+        }
+        cudaGetLastError();
+    }
+    PMB_CHECK(pmb_allgather_host(ctx, &mine, all, sizeof(Rec)));
+    int ok = 1;
+    for (int q = 0; q < f->P; q++) ok = ok && all[q].ok;
+    if (ok) {
+        for (int q = 0; q < f->P && ok; q++)
+            for (int b = 0; b < 2 && ok; b++) {
+                if (q == f->rank) { f->peer_x[q][b] = f->xbuf[b]; continue; }
+                if (cudaIpcOpenMemHandle(&f->peer_x[q][b], all[q].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    f->peer_x[q][b] = NULL;
+                    ok = 0;
+                }
+            }
+        cudaGetLastError();
+    }
+    // second agreement: every rank could map every buffer
+    int mine_ok = ok, all_ok[64];
+    PMB_CHECK(pmb_allgather_host(ctx, &mine_ok, all_ok, sizeof(int)));
+    for (int q = 0; q < f->P; q++) ok = ok && all_ok[q];
+    f->p2p = ok;
+    if (!ok) {
+        for (int q = 0; q < f->P; q++)
+            for (int b = 0; b < 2; b++)
+                if (q != f->rank && f->peer_x[q][b]) { cudaIpcCloseMemHandle(f->peer_x[q][b]); f->peer_x[q][b] = NULL; }
+        // peers may still be unmapping: nobody frees before everybody is done
+        PMB_CHECK(pmb_allgather_host(ctx, &mine_ok, all_ok, sizeof(int)));
+        for (int b = 0; b < 2; b++) if (f->xbuf[b]) { cudaFree(f->xbuf[b]); f->xbuf[b] = NULL; }
+        cudaGetLastError();
+    }
+    return PMB_OK;
+}
+
+static void p2p_teardown(pmb_fft *f)
+{
+    if (!f->p2p) return;
+    for (int q = 0; q < f->P; q++)
+        for (int b = 0; b < 2; b++)
+            if (q != f->rank && f->peer_x[q][b]) cudaIpcCloseMemHandle(f->peer_x[q][b]);
+    // the owner frees only after every peer has unmapped (collective: plans are destroyed in the
+    // same order on every rank); if the communicator is already gone the process is exiting anyway
+    if (f->ctx->comm) pmb_stream_barrier(f->ctx);
+    cudaStreamSynchronize(f->ctx->stream);
+    for (int b = 0; b < 2; b++) if (f->xbuf[b]) cudaFree(f->xbuf[b]);
+    f->p2p = 0;
 }
 
 extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, pmb_fft **out)
@@ -135,6 +208,7 @@ extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int 
         f->work_bytes = (size_t) celems * 2 * dtype_elsize + 256;
         PMB_CUDA(cudaMalloc(&f->work0, f->work_bytes));
         PMB_CUDA(cudaMalloc(&f->work1, f->work_bytes));
+        PMB_CHECK(p2p_setup(f));
     }
     *out = f;
     return PMB_OK;
@@ -150,6 +224,7 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
         if (f->m0 > 0) { cufftDestroy(f->slab_r2c); cufftDestroy(f->slab_c2r); }
         if (f->m1 > 0) cufftDestroy(f->line);
     }
+    p2p_teardown(f);
     if (f->work0) cudaFree(f->work0);
     if (f->work1) cudaFree(f->work1);
     for (int i = 0; i < FFT_NEV; i++) { cudaEventDestroy(f->ev[i][0]); cudaEventDestroy(f->ev[i][1]); }
@@ -316,6 +391,99 @@ static int slab_pack(pmb_fft *f, const void *src, void *dst, int dir)
     return PMB_OK;
 }
 
+// Global transpose fused with the NVLink transfer: for every destination rank q the (R x ncols[q])
+// block  in[r * in_ld + col0[q] + c]  is written transposed,  out[q][c * out_ld + r] (* s), straight
+// into the landing buffer of rank q (peer memory; q == me is the local buffer).  32 x 32 tiles through
+// shared memory: 512-byte coalesced reads locally, 512-byte contiguous stores over NVLink.  Tiles are
+// dealt round-robin over the destinations, starting at my right neighbour, so that at any moment the
+// traffic is spread over all links / peers.
+struct XDest {
+    void *out[64];        // landing buffer of rank q, already offset to my first output column
+    int64_t col0[64];     // first source column of the block for rank q
+    int64_t ncols[64];    // columns of that block
+};
+
+template <typename C>
+__global__ void __launch_bounds__(256)
+pmb_k_xpose_scatter(const C *__restrict__ in, int64_t in_ld, int64_t R, int64_t out_ld, XDest d, int P, int me,
+                    double s, int64_t tiles_r, int64_t tiles_c_max)
+{
+    __shared__ C tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int64_t per_dest = tiles_r * tiles_c_max;
+    const int64_t ntiles = per_dest * P;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int q = (int) (t % P) + me + 1;
+        if (q >= P) q -= P;
+        const int64_t lt = t / P;
+        const int64_t tc = lt / tiles_r, tr = lt - tc * tiles_r;
+        const int64_t r0 = tr * 32, c0 = tc * 32;
+        const int64_t nc = d.ncols[q];
+        if (c0 >= nc) continue;          // uniform over the block
+        const C *src = in + d.col0[q];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < R && c < nc) tile[ty + 8 * k][tx] = src[r * in_ld + c];
+        }
+        __syncthreads();
+        C *dst = (C *) d.out[q];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t c = c0 + ty + 8 * k, r = r0 + tx;
+            if (r < R && c < nc) {
+                C v = tile[tx][ty + 8 * k];
+                v.x = (decltype(v.x)) (v.x * (decltype(v.x)) s);
+                v.y = (decltype(v.y)) (v.y * (decltype(v.y)) s);
+                dst[c * out_ld + r] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename C>
+static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, int64_t out_ld, const XDest &d, double s)
+{
+    int64_t cmax = 0;
+    for (int q = 0; q < f->P; q++) if (d.ncols[q] > cmax) cmax = d.ncols[q];
+    if (R == 0 || cmax == 0) return PMB_OK;
+    const int64_t tr = (R + 31) / 32, tc = (cmax + 31) / 32;
+    int64_t grid = tr * tc * f->P;
+    const int64_t cap = (int64_t) f->ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, in_ld, R, out_ld, d, f->P, f->rank, s, tr, tc);
+    PMB_LAUNCH_CHECK(f->ctx);
+    return PMB_OK;
+}
+
+// forward: work0 (m0, n1*nc) -> rank q gets the columns of its j-range, transposed, as rows
+// (m1_q*nc) x n0 with my planes at columns [s0, s0 + m0)
+static void xdest_fwd(const pmb_fft *f, int b, XDest *d)
+{
+    const size_t csz = 2 * (size_t) f->elsize;
+    for (int q = 0; q < f->P; q++) {
+        int64_t blk, s1q, m1q;
+        block_partition(f->n[1], f->P, q, &blk, &s1q, &m1q);
+        d->out[q] = (char *) f->peer_x[q][b] + (size_t) f->s0 * csz;
+        d->col0[q] = s1q * f->nc;
+        d->ncols[q] = m1q * f->nc;
+    }
+}
+// backward: work0 (m1*nc, n0) -> rank p gets the columns of its plane range, transposed, as rows
+// m0_p x (n1*nc) with my (j, k) lines at columns [s1*nc, (s1 + m1)*nc)
+static void xdest_bwd(const pmb_fft *f, int b, XDest *d)
+{
+    const size_t csz = 2 * (size_t) f->elsize;
+    for (int p = 0; p < f->P; p++) {
+        int64_t blk, s0p, m0p;
+        block_partition(f->n[0], f->P, p, &blk, &s0p, &m0p);
+        d->out[p] = (char *) f->peer_x[p][b] + (size_t) (f->s1 * f->nc) * csz;
+        d->col0[p] = s0p;
+        d->ncols[p] = m0p;
+    }
+}
+
 // counts / offsets (in complex elements) of the global transpose.
 // fwd: send to q the block (m0, m1_q, nc); receive from p the block (m0_p, m1, nc).
 static void slab_counts(const pmb_fft *f, int fwd, int64_t *sc, int64_t *so, int64_t *rc, int64_t *ro)
@@ -373,6 +541,22 @@ extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scal
     }
     // 1. local planes: 2-D r2c over (n1, n2):  real (m0, n1, 2nc) -> work0 (m0, n1, nc)
     if (f->m0 > 0) PMB_CHECK(exec_r2c(f, f->slab_r2c, real, f->work0));
+    if (f->p2p) {
+        // 2. transpose straight into the landing buffers of the owners of each j-range (NVLink
+        //    stores; normalisation folded in), 3. in-stream barrier, 4. lines along axis 0 out of
+        //    the landing buffer into the result.  Landing buffers alternate between transforms, so
+        //    a rank that runs ahead never overwrites a buffer a peer is still reading: it cannot
+        //    start transform t + 2 before everybody has passed the barrier of transform t + 1.
+        const int b = f->xcur;
+        f->xcur ^= 1;
+        XDest d;
+        xdest_fwd(f, b, &d);
+        if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, f->work0, f->n[1] * f->nc, f->m0, f->n[0], d, scale));
+        else PMB_CHECK(xpose_scatter<float2>(f, f->work0, f->n[1] * f->nc, f->m0, f->n[0], d, scale));
+        PMB_CHECK(pmb_stream_barrier(ctx));
+        if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, f->xbuf[b], cplx, CUFFT_FORWARD));
+        return PMB_OK;
+    }
     // 2. pack per destination
     if (f->elsize == 8) PMB_CHECK(slab_pack<double2>(f, f->work0, f->work1, 0));
     else PMB_CHECK(slab_pack<float2>(f, f->work0, f->work1, 0));
@@ -405,6 +589,19 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
     }
     // 1. inverse lines along axis 0: cplx (m1*nc, n0) -> work0 (input preserved)
     if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx, f->work0, CUFFT_INVERSE));
+    if (f->p2p) {
+        // 2. transpose straight into the (m0_p, n1, nc) plane layout of every owner p, 3. barrier,
+        // 4. 2-D c2r of my planes out of the landing buffer
+        const int b = f->xcur;
+        f->xcur ^= 1;
+        XDest d;
+        xdest_bwd(f, b, &d);
+        if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, f->work0, f->n[0], f->m1 * f->nc, f->n[1] * f->nc, d, 1.0));
+        else PMB_CHECK(xpose_scatter<float2>(f, f->work0, f->n[0], f->m1 * f->nc, f->n[1] * f->nc, d, 1.0));
+        PMB_CHECK(pmb_stream_barrier(ctx));
+        if (f->m0 > 0) PMB_CHECK(exec_c2r(f, f->slab_c2r, f->xbuf[b], real));
+        return PMB_OK;
+    }
     return c2r_from_work(f, real);
 }
 

@@ -35,6 +35,7 @@ struct pmb_ctx {
     // communicator
     ncclComm *comm;
     int rank, nranks;
+    void *barrier_token;     // device word of pmb_stream_barrier
     // routing state kept between pmb_decompose_count and pmb_decompose_fill
     void *route_masks;       // uint64 per particle
     size_t route_masks_bytes;
@@ -43,6 +44,7 @@ struct pmb_ctx {
     int64_t route_npart;
     int route_nblocks;
     int64_t route_per_block;
+    int route_maskbytes;     // 1 / 2 / 8: width of the per-particle rank mask of the last count
     int route_identity;      // the last pmb_decompose_count found indices = arange(npart) to a single rank
     size_t det_chunk_bytes;  // workspace budget of the deterministic paint
     // chunk schedule of the tuned 3-D paint / readout kernels (see pmb_resample.cu)
@@ -56,6 +58,8 @@ struct pmb_ctx {
 void pmb_set_error(const char *fmt, ...);
 int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out);
+int pmb_stream_barrier(pmb_ctx *ctx);
+int pmb_allgather_host(pmb_ctx *ctx, const void *send_h, void *recv_h, size_t nbytes);
 int pmb_resolve_window(pmb_ctx *ctx, int kind, int support_req, int ndim, const int *order,
                        PmbWindow *w, int for_device);
 

@@ -156,19 +156,19 @@ class Layout(object):
             raise ValueError(what)
         return DeviceArray.from_host(numpy.ascontiguousarray(data)), data.dtype, data.shape[1:], True
 
-    def _alltoallv(self, ctx, send, sendcounts, sendoffsets, nrecv, recvcounts, recvoffsets, itemsize):
-        """device alltoallv of `itemsize`-byte records; returns the receive buffer (bytes)"""
-        if self.comm.size == 1:
-            return send
+    def _alltoallv(self, ctx, send, sendcounts, sendoffsets, recv, recvcounts, recvoffsets, itemsize, skip_self=False):
+        """device alltoallv of `itemsize`-byte records from `send` into `recv`; with skip_self the
+        block a rank sends to itself is left to the caller"""
         self.comm.ensure_device_comm(ctx)
-        recv = DeviceArray.empty((int(nrecv), int(itemsize)), 'u1')
-        sc = numpy.ascontiguousarray(sendcounts, dtype='i8')
+        sc = numpy.array(sendcounts, dtype='i8')
         so = numpy.ascontiguousarray(sendoffsets, dtype='i8')
-        rc = numpy.ascontiguousarray(recvcounts, dtype='i8')
+        rc = numpy.array(recvcounts, dtype='i8')
         ro = numpy.ascontiguousarray(recvoffsets, dtype='i8')
+        if skip_self:
+            sc[self.comm.rank] = 0
+            rc[self.comm.rank] = 0
         _lib.check(ctx.lib.pmb_alltoallv(ctx.handle, send.ptr, sc.ctypes.data, so.ctypes.data,
                                          recv.ptr, rc.ctypes.data, ro.ctypes.data, int(itemsize)))
-        ctx.sync()
         return recv
 
     def _exchange(self, data):
@@ -177,16 +177,30 @@ class Layout(object):
         ctx = ddata.ctx
         itemsize = int(numpy.prod(trailing, dtype='i8')) * dtype.itemsize
         nsend = int(self.sendcounts.sum())
-        if self.identity:
+        me, P = self.comm.rank, self.comm.size
+        if self.identity and P == 1:
             # take(arange) is the data itself: device arrays are handed on without a copy (a host
             # input was copied to the device just above, so the caller's array is never aliased)
-            send = ddata
-        else:
-            send = DeviceArray.empty((nsend, itemsize), 'u1')
+            recv = ddata
+        elif P == 1:
+            recv = DeviceArray.empty((nsend, itemsize), 'u1')
             # buffer = data.take(indices, axis=0)  (domain.py:188)
-            _lib.check(ctx.lib.pmb_take(ctx.handle, ddata.ptr, itemsize, self.indices_device.ptr, nsend, send.ptr))
-        recv = self._alltoallv(ctx, send, self.sendcounts, self.sendoffsets, self.recvlength,
-                               self.recvcounts, self.recvoffsets, itemsize)
+            _lib.check(ctx.lib.pmb_take(ctx.handle, ddata.ptr, itemsize, self._indices_ptr(), nsend, recv.ptr))
+        else:
+            # records that stay on this rank are gathered straight into their place in the receive
+            # buffer; only what really leaves is packed into `send` and goes through NCCL
+            recv = DeviceArray.empty((int(self.recvlength), itemsize), 'u1')
+            send = DeviceArray.empty((nsend, itemsize), 'u1')
+            s0, sn = int(self.sendoffsets[me]), int(self.sendcounts[me])
+            ip = self._indices_ptr()
+            for a, b, dst in ((0, s0, send.ptr), (s0, s0 + sn, recv.ptr + int(self.recvoffsets[me]) * itemsize),
+                              (s0 + sn, nsend, send.ptr + (s0 + sn) * itemsize)):
+                if b > a:
+                    src_idx = None if ip is None else ip + 4 * a
+                    src = ddata.ptr + (a * itemsize if ip is None else 0)
+                    _lib.check(ctx.lib.pmb_take(ctx.handle, src, itemsize, src_idx, b - a, dst))
+            self._alltoallv(ctx, send, self.sendcounts, self.sendoffsets, recv,
+                            self.recvcounts, self.recvoffsets, itemsize, skip_self=True)
         out = DeviceArray((int(self.recvlength),) + tuple(trailing), dtype, ptr=recv.ptr, base=recv, ctx=ctx)
         if was_host:
             return out.to_host()
@@ -222,9 +236,15 @@ class Layout(object):
         ncomp = int(numpy.prod(trailing, dtype='i8'))
         itemsize = ncomp * dtype.itemsize
         nback = int(self.sendcounts.sum())
-        # reverse Alltoallv: what I received goes back to its origin (domain.py:274-281)
-        back = self._alltoallv(ctx, ddata, self.recvcounts, self.recvoffsets, nback,
-                               self.sendcounts, self.sendoffsets, itemsize)
+        # reverse Alltoallv: what I received goes back to its origin (domain.py:274-281); the ghosts
+        # this rank holds of its own particles stay where they are (`segments` below)
+        me, P = self.comm.rank, self.comm.size
+        if P == 1:
+            back = ddata
+        else:
+            back = DeviceArray.empty((nback, max(itemsize, 1)), 'u1')
+            back = self._alltoallv(ctx, ddata, self.recvcounts, self.recvoffsets, back,
+                            self.sendcounts, self.sendoffsets, itemsize, skip_self=True)
         full_dtype = numpy.dtype((dtype, tuple(trailing)))
 
         if self.sendlength == 0:
@@ -241,9 +261,14 @@ class Layout(object):
                 dout = DeviceArray.empty((int(self.sendlength),) + tuple(trailing), odt)
             offs = numpy.zeros(self.comm.size + 1, dtype='i8')
             offs[1:] = numpy.cumsum(self.sendcounts)
-            _lib.check(ctx.lib.pmb_gather_sum(ctx.handle, back.ptr, dtype.itemsize, ncomp, self._indices_ptr(),
-                                              offs.ctypes.data, self.comm.size, int(self.sendlength),
-                                              dout.ptr, dout.dtype.itemsize))
+            segs = (ctypes.c_void_p * P)()
+            for q in range(P):
+                segs[q] = back.ptr + int(offs[q]) * itemsize
+            if P > 1:
+                segs[me] = ddata.ptr + int(self.recvoffsets[me]) * itemsize
+            _lib.check(ctx.lib.pmb_gather_sum_segments(ctx.handle, segs, dtype.itemsize, ncomp, self._indices_ptr(),
+                                                       offs.ctypes.data, P, int(self.sendlength),
+                                                       dout.ptr, dout.dtype.itemsize))
             if is_device(out):
                 return out
             if out is None:
@@ -252,6 +277,9 @@ class Layout(object):
             return out
 
         # the remaining modes are host-side bookkeeping on the returned ghosts (never on the force path)
+        if P > 1 and self.sendcounts[me] > 0:
+            ctx.d2d(back.ptr + int(self.sendoffsets[me]) * itemsize, ddata.ptr + int(self.recvoffsets[me]) * itemsize,
+                    int(self.sendcounts[me]) * itemsize)
         recvbuffer = DeviceArray((nback,) + tuple(trailing), dtype, ptr=back.ptr, base=back, ctx=ctx).to_host()
         indices = self.indices
         if mode == 'all':

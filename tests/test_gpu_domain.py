@@ -200,7 +200,7 @@ def test_gather_sum_matches_bincount(D, oracle):
     lay.recvcounts = counts
     lay.recvoffsets = lay.sendoffsets
     lay.recvlength = counts.sum()
-    lay._alltoallv = lambda ctx, send, *a: send            # pretend the reverse alltoallv happened
+    lay._alltoallv = lambda ctx, send, *a, **k: send            # pretend the reverse alltoallv happened
     for dt in ("f8", "f4"):
         for trailing in ((), (3,)):
             vals = rng.uniform(-1, 1, (len(indices),) + trailing).astype(dt)
