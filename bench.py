@@ -154,15 +154,10 @@ class ForceStep(object):
         for d in range(3):
             self._t("transfer", lambda: self.rhok.apply(self.tf[d], out=self.tmp))
             real = self._t("c2r", lambda: self.tmp.c2r(out=Ellipsis))
-            loc = self._t("readout", lambda: real.readout(lpos, out=self._local(lpos.shape[0])))
-            self._t("gather", lambda: layout.gather(loc, out=F[d]))
+            loc = self._t("readout", lambda: real.readout(lpos))
+            F[d] = self._t("gather", lambda: layout.gather(loc))     # nbody.py:214-216
+            del loc
         return F
-
-    def _local(self, n):
-        from pmesh_b200.device import DeviceArray
-        if getattr(self, "_loc", None) is None or self._loc.shape[0] != n:
-            self._loc = DeviceArray.empty((n,), "f8")
-        return self._loc
 
 
 def run_ours(args):

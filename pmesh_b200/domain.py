@@ -252,6 +252,11 @@ class Layout(object):
                 out = numpy.empty(self.sendlength, dtype=full_dtype)
             return out
 
+        if mode == 'sum' and self.identity and P == 1 and out is None and not was_host:
+            # nothing to reduce and nowhere to move: the device column is the result (bincount would
+            # only turn -0.0 into +0.0)
+            return ddata
+
         if mode == 'sum' and dtype in (numpy.dtype('f4'), numpy.dtype('f8')):
             # bincountv(indices, recvbuffer, minlength=sendlength) on the device
             if is_device(out):
