@@ -20,6 +20,8 @@
  *        <- Field.apply with the force-step transfer functions pmesh/pm.py:617-648, examples/nbody.py:154-181
  *   pmb_comm_*
  *        <- mpi4py communicator used by domain.py / pfft       pmesh/domain.py:112-114,199-205
+ *   pmb_whitenoise
+ *        <- _whitenoise.generate (N-GenIC scheme on ranlxd1)    pmesh/_whitenoise.pyx:25-45, pm.py:1656-1696
  *
  * Conventions: plain C types only.  Pointers are DEVICE pointers unless the
  * name ends in _h.  Every function returns 0 on success or a negative
@@ -227,6 +229,16 @@ int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const
  * costs no pass of its own. */
 int pmb_transfer_scaled(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
                         double prefactor, const void *in, void *out);
+
+/* ---- white noise (initial conditions) ----------------------------------------------------------- */
+/* <- pmesh._whitenoise.generate (pmesh/_whitenoise.pyx:25-45) -> pmesh_whitenoise_generator_fill
+ *    (pmesh/_whitenoise_imp.c:68-105, _whitenoise_generics.h:29-232) with gsl_rng_ranlxd1
+ *    (pmesh/gsl/ranlxd.c).  Fills the local block [start, start + size) of the Hermitian
+ *    half-spectrum (k_z <= N/2) of an nmesh[0..3) Fourier mesh; cplx is complex64 (elsize 8) or
+ *    complex128 (elsize 16) with byte strides.  The random streams are bit-identical to the
+ *    reference's; values agree to the last bits of libm's log / sin / cos.  Partition invariant. */
+int pmb_whitenoise(pmb_ctx *ctx, void *cplx, int elsize, const int64_t *nmesh, const int64_t *start,
+                   const int64_t *size, const int64_t *strides, unsigned int seed, int unitary);
 
 #ifdef __cplusplus
 }

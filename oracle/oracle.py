@@ -20,6 +20,8 @@ Layers
 * Layout.exchange / gather  : numpy simulation of the Alltoallv over all ranks
 * r2c / c2r / transfer      : numpy.fft, restating pmesh/pm.py:655-694, 987-1019,
                               1202-1226 and examples/nbody.py:154-181
+* white noise               : ``oracle/whitenoise_oracle.c`` (ranlxd1 in integer arithmetic +
+                              the N-GenIC column scheme), pinned to the compiled reference
 """
 import ctypes
 import os
@@ -48,10 +50,10 @@ MAXDIM = 8
 
 
 def build(force=False):
-    """gcc -O2 -ffp-contract=off pm_oracle.c -> libpm_oracle.so"""
-    src = os.path.join(HERE, "pm_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
+    """gcc -O2 -ffp-contract=off pm_oracle.c whitenoise_oracle.c -> libpm_oracle.so"""
+    srcs = [os.path.join(HERE, "pm_oracle.c"), os.path.join(HERE, "whitenoise_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(x) for x in srcs):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO] + srcs + ["-lm"])
     return _SO
 
 
@@ -381,3 +383,27 @@ def transfer(cplx, nmesh, boxsize, kind, direction=0, r=None):
     if kind == "ik":
         return 1j * k[direction] * cplx
     raise ValueError(kind)
+
+
+# ------------------------------------------------------------------------------------------ white noise
+def whitenoise_stream(seed, n):
+    """the first n uniforms of the ranlxd1 stream seeded with `seed` (pmesh/gsl/ranlxd.c)"""
+    L = lib()
+    out = numpy.empty(n, dtype='f8')
+    L.wn_oracle_stream(ctypes.c_ulong(seed), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n))
+    return out
+
+
+def whitenoise(complex, start, Nmesh, seed, unitary=False):
+    """fill the local block `complex` (complex64 / complex128, any strides) of the Nmesh^3 Fourier mesh
+    starting at `start`; restates pmesh/whitenoise.py:4-24 -> _whitenoise.pyx:25-45 (3-D only)"""
+    assert complex.ndim == 3 and complex.dtype.kind == 'c'
+    L = lib()
+    A = ctypes.c_ssize_t * 3
+    st = numpy.empty(3, dtype='intp'); st[:] = start
+    nm = numpy.empty(3, dtype='intp'); nm[:] = Nmesh
+    rc = L.wn_oracle_fill(ctypes.c_void_p(complex.ctypes.data), ctypes.c_int(complex.dtype.itemsize),
+                            A(*nm), A(*st), A(*complex.shape), A(*complex.strides),
+                            ctypes.c_uint(seed), ctypes.c_int(bool(unitary)))
+    assert rc == 0
+    return complex

@@ -145,14 +145,15 @@ __device__ __forceinline__ uint64_t pmb_route_mask(const RouteGeom &g, const dou
     return mask;
 }
 
-// block b owns particles [b*per_block, (b+1)*per_block).  MaskT: the narrowest unsigned type that
-// holds one bit per rank (1 byte per particle up to 8 ranks instead of 8).
+// WARP w owns the contiguous particles [w*per_unit, (w+1)*per_unit): no block-level synchronisation
+// anywhere.  Lane r (and r + 32) of a warp keeps the count / cursor of rank r in a register.
+// MaskT: the narrowest unsigned type that holds one bit per rank (1 byte per particle up to 8 ranks).
+#define ROUTE_UNROLL 4
 template <int NDIM, typename MaskT>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t npart,
-                  int64_t per_block, MaskT *masks, int32_t *blockhist)
+                  int64_t per_unit, MaskT *masks, int32_t *unithist)
 {
-    __shared__ int hist[ROUTE_MAXRANKS];
     extern __shared__ double s_edges[];
     const double *edges[NDIM];
     {
@@ -164,87 +165,127 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
             o += g.nedges[d];
         }
     }
-    if (threadIdx.x < ROUTE_MAXRANKS) hist[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t begin = blockIdx.x * per_block;
-    const int64_t end = min(begin + per_block, npart);
     const int lane = threadIdx.x & 31;
-    for (int64_t base = begin; base < end; base += ROUTE_BLOCK) {
-        const int64_t i = base + threadIdx.x;
-        uint64_t mask = 0;
-        if (i < end) {
-            mask = pmb_route_mask<NDIM>(g, edges, pos, elsize, ps0, ps1, i);
-            __stcs(masks + i, (MaskT) mask);
+    const int64_t unit = (int64_t) blockIdx.x * (ROUTE_BLOCK / 32) + (threadIdx.x >> 5);
+    const int64_t begin = unit * per_unit;
+    const int64_t end = min(begin + per_unit, npart);
+    int c0 = 0, c1 = 0;
+    for (int64_t base = begin; base < end; base += 32 * ROUTE_UNROLL) {
+        uint64_t mask[ROUTE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const int64_t i = base + u * 32 + lane;
+            mask[u] = i < end ? pmb_route_mask<NDIM>(g, edges, pos, elsize, ps0, ps1, i) : 0;
         }
-        for (int r = 0; r < g.nranks; r++) {
-            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
-            if (lane == 0 && b) atomicAdd(&hist[r], __popc(b));
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const int64_t i = base + u * 32 + lane;
+            if (i < end) __stcs(masks + i, (MaskT) mask[u]);
+            // ranks that any lane of the warp targets (usually one or two)
+            unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned) mask[u]);
+            unsigned hi = g.nranks > 32 ? __reduce_or_sync(0xffffffffu, (unsigned) (mask[u] >> 32)) : 0u;
+            while (lo) {
+                const int r = __ffs(lo) - 1;
+                lo &= lo - 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, (mask[u] >> r) & 1);
+                if (lane == r) c0 += __popc(bal);
+            }
+            while (hi) {
+                const int r = __ffs(hi) - 1;
+                hi &= hi - 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, (mask[u] >> (r + 32)) & 1);
+                if (lane == r) c1 += __popc(bal);
+            }
         }
     }
+    if (lane < g.nranks) unithist[unit * g.nranks + lane] = c0;
+    if (lane + 32 < g.nranks) unithist[unit * g.nranks + lane + 32] = c1;
+}
+
+// block r scans the unit counts of rank r: thread t sums its chunk of units; the exclusive scan of
+// the chunk sums goes to partial[r][t], the total to totals[r]
+__global__ void __launch_bounds__(256)
+pmb_k_route_scan(const int32_t *unithist, int64_t nunits, int nranks, int64_t *totals, int64_t *partial)
+{
+    __shared__ int64_t sums[256];
+    const int r = blockIdx.x, t = threadIdx.x;
+    const int64_t chunk = (nunits + 255) / 256;
+    const int64_t u0 = min((int64_t) t * chunk, nunits), u1 = min(u0 + chunk, nunits);
+    int64_t sum = 0;
+    for (int64_t u = u0; u < u1; u++) sum += unithist[u * nranks + r];
+    sums[t] = sum;
     __syncthreads();
-    if (threadIdx.x < g.nranks) blockhist[(int64_t) blockIdx.x * g.nranks + threadIdx.x] = hist[threadIdx.x];
+    if (t == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < 256; k++) { const int64_t v = sums[k]; sums[k] = run; run += v; }
+        totals[r] = run;
+    }
+    __syncthreads();
+    partial[(int64_t) r * 256 + t] = sums[t];
 }
 
-// one thread per rank: totals and exclusive per-block cursors (rank-major output order)
-__global__ void pmb_k_route_scan(int32_t *blockhist, int nblocks, int nranks, int64_t *totals)
+// counts -> write cursors, rank-major output order (rank ascending, then particle ascending)
+__global__ void __launch_bounds__(256)
+pmb_k_route_cursors(int32_t *unithist, int64_t nunits, int nranks, const int64_t *totals, const int64_t *partial)
 {
-    const int r = threadIdx.x;
-    if (r >= nranks) return;
-    int64_t t = 0;
-    for (int b = 0; b < nblocks; b++) t += blockhist[(int64_t) b * nranks + r];
-    totals[r] = t;
-}
-
-__global__ void pmb_k_route_cursors(int32_t *blockhist, int nblocks, int nranks, const int64_t *totals)
-{
-    const int r = threadIdx.x;
-    if (r >= nranks) return;
+    const int r = blockIdx.x, t = threadIdx.x;
     int64_t base = 0;
     for (int q = 0; q < r; q++) base += totals[q];
-    for (int b = 0; b < nblocks; b++) {
-        int32_t c = blockhist[(int64_t) b * nranks + r];
-        blockhist[(int64_t) b * nranks + r] = (int32_t) base;
+    base += partial[(int64_t) r * 256 + t];
+    const int64_t chunk = (nunits + 255) / 256;
+    const int64_t u0 = min((int64_t) t * chunk, nunits), u1 = min(u0 + chunk, nunits);
+    for (int64_t u = u0; u < u1; u++) {
+        const int32_t c = unithist[u * nranks + r];
+        unithist[u * nranks + r] = (int32_t) base;
         base += c;
     }
 }
 
 template <typename MaskT>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
-pmb_k_route_fill(int nranks, int64_t npart, int64_t per_block, const MaskT *masks,
-                 const int32_t *blockcursor, int32_t *indices)
+pmb_k_route_fill(int nranks, int64_t npart, int64_t per_unit, const MaskT *masks,
+                 const int32_t *unitcursor, int32_t *indices)
 {
-    __shared__ int cursor[ROUTE_MAXRANKS];
-    __shared__ int warpcount[ROUTE_BLOCK / 32][ROUTE_MAXRANKS];
-    if (threadIdx.x < nranks) cursor[threadIdx.x] = blockcursor[(int64_t) blockIdx.x * nranks + threadIdx.x];
-    __syncthreads();
-    const int64_t begin = blockIdx.x * per_block;
-    const int64_t end = min(begin + per_block, npart);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    for (int64_t base = begin; base < end; base += ROUTE_BLOCK) {
-        const int64_t i = base + threadIdx.x;
-        const uint64_t mask = i < end ? (uint64_t) __ldcs(masks + i) : 0;
-        for (int r = 0; r < nranks; r++) {
-            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
-            if (lane == 0) warpcount[warp][r] = __popc(b);
+    const int64_t unit = (int64_t) blockIdx.x * (ROUTE_BLOCK / 32) + (threadIdx.x >> 5);
+    const int64_t begin = unit * per_unit;
+    const int64_t end = min(begin + per_unit, npart);
+    if (begin >= end) return;
+    int c0 = lane < nranks ? unitcursor[unit * nranks + lane] : 0;
+    int c1 = lane + 32 < nranks ? unitcursor[unit * nranks + lane + 32] : 0;
+    for (int64_t base = begin; base < end; base += 32 * ROUTE_UNROLL) {
+        uint64_t mask[ROUTE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const int64_t i = base + u * 32 + lane;
+            mask[u] = i < end ? (uint64_t) __ldcs(masks + i) : 0;
         }
-        __syncthreads();
-        for (int r = 0; r < nranks; r++) {
-            unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1);
-            if ((mask >> r) & 1) {
-                int pos = cursor[r];
-                for (int w = 0; w < warp; w++) pos += warpcount[w][r];
-                pos += __popc(b & lt);
-                indices[pos] = (int32_t) i;
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const int64_t i = base + u * 32 + lane;
+            unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned) mask[u]);
+            unsigned hi = nranks > 32 ? __reduce_or_sync(0xffffffffu, (unsigned) (mask[u] >> 32)) : 0u;
+            while (lo) {
+                const int r = __ffs(lo) - 1;
+                lo &= lo - 1;
+                const bool mine = (mask[u] >> r) & 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                const int cur = __shfl_sync(0xffffffffu, c0, r);
+                if (mine) indices[cur + __popc(bal & lt)] = (int32_t) i;
+                if (lane == r) c0 += __popc(bal);
+            }
+            while (hi) {
+                const int r = __ffs(hi) - 1;
+                hi &= hi - 1;
+                const bool mine = (mask[u] >> (r + 32)) & 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                const int cur = __shfl_sync(0xffffffffu, c1, r);
+                if (mine) indices[cur + __popc(bal & lt)] = (int32_t) i;
+                if (lane == r) c1 += __popc(bal);
             }
         }
-        __syncthreads();
-        if (threadIdx.x < nranks) {
-            int s = 0;
-            for (int w = 0; w < ROUTE_BLOCK / 32; w++) s += warpcount[w][threadIdx.x];
-            cursor[threadIdx.x] += s;
-        }
-        __syncthreads();
     }
 }
 
@@ -339,32 +380,34 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
         return PMB_OK;
     }
 
-    int64_t nblocks = (a->npart + ROUTE_BLOCK - 1) / ROUTE_BLOCK;
+    // units = warps; every unit owns a contiguous, 128-aligned range of particles
+    const int wpb = ROUTE_BLOCK / 32;
+    const int64_t gran = 32 * ROUTE_UNROLL;
+    int64_t nblocks = (a->npart + ROUTE_BLOCK * ROUTE_UNROLL - 1) / (ROUTE_BLOCK * ROUTE_UNROLL);
     const int64_t cap = (int64_t) ctx->sm_count * 8;
     if (nblocks > cap) nblocks = cap;
-    int64_t per_block = (a->npart + nblocks - 1) / nblocks;
-    per_block = (per_block + ROUTE_BLOCK - 1) / ROUTE_BLOCK * ROUTE_BLOCK;
-    nblocks = (a->npart + per_block - 1) / per_block;
+    int64_t nunits = nblocks * wpb;
+    int64_t per_unit = (a->npart + nunits - 1) / nunits;
+    per_unit = (per_unit + gran - 1) / gran * gran;
+    nunits = (a->npart + per_unit - 1) / per_unit;
+    nblocks = (nunits + wpb - 1) / wpb;
+    const int64_t nunits_alloc = nblocks * wpb;          // trailing units of the last block are empty
+    const size_t b_hist = (sizeof(int32_t) * nunits_alloc * a->nranks + 7) & ~(size_t) 7;
     int rc = ensure(&ctx->route_masks, &ctx->route_masks_bytes, sizeof(uint64_t) * a->npart, ctx->stream);
     if (rc == PMB_OK)
         rc = ensure(&ctx->route_blockhist, &ctx->route_blockhist_bytes,
-                    sizeof(int32_t) * nblocks * a->nranks + sizeof(int64_t) * ROUTE_MAXRANKS, ctx->stream);
+                    b_hist + sizeof(int64_t) * ROUTE_MAXRANKS * 257, ctx->stream);
     if (rc != PMB_OK) { cudaFree(tables); return rc; }
     int32_t *hist = (int32_t *) ctx->route_blockhist;
-    int64_t *totals = (int64_t *) ((char *) ctx->route_blockhist + ((sizeof(int32_t) * nblocks * a->nranks + 7) & ~(size_t) 7));
-    // keep totals inside the allocation
-    if ((char *) (totals + ROUTE_MAXRANKS) > (char *) ctx->route_blockhist + ctx->route_blockhist_bytes) {
-        cudaFree(tables);
-        pmb_set_error("internal: routing scratch too small");
-        return PMB_EINVAL;
-    }
+    int64_t *totals = (int64_t *) ((char *) ctx->route_blockhist + b_hist);
+    int64_t *partial = totals + ROUTE_MAXRANKS;
     int tot_edges = 0;
     for (int d = 0; d < a->ndim; d++) tot_edges += a->nedges[d];
     const size_t smem = sizeof(double) * tot_edges;
     ctx->route_maskbytes = a->nranks <= 8 ? 1 : (a->nranks <= 16 ? 2 : 8);
 #define ROUTE_COUNT(ND, MT)                                                                          \
     pmb_k_route_count<ND, MT><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(                     \
-        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_block, (MT *) ctx->route_masks, hist)
+        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_unit, (MT *) ctx->route_masks, hist)
 #define ROUTE_COUNT_ND(MT)                                                                           \
     do {                                                                                             \
         if (a->ndim == 1) ROUTE_COUNT(1, MT); else if (a->ndim == 2) ROUTE_COUNT(2, MT); else ROUTE_COUNT(3, MT); \
@@ -375,9 +418,9 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
 #undef ROUTE_COUNT_ND
 #undef ROUTE_COUNT
     ctx->launches++;
-    pmb_k_route_scan<<<1, ROUTE_MAXRANKS, 0, ctx->stream>>>(hist, (int) nblocks, a->nranks, totals);
+    pmb_k_route_scan<<<a->nranks, 256, 0, ctx->stream>>>(hist, nunits_alloc, a->nranks, totals, partial);
     ctx->launches++;
-    pmb_k_route_cursors<<<1, ROUTE_MAXRANKS, 0, ctx->stream>>>(hist, (int) nblocks, a->nranks, totals);
+    pmb_k_route_cursors<<<a->nranks, 256, 0, ctx->stream>>>(hist, nunits_alloc, a->nranks, totals, partial);
     ctx->launches++;
     int64_t totals_h[ROUTE_MAXRANKS];
     cudaError_t e = cudaGetLastError();
@@ -394,7 +437,7 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
     PMB_REQUIRE(tot < ((int64_t) 1 << 31), "routed particle count overflows int32 offsets (domain.py:590)");
     *ntotal = tot;
     ctx->route_nblocks = (int) nblocks;
-    ctx->route_per_block = per_block;
+    ctx->route_per_block = per_unit;
     return PMB_OK;
 }
 

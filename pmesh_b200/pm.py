@@ -946,7 +946,31 @@ class ParticleMesh(object):
         raise NotImplementedError("ravel/unravel need the distributed sort; outside the force-step path (SURVEY 8f-2)")
 
     def generate_whitenoise(self, seed, unitary=False, mean=0, type=TransposedComplexField, mode=None, base=None):
-        raise NotImplementedError("white noise generation is the next scope row (SURVEY 8f-1)")
+        """ Generate white noise to the field with the given seed (reference pm.py:1656-1696).
+
+            The scheme is compatible with Gadget / N-GenIC for three-dimensional meshes and does not
+            depend on the number of ranks.
+
+            seed : int
+            mean : float, the mean of the field (the k = 0 mode)
+            unitary : True for a unitary white noise (amplitude fixed to 1, only the phase is random)
+            type : the field to return; a RealField is the c2r of the complex noise
+        """
+        from .whitenoise import generate
+        if mode is not None:
+            warnings.warn("mode argument is deprecated, use type", DeprecationWarning, stacklevel=2)
+            type = mode
+        type = _typestr_to_type(type)
+        complex_type = TransposedComplexField if type is RealField else type
+        complex = self.create(type=complex_type, base=base)
+        generate(complex._dev, complex.start, complex.Nmesh, seed, bool(unitary))
+        complex._mark_device_written()
+        if mean != 0:
+            # the generator leaves the k = 0 mode at zero (pm.py:1685-1691 sets it to `mean`)
+            complex.csetitem([0] * self.ndim, mean)
+        if type is RealField:
+            return complex.c2r(out=Ellipsis)
+        return complex
 
     def mesh_coordinates(self, dtype=None):
         coord = numpy.indices(tuple(self._layout['i_shape']), dtype).reshape(self.ndim, -1).T

@@ -214,3 +214,42 @@ extern "C" int hh_readout(const pmb_resample_args *a)
     }
     return -3;
 }
+
+// ---- white noise: the column routines of pmb_whitenoise.cu, walked serially on the host ------------
+#include "../../pmesh_b200/csrc/pmb_wnrng.h"
+
+extern "C" void hh_wn_stream(unsigned int seed, double *out, int n)
+{
+    WnRng g;
+    wn_seed(g, seed);
+    for (int i = 0; i < n; i++) out[i] = wn_uniform(g);
+}
+
+extern "C" int hh_whitenoise(void *canvas, int elsize, const int64_t *nmesh, const int64_t *start, const int64_t *size,
+                             const int64_t *strides, unsigned int seed, int unitary)
+{
+    const int64_t ncol = size[0] * size[1];
+    if (ncol == 0) return 0;
+    std::vector<unsigned int> tab((size_t) ncol * 2, 0u);
+    WnTables T;
+    T.N0 = nmesh[0]; T.N1 = nmesh[1]; T.s0 = start[0]; T.s1 = start[1]; T.m0 = size[0]; T.m1 = size[1];
+    T.t00 = tab.data(); T.t11 = tab.data() + ncol;
+    wn_build_tables(T, seed);
+    WnArgs a;
+    for (int d = 0; d < 3; d++) { a.N[d] = nmesh[d]; a.start[d] = start[d]; a.size[d] = size[d]; a.strides[d] = strides[d]; }
+    a.t00 = T.t00; a.t11 = T.t11; a.unitary = unitary; a.fast_axis = 1;
+    for (int64_t li = 0; li < size[0]; li++)
+        for (int64_t lj = 0; lj < size[1]; lj++) {
+            WnColumn c;
+            wn_column_init(c, a, li, lj);
+            for (int64_t k = 0; k <= nmesh[2] / 2; k++) {
+                double re, im;
+                bool in = elsize == 16 ? wn_column_mode<double>(c, a, k, re, im) : wn_column_mode<float>(c, a, k, re, im);
+                if (!in) continue;
+                char *p = (char *) canvas + li * strides[0] + lj * strides[1] + (k - start[2]) * strides[2];
+                if (elsize == 16) { ((double *) p)[0] = re; ((double *) p)[1] = im; }
+                else { ((float *) p)[0] = (float) re; ((float *) p)[1] = (float) im; }
+            }
+        }
+    return 0;
+}

@@ -89,6 +89,16 @@ def main():
             gd = f.readout(DeviceArray.from_host(allpos[r]), layout=layout)
             assert numpy.array_equal(gd.to_host(), got)
 
+        # 4b. white noise does not depend on the partition: my block of the transposed complex field
+        #     equals the same block of the oracle's whole field
+        cdt = "complex128" if dtype == "f8" else "complex64"
+        wn_full = oracle.whitenoise(numpy.zeros((n, n, n // 2 + 1), dtype=cdt), 0, (n, n, n), 120577 + n, False)
+        wn = pm.generate_whitenoise(120577 + n)
+        s1, m1 = wn.start[1], wn.shape[1]
+        assert wn.shape == (n, m1, n // 2 + 1)
+        if wn.size:
+            assert abs(wn.value - wn_full[:, s1:s1 + m1, :]).max() < (1e-13 if dtype == "f8" else 5e-7)
+
         # 5. gather modes on real ghosts (tests/test_domain.py:229-266 semantics)
         ones = numpy.ones(layout.recvlength)
         nghost = layout.gather(ones, mode="sum")
