@@ -130,6 +130,21 @@ int pmb_field_scale(pmb_ctx *ctx, void *mesh, int elsize, int is_complex, int nd
 int pmb_field_sum(pmb_ctx *ctx, const void *mesh, int elsize, int ndim, const int64_t *size,
                   const int64_t *strides, double *sum_h);
 
+/* ---- particle columns: the element-wise updates of a KDK step -------------------------------------
+ * <- the numpy in-place arithmetic of the reference's integrator, examples/nbody.py:84-102 (symp2:
+ *    V += F * K; S += V * D) and :200 (X = S + Q).  Columns are float32 / float64 (elsize) with byte
+ *    strides; one multiply and one add per element, rounded like numpy (no FMA). */
+/* y += a * x */
+int pmb_axpy(pmb_ctx *ctx, void *y, int64_t y_stride, const void *x, int64_t x_stride, double a, int elsize, int64_t n);
+/* out = a * x + b * y   (y == NULL: out = a * x) */
+int pmb_lincomb(pmb_ctx *ctx, void *out, int64_t out_stride, const void *x, int64_t x_stride, double a,
+                const void *y, int64_t y_stride, double b, int elsize, int64_t n);
+/* fused kick + drift in one pass: V += F * kick; S += V * drift.  V, S are contiguous (npart, ncol)
+ * rows; the force is column-wise, F_cols_h[d] = dense device column (npart,) as readout / gather
+ * produce it (host array of ncol device pointers).  S == NULL: kick only. */
+int pmb_kick_drift(pmb_ctx *ctx, void *V, void *S, const void *const *F_cols_h, int ncol,
+                   double kick, double drift, int elsize, int64_t npart);
+
 /* ---- synthetic particles (bench / tests): counter-based, reproducible ------------- */
 /* uniform in [0, box) per axis: pos[i,d] = box[d] * u(seed, i + first, d) */
 int pmb_particles_uniform(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,

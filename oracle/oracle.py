@@ -407,3 +407,42 @@ def whitenoise(complex, start, Nmesh, seed, unitary=False):
                             ctypes.c_uint(seed), ctypes.c_int(bool(unitary)))
     assert rc == 0
     return complex
+
+
+# ------------------------------------------------------------------------------------------ the driver
+def nbody_force(Q, S, nmesh, boxsize, window, factor=1.0):
+    """examples/nbody.py:196-218 on one rank with numpy: the force at X = S + Q, shape (N, 3)"""
+    n, L = nmesh, boxsize
+    X = S + Q
+    rho = numpy.zeros((n, n, n))
+    paint(rho, X, window, scale=n / L, period=[n] * 3)
+    rho[...] *= 1.0 * n ** 3 / len(X)
+    rhok = r2c(rho)
+    F = numpy.empty_like(Q)
+    for d in range(3):
+        fr = c2r(transfer(rhok, [n] * 3, [L] * 3, "gravity_fd4", d), [n] * 3)
+        F[..., d] = readout(fr, X, window, scale=n / L, period=[n] * 3)
+    return factor * F
+
+
+def nbody_symp2(Q, S, V, nmesh, boxsize, window, time_steps, K, D, Om0):
+    """examples/nbody.py:84-102 (symp2) with numpy in-place arithmetic; returns (S, V)"""
+    S, V = S.copy(), V.copy()
+    F = nbody_force(Q, S, nmesh, boxsize, window, 1.5 * Om0)
+    for ai, af in zip(time_steps[:-1], time_steps[1:]):
+        ac = (ai * af) ** 0.5
+        V[...] += F * K(ai, ac, ai)
+        S[...] += V * D(ai, af, ac)
+        F[...] = nbody_force(Q, S, nmesh, boxsize, window, 1.5 * Om0)
+        V[...] += F * K(ac, af, af)
+    return S, V
+
+
+def nbody_lpt1(dlinear, Q, nmesh, boxsize, window):
+    """examples/nbody.py:262-270: DX1[:, d] = readout(c2r(i k_d / k^2 dlinear), Q)"""
+    n, L = nmesh, boxsize
+    DX1 = numpy.zeros_like(Q)
+    for d in range(3):
+        fr = c2r(transfer(dlinear, [n] * 3, [L] * 3, "gradient_k", d), [n] * 3)
+        DX1[..., d] = readout(fr, Q, window, scale=n / L, period=[n] * 3)
+    return DX1

@@ -582,3 +582,96 @@ extern "C" int pmb_particles_lattice(pmb_ctx *ctx, void *pos, int pos_elsize, in
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }
+
+// ---- particle columns: the element-wise updates of a KDK (leap-frog) step ---------------------------
+// The reference's integrator (examples/nbody.py:84-102, `symp2`) is numpy in place: V += F * K;
+// S += V * D; X = S + Q.  Same arithmetic, same rounding order (one multiply, one add per element, no
+// FMA: the library is built -fmad=false), on device-resident columns of any byte stride.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pmb_k_lincomb(char *out, int64_t so, const char *x, int64_t sx, const char *y, int64_t sy, double a, double b, int mode, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const T ta = (T) a, tb = (T) b;
+    for (; i < n; i += stride) {
+        const T xv = *(const T *) (x + i * sx);
+        T r;
+        if (mode == 0) r = *(T *) (out + i * so) + xv * ta;                       // out += a x
+        else if (mode == 1) r = xv * ta + *(const T *) (y + i * sy) * tb;         // out = a x + b y
+        else r = xv * ta;                                                         // out = a x
+        *(T *) (out + i * so) = r;
+    }
+}
+
+// V += F * kick; S += V * drift in one pass.  V, S: (npart, NCOL) rows (like positions); the force is
+// held column-wise, F[d] dense (npart,), the way readout / gather produce it.  S may be NULL (kick only).
+struct KdCols { const void *f[3]; };
+template <typename T, int NCOL>
+__global__ void __launch_bounds__(256)
+pmb_k_kick_drift(T *__restrict__ V, T *__restrict__ S, KdCols F, double kick, double drift, int64_t npart)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t n = npart * NCOL;
+    const T tk = (T) kick, td = (T) drift;
+    for (; i < n; i += stride) {
+        const int64_t p = i / NCOL;
+        const int d = (int) (i - p * NCOL);
+        const T f = __ldcs((const T *) F.f[d] + p);
+        const T v = V[i] + f * tk;
+        V[i] = v;
+        if (S) S[i] = S[i] + v * td;
+    }
+}
+
+static int lincomb(pmb_ctx *ctx, void *out, int64_t so, const void *x, int64_t sx, const void *y, int64_t sy,
+                   double a, double b, int mode, int elsize, int64_t n)
+{
+    PMB_REQUIRE(ctx && n >= 0, "bad arguments");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "columns must be float32 or float64");
+    if (n == 0) return PMB_OK;
+    PMB_REQUIRE(out && x && (mode != 1 || y), "null column");
+    const int grid = pmb_grid(ctx, n, 256, 8);
+    if (elsize == 8) pmb_k_lincomb<double><<<grid, 256, 0, ctx->stream>>>((char *) out, so, (const char *) x, sx, (const char *) y, sy, a, b, mode, n);
+    else pmb_k_lincomb<float><<<grid, 256, 0, ctx->stream>>>((char *) out, so, (const char *) x, sx, (const char *) y, sy, a, b, mode, n);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+extern "C" int pmb_axpy(pmb_ctx *ctx, void *y, int64_t y_stride, const void *x, int64_t x_stride, double a, int elsize, int64_t n)
+{
+    return lincomb(ctx, y, y_stride, x, x_stride, NULL, 0, a, 0.0, 0, elsize, n);
+}
+
+extern "C" int pmb_lincomb(pmb_ctx *ctx, void *out, int64_t out_stride, const void *x, int64_t x_stride, double a,
+                           const void *y, int64_t y_stride, double b, int elsize, int64_t n)
+{
+    return lincomb(ctx, out, out_stride, x, x_stride, y, y_stride, a, b, y ? 1 : 2, elsize, n);
+}
+
+template <typename T>
+static void kick_drift_launch(pmb_ctx *ctx, void *V, void *S, const KdCols &F, int ncol, double kick, double drift, int64_t npart)
+{
+    const int grid = pmb_grid(ctx, npart * ncol, 256, 8);
+    if (ncol == 1) pmb_k_kick_drift<T, 1><<<grid, 256, 0, ctx->stream>>>((T *) V, (T *) S, F, kick, drift, npart);
+    else if (ncol == 2) pmb_k_kick_drift<T, 2><<<grid, 256, 0, ctx->stream>>>((T *) V, (T *) S, F, kick, drift, npart);
+    else pmb_k_kick_drift<T, 3><<<grid, 256, 0, ctx->stream>>>((T *) V, (T *) S, F, kick, drift, npart);
+}
+
+extern "C" int pmb_kick_drift(pmb_ctx *ctx, void *V, void *S, const void *const *F_cols_h, int ncol,
+                              double kick, double drift, int elsize, int64_t npart)
+{
+    PMB_REQUIRE(ctx && npart >= 0, "bad arguments");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "columns must be float32 or float64");
+    PMB_REQUIRE(ncol >= 1 && ncol <= 3, "1..3 columns");
+    if (npart == 0) return PMB_OK;
+    PMB_REQUIRE(V && F_cols_h, "null column");
+    KdCols F;
+    for (int d = 0; d < 3; d++) F.f[d] = d < ncol ? F_cols_h[d] : NULL;
+    for (int d = 0; d < ncol; d++) PMB_REQUIRE(F.f[d], "null force column %d", d);
+    if (elsize == 8) kick_drift_launch<double>(ctx, V, S, F, ncol, kick, drift, npart);
+    else kick_drift_launch<float>(ctx, V, S, F, ncol, kick, drift, npart);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}

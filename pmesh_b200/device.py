@@ -124,6 +124,36 @@ class DeviceArray(object):
         self.ctx.memset(self.ptr, 0, self.nbytes)
         return self
 
+    # ---- element-wise column arithmetic (pmb_axpy / pmb_lincomb) --------------------------------
+    def _flat(self):
+        """(ptr, byte stride, n) of the array seen as a 1-D strided column"""
+        if self.is_contiguous:
+            return self.ptr, self.dtype.itemsize, self.size
+        if self.ndim == 1:
+            return self.ptr, self.strides[0], self.shape[0]
+        raise ValueError("element-wise device arithmetic needs a contiguous array or a 1-D strided column")
+
+    def iadd_scaled(self, x, a=1.0):
+        """self += a * x   (numpy: ``self[...] += x * a``)"""
+        assert x.shape == self.shape and x.dtype == self.dtype and self.dtype.kind == 'f'
+        py, sy, n = self._flat()
+        px, sx, _ = x._flat()
+        _lib.check(self.ctx.lib.pmb_axpy(self.ctx.handle, py, sy, px, sx, float(a), self.dtype.itemsize, n))
+        return self
+
+    def assign_lincomb(self, x, a=1.0, y=None, b=1.0):
+        """self = a * x + b * y   (y None: self = a * x)"""
+        assert x.shape == self.shape and x.dtype == self.dtype and self.dtype.kind == 'f'
+        po, so, n = self._flat()
+        px, sx, _ = x._flat()
+        py, sy = (None, 0)
+        if y is not None:
+            assert y.shape == self.shape and y.dtype == self.dtype
+            py, sy, _ = y._flat()
+        _lib.check(self.ctx.lib.pmb_lincomb(self.ctx.handle, po, so, px, sx, float(a), py, sy, float(b),
+                                            self.dtype.itemsize, n))
+        return self
+
     def column(self, d):
         """view of column d of an (N, k) array"""
         assert self.ndim == 2
