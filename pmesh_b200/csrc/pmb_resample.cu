@@ -453,6 +453,43 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
             PMB_LAUNCH_CHECK(ctx);
             return PMB_OK;
         }
+        if (fam >= 2 && unit > 0 && pmb_env_flag("PMB_CARRY_FAM", 1)) {
+            // TSC / PCS and every gradient window: the same y-carry with FAM - 1 carried rows
+            // (pmb_k_paint_carry32), when the canvas can be addressed with 32-bit element indices
+            bool idx32 = true;
+            int64_t span = 0;
+            for (int d = 0; d < 3; d++) {
+                if (a->strides[d] < 0 || a->strides[d] % (int64_t) sizeof(MeshT)) idx32 = false;
+                span += (a->size[d] - 1) * (a->strides[d] / (int64_t) sizeof(MeshT));
+            }
+            if (span >= ((int64_t) 1 << 31) - 1) idx32 = false;
+            if (idx32) {
+                PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks, 1));
+                const int64_t nunits = (nchunks + unit - 1) / unit;
+                const int64_t capu = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
+                const int gridu = (int) (nunits < capu ? nunits : capu);
+                PmbGeom32o go;
+                for (int d = 0; d < 3; d++) {
+                    go.g.scale[d] = g.scale[d]; go.g.translate[d] = g.translate[d];
+                    go.g.period[d] = (int) g.period[d]; go.g.size[d] = (int) g.size[d];
+                    go.g.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
+                    go.order[d] = a->order[d];
+                }
+                go.pcsfix = a->pcs_gradient_scale_fix;
+                const bool pos8 = pmb_pos_is_f8_rows(p);
+#define PMB_CARRY_PAINT(FAMV)                                                                                  \
+                do {                                                                                           \
+                    if (pos8) { PMB_DISPATCH_CHECK(chk, (pmb_k_paint_carry32<MeshT, FAMV, CHECK, true><<<gridu, PMB_CHUNK, 0, ctx->stream>>>( \
+                                    go, p, (MeshT *) mesh, a->npart, order, nchunks, unit))); }                \
+                    else { PMB_DISPATCH_CHECK(chk, (pmb_k_paint_carry32<MeshT, FAMV, CHECK, false><<<gridu, PMB_CHUNK, 0, ctx->stream>>>( \
+                                    go, p, (MeshT *) mesh, a->npart, order, nchunks, unit))); }                \
+                } while (0)
+                if (fam == 2) PMB_CARRY_PAINT(2); else if (fam == 3) PMB_CARRY_PAINT(3); else PMB_CARRY_PAINT(4);
+#undef PMB_CARRY_PAINT
+                PMB_LAUNCH_CHECK(ctx);
+                return PMB_OK;
+            }
+        }
         PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks));
         unsigned long long *ticket;
         PMB_CHECK(pmb_sched_ticket(ctx, &ticket));

@@ -485,6 +485,180 @@ pmb_k_paint_cic_carry32(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart,
     }
 }
 
+// ---- y-carry paint for every tuned window (FAM = 2, 3, 4) and gradient windows -----------------------
+// The CIC trick above, generalised: a FAM-wide stencil shares FAM - 1 of its y rows with the stencil of
+// the next particle along y, so the partial sums of rows b = 1 .. FAM-1 (FAM x FAM values each) are
+// carried in registers to the next chunk and only row b = 0 -- complete at that point -- is written,
+// after the warp has merged the overlapping z cells of neighbouring lanes.  Global reds per particle
+// drop from FAM^2 rows to FAM rows (TSC: 9 -> 3, PCS: 16 -> 4), and the wide windows are bound by
+// exactly that number (profiles/README.md: ~0.4 T fp64 reds/s whatever the window).  A carry that
+// does not match the next particle (row ends, large displacements, end of a run) is flushed with
+// plain reds: any particle order gives the right answer, lattice-like order gives the speed.
+template <int FAM, bool CHECK>
+__device__ __forceinline__ void pmb_axis32(double xin, int order, double scale, double translate, int pcsfix,
+                                           int per, int sz, int es, double *V, int *e)
+{
+    const double X = pmb_gridpos(xin, scale, translate);
+    int I[FAM];
+    pmb_axis_tuned<FAM>(X, order, scale, pcsfix, I, V);
+    int t = I[0];
+    if (per > 0) t = pmb_wrap32(t, per);
+#pragma unroll
+    for (int s = 0; s < FAM; s++) {
+        e[s] = (!CHECK || (unsigned) t < (unsigned) sz) ? t * es : -1;
+        t += 1;
+        if (per > 0 && t == per) t = 0;
+    }
+}
+
+struct PmbGeom32o {
+    PmbGeom32 g;
+    int order[3];
+    int pcsfix;
+};
+
+template <typename MeshT, int FAM, bool CHECK, bool POS8>
+__global__ void __launch_bounds__(PMB_CHUNK, (FAM == 2 ? 4 : (FAM == 3 ? 2 : 1)))
+pmb_k_paint_carry32(PmbGeom32o go, PmbParticles p, MeshT *mesh, int64_t npart,
+                    const uint32_t *__restrict__ order, int64_t nchunks, int unit)
+{
+    const PmbGeom32 &g = go.g;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    const int lane = threadIdx.x & 31;
+    const int64_t nunits = (nchunks + unit - 1) / unit;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        // carry: partial sums of the y rows b = 1 .. FAM-1 of the previous particle of this thread,
+        // stored at row index b - 1, and where they go (per-axis element indices; cey < 0: no carry)
+        double cv[FAM - 1][FAM][FAM];
+        int cex[FAM], cez[FAM], cey[FAM - 1];
+#pragma unroll
+        for (int b = 0; b < FAM - 1; b++) {
+            cey[b] = -2;
+#pragma unroll
+            for (int a = 0; a < FAM; a++)
+#pragma unroll
+                for (int c = 0; c < FAM; c++) cv[b][a][c] = 0;
+        }
+#pragma unroll
+        for (int a = 0; a < FAM; a++) { cex[a] = -2; cez[a] = -2; }
+        bool have = false;
+        const int64_t cend = min((u + 1) * (int64_t) unit, nchunks);
+        int64_t chunk = order ? (int64_t) order[u * unit] : u * unit;
+        double xn0 = 0, xn1 = 0, xn2 = 0, mn = 0;
+        {
+            const int64_t i0 = chunk * PMB_CHUNK + threadIdx.x;
+            if (i0 < npart) {
+                pmb_load_pos3<POS8>(p, i0, xn0, xn1, xn2);
+                mn = pmb_load_mass(p, i0);
+            }
+        }
+        for (int64_t cb = u * unit; cb < cend; cb++) {
+            const bool active = chunk * PMB_CHUNK + threadIdx.x < npart;
+            const double x0 = xn0, x1 = xn1, x2 = xn2, m = mn;
+            if (cb + 1 < cend) {
+                chunk = order ? (int64_t) order[cb + 1] : cb + 1;
+                const int64_t in = chunk * PMB_CHUNK + threadIdx.x;
+                if (in < npart) {
+                    pmb_load_pos3<POS8>(p, in, xn0, xn1, xn2);
+                    mn = pmb_load_mass(p, in);
+                }
+            }
+            double Vx[FAM], Vy[FAM], Vz[FAM];
+            int ex[FAM], ey[FAM], ez[FAM];
+            pmb_axis32<FAM, CHECK>(x0, go.order[0], g.scale[0], g.translate[0], go.pcsfix, g.period[0], g.size[0], g.estride[0], Vx, ex);
+            pmb_axis32<FAM, CHECK>(x1, go.order[1], g.scale[1], g.translate[1], go.pcsfix, g.period[1], g.size[1], g.estride[1], Vy, ey);
+            pmb_axis32<FAM, CHECK>(x2, go.order[2], g.scale[2], g.translate[2], go.pcsfix, g.period[2], g.size[2], g.estride[2], Vz, ez);
+            // does the carry continue into this particle?  same x and z cells, y shifted by one
+            bool same = have && active;
+#pragma unroll
+            for (int a = 0; a < FAM; a++) same = same && cex[a] == ex[a] && cez[a] == ez[a];
+#pragma unroll
+            for (int b = 0; b < FAM - 1; b++) same = same && cey[b] == ey[b];
+            if (have && !same) {
+#pragma unroll
+                for (int b = 0; b < FAM - 1; b++)
+#pragma unroll
+                    for (int a = 0; a < FAM; a++)
+#pragma unroll
+                        for (int c = 0; c < FAM; c++)
+                            if (!CHECK || (cex[a] >= 0 && cey[b] >= 0 && cez[c] >= 0))
+                                pmb_red<MeshT>((char *) mesh, (int64_t) (cex[a] + cey[b] + cez[c]) * sizeof(MeshT), cv[b][a][c], policy);
+            }
+            // row b = 0 of this particle (+ the carried partial sums): complete, goes out below
+            double r0[FAM][FAM];
+            double wx[FAM];
+#pragma unroll
+            for (int a = 0; a < FAM; a++) wx[a] = Vx[a] * m;          // ((V0 * m) * V1) * V2, the tuned routines' order
+#pragma unroll
+            for (int a = 0; a < FAM; a++)
+#pragma unroll
+                for (int c = 0; c < FAM; c++) {
+                    const double v = (wx[a] * Vy[0]) * Vz[c];
+                    r0[a][c] = same ? v + cv[0][a][c] : v;
+                }
+            // rows b = 1 .. FAM-1 become the new carry (ascending b: slot b - 1 was consumed already)
+#pragma unroll
+            for (int b = 1; b < FAM; b++)
+#pragma unroll
+                for (int a = 0; a < FAM; a++)
+#pragma unroll
+                    for (int c = 0; c < FAM; c++) {
+                        const double v = (wx[a] * Vy[b]) * Vz[c];
+                        cv[b - 1][a][c] = (same && b < FAM - 1) ? v + cv[b][a][c] : v;
+                    }
+            have = active;
+#pragma unroll
+            for (int a = 0; a < FAM; a++) { cex[a] = ex[a]; cez[a] = ez[a]; }
+#pragma unroll
+            for (int b = 0; b < FAM - 1; b++) cey[b] = ey[b + 1];
+            // row 0: merge along z inside the warp.  accept[c]: the lane c below me holds, as its z point
+            // c, the cell that is my z point 0 (same x / y cells); taken[c]: my z point c is delivered
+            // by the lane c above me.
+            const bool row_ok = active && (!CHECK || ey[0] >= 0);
+            int base[FAM];
+#pragma unroll
+            for (int c = 0; c < FAM; c++)
+                base[c] = (row_ok && (!CHECK || (ex[0] >= 0 && ez[c] >= 0))) ? ex[0] + ey[0] + ez[c] : -1;
+            bool accept[FAM], taken[FAM];
+            accept[0] = taken[0] = false;
+#pragma unroll
+            for (int c = 1; c < FAM; c++) {
+                const int theirs = __shfl_up_sync(0xffffffffu, base[c], c);
+                accept[c] = lane >= c && base[0] >= 0 && theirs == base[0];
+                taken[c] = __shfl_down_sync(0xffffffffu, (int) accept[c], c) != 0 && lane + c < 32;
+            }
+#pragma unroll
+            for (int a = 0; a < FAM; a++) {
+                double acc = r0[a][0];
+#pragma unroll
+                for (int c = 1; c < FAM; c++) {
+                    const double r = __shfl_up_sync(0xffffffffu, r0[a][c], c);
+                    if (accept[c]) acc += r;
+                }
+                if (row_ok && (!CHECK || ex[a] >= 0)) {
+                    if (!CHECK || ez[0] >= 0)
+                        pmb_red<MeshT>((char *) mesh, (int64_t) (ex[a] + ey[0] + ez[0]) * sizeof(MeshT), acc, policy);
+#pragma unroll
+                    for (int c = 1; c < FAM; c++)
+                        if (!taken[c] && (!CHECK || ez[c] >= 0))
+                            pmb_red<MeshT>((char *) mesh, (int64_t) (ex[a] + ey[0] + ez[c]) * sizeof(MeshT), r0[a][c], policy);
+                }
+            }
+        }
+        if (have) {
+#pragma unroll
+            for (int b = 0; b < FAM - 1; b++)
+#pragma unroll
+                for (int a = 0; a < FAM; a++)
+#pragma unroll
+                    for (int c = 0; c < FAM; c++)
+                        if (!CHECK || (cex[a] >= 0 && cey[b] >= 0 && cez[c] >= 0))
+                            pmb_red<MeshT>((char *) mesh, (int64_t) (cex[a] + cey[b] + cez[c]) * sizeof(MeshT), cv[b][a][c], policy);
+        }
+    }
+}
+
 // ---- readout -----------------------------------------------------------------------------------
 template <typename MeshT, bool VOL>
 __device__ __forceinline__ double pmb_mesh_load(const char *mesh, int64_t off, uint64_t policy)

@@ -105,6 +105,16 @@ def main():
         assert nghost.min() >= 1 and abs(nghost.sum() - lays[r][0].sum()) < 1e-9
         assert numpy.array_equal(layout.gather(lpos, mode="any"), allpos[r])
         assert numpy.allclose(layout.gather(lpos, mode="mean"), allpos[r])
+        # 6. the driver's force (pmesh_b200.nbody.force <- examples/nbody.py:196-218) on my particles ==
+        #    the serial numpy driver on everybody's particles
+        if dtype == "f8":
+            from pmesh_b200 import nbody
+            Fmine = nbody.force(pm, allpos[r], factor=0.45)
+            Fall = oracle.nbody_force(numpy.concatenate(allpos), 0.0, n, L, res, 0.45)
+            off = sum(len(allpos[q]) for q in range(r))
+            got = numpy.stack([f.to_host() for f in Fmine], axis=1)
+            assert rel(got, Fall[off:off + len(allpos[r])]) < 1e-6
+
         comm.Barrier()
         if r == 0:
             print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
