@@ -681,6 +681,17 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
                 }
+                if (pmb_env_flag("PMB_READOUT_PIPE", 0)) {
+                    if (pmb_pos_is_f8_rows(p)) {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_pipe<MeshT, CHECK, true><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                    } else {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_pipe<MeshT, CHECK, false><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                    }
+                    PMB_LAUNCH_CHECK(ctx);
+                    return PMB_OK;
+                }
                 if (pmb_pos_is_f8_rows(p)) {
                     PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, true><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
                         g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));

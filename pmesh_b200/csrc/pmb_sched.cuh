@@ -787,3 +787,91 @@ pmb_k_readout_cic32(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh,
         x0 = xn0; x1 = xn1; x2 = xn2;
     }
 }
+
+// ---- CIC gather, three chunks in flight ------------------------------------------------------------
+// ncu on pmb_k_readout_cic32: DRAM traffic = algorithmic bytes, 58 % of peak, top stall long
+// scoreboard (11.5 of 19.7 cycles per instruction): a chunk issues its 8 mesh gathers and then sits
+// on them.  Here a CTA keeps three chunks in different stages: the positions of chunk k+2 are being
+// loaded, the mesh values of chunk k+1 are being gathered (addresses from positions that arrived
+// one iteration ago), and chunk k -- whose values arrived during the previous iteration -- is
+// weighted, summed (reference point order: bit-identical results) and stored.
+template <typename MeshT, bool CHECK, bool POS8>
+__global__ void __launch_bounds__(PMB_CHUNK, 3)
+pmb_k_readout_cic32_pipe(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh, int64_t npart,
+                         void *out, int out_elsize, int64_t out_stride,
+                         const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    __shared__ long long s_chunk[4];
+    if (threadIdx.x == 0) {
+        s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
+        s_chunk[1] = pmb_next_chunk(ticket, order, nchunks);
+        s_chunk[2] = pmb_next_chunk(ticket, order, nchunks);
+    }
+    __syncthreads();
+    int64_t c0 = s_chunk[0], c1 = s_chunk[1], c2 = s_chunk[2];
+    // stage state of chunk c0: weights + gathered values; of chunk c1: positions
+    double V0[3][2];           // [axis][point] weights of the chunk being consumed
+    double mv[8];
+    bool ok0[8];
+    double x1[3] = {0, 0, 0};  // positions of the chunk whose gathers are issued next
+
+    auto gather = [&](double xa, double xb, double xc, double (&V)[3][2], double (&m)[8], bool (&ok)[8]) {
+        int ex[2], ey[2], ez[2];
+        pmb_cic_axis32<CHECK>(xa, g.scale[0], g.translate[0], g.period[0], g.size[0], g.estride[0], V[0][0], V[0][1], ex[0], ex[1]);
+        pmb_cic_axis32<CHECK>(xb, g.scale[1], g.translate[1], g.period[1], g.size[1], g.estride[1], V[1][0], V[1][1], ey[0], ey[1]);
+        pmb_cic_axis32<CHECK>(xc, g.scale[2], g.translate[2], g.period[2], g.size[2], g.estride[2], V[2][0], V[2][1], ez[0], ez[1]);
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int q = a * 4 + b * 2 + c;
+                    ok[q] = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0);
+                    m[q] = ok[q] ? pmb_mesh_load<MeshT, false>((const char *) mesh, (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), policy) : 0.0;
+                }
+    };
+
+    // prologue: chunk c0 gathered, positions of c1 in flight
+    {
+        double a0 = 0, a1 = 0, a2 = 0;
+        if (c0 >= 0 && c0 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c0 * PMB_CHUNK + threadIdx.x, a0, a1, a2);
+        if (c1 >= 0 && c1 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c1 * PMB_CHUNK + threadIdx.x, x1[0], x1[1], x1[2]);
+        gather(a0, a1, a2, V0, mv, ok0);
+    }
+    for (int it = 0; c0 >= 0; it++) {
+        unsigned long long tk = 0;
+        if (threadIdx.x == 0) tk = atomicAdd(ticket, 1ull);
+        // positions of c2
+        double x2[3] = {0, 0, 0};
+        if (c2 >= 0 && c2 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c2 * PMB_CHUNK + threadIdx.x, x2[0], x2[1], x2[2]);
+        // gathers of c1 (its positions arrived during the previous iteration)
+        double V1[3][2], mn[8];
+        bool ok1[8];
+        if (c1 >= 0) gather(x1[0], x1[1], x1[2], V1, mn, ok1);
+        // consume c0
+        const int64_t i = c0 * PMB_CHUNK + threadIdx.x;
+        if (i < npart) {
+            double value = 0;
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int q = a * 4 + b * 2 + c;
+                        if (!CHECK || ok0[q]) value += mv[q] * ((V0[0][a] * V0[1][b]) * V0[2][c]);
+                    }
+            pmb_st_real_stream(out, i * out_stride, out_elsize, value);
+        }
+        if (threadIdx.x == 0) s_chunk[(it + 3) & 3] = pmb_resolve_chunk(tk, order, nchunks);
+        __syncthreads();
+        c0 = c1; c1 = c2; c2 = s_chunk[(it + 3) & 3];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { mv[q] = mn[q]; ok0[q] = ok1[q]; }
+#pragma unroll
+        for (int d = 0; d < 3; d++) { V0[d][0] = V1[d][0]; V0[d][1] = V1[d][1]; x1[d] = x2[d]; }
+    }
+}

@@ -329,3 +329,19 @@ def test_scheduled_kernels_large_inputs(W, oracle, name, order):
             field = rng.uniform(-1, 1, shape).astype(dtype)
             r = W.windows[name].readout(DeviceArray.from_host(field), dpos, transform=tr)
             assert_array_equal(r.to_host(), oracle.readout(field, pos, name, translate=translate, period=[N] * 3))
+            # gradient windows (paint_jvp / the paint of a vjp) take the same scheduled / carry kernels
+            for diffdir in ((1,) if dtype == "f4" else (0, 2)):
+                want = numpy.zeros(shape, dtype)
+                oracle.paint(want, pos, name, mass=mass, diffdir=diffdir, translate=translate, period=[N] * 3)
+                mesh = DeviceArray.zeros(shape, dtype)
+                W.windows[name].paint(mesh, dpos, mass=dmass, diffdir=diffdir, transform=tr, mode="atomic")
+                assert_allclose(mesh.to_host(), want, rtol=tol, atol=tol * max(abs(want).max(), 1e-30))
+    # anisotropic scale, non-periodic canvas (points outside are dropped), float32 positions
+    tr = W.Affine(3, scale=[0.9, 1.1, 0.5], translate=[1.0, -2.0, 3.5], period=0)
+    shape = (60, 70, 40)
+    p4 = pos.astype("f4")
+    want = numpy.zeros(shape, "f8")
+    oracle.paint(want, p4, name, mass=mass, scale=[0.9, 1.1, 0.5], translate=[1.0, -2.0, 3.5], period=[0] * 3)
+    mesh = DeviceArray.zeros(shape, "f8")
+    W.windows[name].paint(mesh, DeviceArray.from_host(p4), mass=dmass, transform=tr, mode="atomic")
+    assert_allclose(mesh.to_host(), want, rtol=1e-6, atol=1e-6 * abs(want).max())
