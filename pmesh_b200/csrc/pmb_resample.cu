@@ -433,7 +433,16 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
                 }
-                if (pmb_pos_is_f8_rows(p)) {
+                const int pminb = pmb_env_flag("PMB_PAINT_MINB", 4);
+                if (pminb >= 5 && pmb_pos_is_f8_rows(p)) {
+                    if (pminb == 5) {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, true, 5><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (MeshT *) mesh, a->npart, order, nchunks, unit)));
+                    } else {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, true, 6><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (MeshT *) mesh, a->npart, order, nchunks, unit)));
+                    }
+                } else if (pmb_pos_is_f8_rows(p)) {
                     PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, true><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
                         g32, p, (MeshT *) mesh, a->npart, order, nchunks, unit)));
                 } else {
@@ -687,6 +696,25 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                             g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
                     } else {
                         PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_pipe<MeshT, CHECK, false><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                    }
+                    PMB_LAUNCH_CHECK(ctx);
+                    return PMB_OK;
+                }
+                // resident CTAs per SM: measured at 1024^3 (ms): 5 -> 11.44, 6 -> 10.73 (the gather is
+                // latency-bound: more warps in flight beat more loads per warp, cf. the _pipe variant)
+                const int minb = pmb_env_flag("PMB_READOUT_MINB", 6);
+                if (minb >= 6 && pmb_pos_is_f8_rows(p)) {
+                    const int64_t capb = (int64_t) ctx->sm_count * minb;
+                    const int gridb = (int) (nchunks < capb ? nchunks : capb);
+                    if (minb == 6) {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, true, 6><<<gridb, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                    } else if (minb == 7) {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, true, 7><<<gridb, PMB_CHUNK, 0, ctx->stream>>>(
+                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
+                    } else {
+                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32<MeshT, CHECK, true, 8><<<gridb, PMB_CHUNK, 0, ctx->stream>>>(
                             g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
                     }
                     PMB_LAUNCH_CHECK(ctx);

@@ -402,8 +402,8 @@ __device__ __forceinline__ void pmb_cic_axis32(double xin, double scale, double 
     e1 = (!CHECK || (unsigned) t1 < (unsigned) sz) ? t1 * es : -1;
 }
 
-template <typename MeshT, bool CHECK, bool POS8>
-__global__ void __launch_bounds__(PMB_CHUNK, 4)
+template <typename MeshT, bool CHECK, bool POS8, int MINB = 4>
+__global__ void __launch_bounds__(PMB_CHUNK, MINB)
 pmb_k_paint_cic_carry32(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart,
                         const uint32_t *__restrict__ order, int64_t nchunks, int unit)
 {
@@ -726,8 +726,8 @@ pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, 
 // Same pipeline as pmb_k_readout_sched (dynamic tickets, positions of the next chunk prefetched) with
 // the lean index arithmetic of pmb_k_paint_cic_carry32.  Sums in the reference's point order:
 // bit-identical results.
-template <typename MeshT, bool CHECK, bool POS8>
-__global__ void __launch_bounds__(PMB_CHUNK, 5)
+template <typename MeshT, bool CHECK, bool POS8, int MINB = 5>
+__global__ void __launch_bounds__(PMB_CHUNK, MINB)
 pmb_k_readout_cic32(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh, int64_t npart,
                     void *out, int out_elsize, int64_t out_stride,
                     const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
