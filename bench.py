@@ -160,6 +160,17 @@ class ForceStep(object):
         return F
 
 
+def _strided_sum(ctx, a):
+    """float64 sum of a (strided, up to 3-D) device view (pmb_field_sum)"""
+    import ctypes
+    from pmesh_b200 import _lib
+    out = ctypes.c_double(0.0)
+    sz = (ctypes.c_int64 * 3)(*a.shape)
+    st = (ctypes.c_int64 * 3)(*a.strides)
+    _lib.check(ctx.lib.pmb_field_sum(ctx.handle, a.ptr, a.dtype.itemsize, len(a.shape), sz, st, ctypes.byref(out)))
+    return out.value
+
+
 def run_ours(args):
     from pmesh_b200 import _lib, comm as C
     from pmesh_b200.device import DeviceArray, PinnedArray
@@ -229,7 +240,7 @@ def run_ours(args):
     if args.window == "cic" and big:
         kname = {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32"}[dom[0]]
     elif args.window in ("nnb", "cic", "tsc", "pcs"):
-        kname = {"paint": "pmb_k_paint_sched" if big else "pmb_k_paint_tuned",
+        kname = {"paint": ("pmb_k_paint_carry32" if args.window in ("tsc", "pcs") else "pmb_k_paint_sched") if big else "pmb_k_paint_tuned",
                  "readout": "pmb_k_readout_sched" if big else "pmb_k_readout_tuned"}[dom[0]]
     else:
         kname = "pmb_k_%s_dyn" % dom[0]
@@ -246,6 +257,19 @@ def run_ours(args):
                 "paint_ms": round(t_paint, 4), "readout_ms": round(t_read, 4),
                 "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),
                 "readout_frac": round(ab_read / (t_read * 1e-3) / 1e9 / peak, 4)}
+    # ---- size-independent properties at the full benchmark size (outside every timed region) ----
+    # mass conservation of the scatter: sum(rho) == number of particles; momentum conservation of
+    # the whole force step (same window for paint and readout, antisymmetric transfer):
+    # |sum_p F_d(p)| << N * rms(F)
+    rho.fill(0.0)
+    pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+    mass = _strided_sum(ctx, rho._device())
+    mass = comm.allreduce(mass, op=C.SUM)
+    fsum = [comm.allreduce(F[d].sum(), op=C.SUM) for d in range(3)]
+    fsq = comm.allreduce(sum(F[d].dot(F[d]) for d in range(3)), op=C.SUM)
+    frms = (fsq / (3.0 * ntot)) ** 0.5
+    verify = {"mass_conservation_rel_err": abs(mass - ntot) / ntot,
+              "net_force_over_n_rms_force": max(abs(f) for f in fsum) / (ntot * max(frms, 1e-300))}
     del lpos, layout, rho, out
 
     # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timing ----
@@ -293,6 +317,7 @@ def run_ours(args):
             "cufft_library_ms_per_step": round(fft_step, 3),
             "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "verify": verify,
         }
         if args.breakdown:
             line["stage_ms_per_step"] = dict((k, round(v / args.steps, 3)) for k, v in step.stage.items())

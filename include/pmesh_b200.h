@@ -145,6 +145,11 @@ int pmb_lincomb(pmb_ctx *ctx, void *out, int64_t out_stride, const void *x, int6
 int pmb_kick_drift(pmb_ctx *ctx, void *V, void *S, const void *const *F_cols_h, int ncol,
                    double kick, double drift, int elsize, int64_t npart);
 
+/* sum_i x[i] * y[i] accumulated in float64 (strided float32 / float64 columns): diagnostics such as the
+ * rms of a force column or the particle-side term of cdot (pm.py:897-902) */
+int pmb_dot(pmb_ctx *ctx, const void *x, int64_t x_stride, const void *y, int64_t y_stride, int elsize,
+            int64_t n, double *dot_h);
+
 /* ---- synthetic particles (bench / tests): counter-based, reproducible ------------- */
 /* uniform in [0, box) per axis: pos[i,d] = box[d] * u(seed, i + first, d) */
 int pmb_particles_uniform(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,

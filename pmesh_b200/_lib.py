@@ -63,7 +63,7 @@ SYMBOLS = [
     "pmb_memcpy_d2d", "pmb_memset", "pmb_mem_info", "pmb_timer_start", "pmb_timer_stop", "pmb_launch_count",
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
     "pmb_paint", "pmb_readout", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum",
-    "pmb_axpy", "pmb_lincomb", "pmb_kick_drift",
+    "pmb_axpy", "pmb_lincomb", "pmb_kick_drift", "pmb_dot",
     "pmb_particles_uniform", "pmb_particles_lattice",
     "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
@@ -93,6 +93,7 @@ _ARGTYPES = {
     "pmb_axpy": [_P, _P, _L, _P, _L, _D, _I, _L],
     "pmb_lincomb": [_P, _P, _L, _P, _L, _D, _P, _L, _D, _I, _L],
     "pmb_kick_drift": [_P, _P, _P, _P, _I, _D, _D, _I, _L],
+    "pmb_dot": [_P, _P, _L, _P, _L, _I, _L, _P],
     "pmb_particles_uniform": [_P, _P, _I, _L, _I, _P, ctypes.c_uint64, _L],
     "pmb_particles_lattice": [_P, _P, _I, _L, _I, _P, _P, _D, _D, ctypes.c_uint64, _L],
     "pmb_decompose_count": [_P, _P, _P, _P], "pmb_decompose_fill": [_P, _P, _P],

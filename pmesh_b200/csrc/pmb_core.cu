@@ -675,3 +675,50 @@ extern "C" int pmb_kick_drift(pmb_ctx *ctx, void *V, void *S, const void *const 
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }
+
+// sum_i x[i] * y[i] in float64 (diagnostics: rms of a column, cdot-style reductions); strided columns
+template <typename T>
+__global__ void __launch_bounds__(256)
+pmb_k_dot(const char *x, int64_t sx, const char *y, int64_t sy, int64_t n, double *out)
+{
+    __shared__ double sh[32];
+    double acc = 0;
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) acc += (double) *(const T *) (x + i * sx) * (double) *(const T *) (y + i * sy);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[blockIdx.x] = acc;
+    }
+}
+
+extern "C" int pmb_dot(pmb_ctx *ctx, const void *x, int64_t x_stride, const void *y, int64_t y_stride, int elsize,
+                       int64_t n, double *dot_h)
+{
+    PMB_REQUIRE(ctx && dot_h && n >= 0, "bad arguments");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "columns must be float32 or float64");
+    *dot_h = 0;
+    if (n == 0) return PMB_OK;
+    PMB_REQUIRE(x && y, "null column");
+    const int grid = pmb_grid(ctx, n, 256, 4);
+    void *partial;
+    PMB_CHECK(pmb_scratch(ctx, sizeof(double) * grid, &partial));
+    if (elsize == 8) pmb_k_dot<double><<<grid, 256, 0, ctx->stream>>>((const char *) x, x_stride, (const char *) y, y_stride, n, (double *) partial);
+    else pmb_k_dot<float><<<grid, 256, 0, ctx->stream>>>((const char *) x, x_stride, (const char *) y, y_stride, n, (double *) partial);
+    PMB_LAUNCH_CHECK(ctx);
+    double *h = (double *) malloc(sizeof(double) * grid);
+    if (!h) return PMB_ENOMEM;
+    cudaError_t e = cudaMemcpyAsync(h, partial, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); return pmb_cuda_fail(e, "dot copy", __FILE__, __LINE__); }
+    double s = 0;
+    for (int i = 0; i < grid; i++) s += h[i];
+    free(h);
+    *dot_h = s;
+    return PMB_OK;
+}

@@ -154,6 +154,27 @@ class DeviceArray(object):
                                             self.dtype.itemsize, n))
         return self
 
+    def sum(self):
+        """sum of all elements in float64 (device reduction; float32 / float64 arrays)"""
+        import ctypes
+        assert self.dtype.kind == 'f' and self.dtype.itemsize in (4, 8)
+        ptr, stride, n = self._flat()
+        out = ctypes.c_double(0.0)
+        sz = (ctypes.c_int64 * 3)(n)
+        st = (ctypes.c_int64 * 3)(stride)
+        _lib.check(self.ctx.lib.pmb_field_sum(self.ctx.handle, ptr, self.dtype.itemsize, 1, sz, st, ctypes.byref(out)))
+        return out.value
+
+    def dot(self, other):
+        """sum(self * other) in float64 (device reduction)"""
+        import ctypes
+        assert other.shape == self.shape and other.dtype == self.dtype and self.dtype.kind == 'f'
+        px, sx, n = self._flat()
+        py, sy, _ = other._flat()
+        out = ctypes.c_double(0.0)
+        _lib.check(self.ctx.lib.pmb_dot(self.ctx.handle, px, sx, py, sy, self.dtype.itemsize, n, ctypes.byref(out)))
+        return out.value
+
     def column(self, d):
         """view of column d of an (N, k) array"""
         assert self.ndim == 2

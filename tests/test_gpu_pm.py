@@ -234,3 +234,29 @@ def test_force_step_vs_oracle(P, oracle, res, n, dtype):
         Fw[:, d] = oracle.readout(fr.astype(dtype), X, res, scale=n / L, period=[n] * 3)
     tol = 1e-6 if dtype == "f8" else 2e-4
     rel_close(F, Fw, tol)
+
+
+def test_conservation_properties_at_scale():
+    """size-independent properties of the force step where the oracle is too slow (192^3 = 7 M
+    particles; bench.py reports the same two numbers at the full 1024^3): the scatter conserves mass,
+    sum(rho) == N, and the force step conserves momentum, |sum_p F(p)| << N rms(F)."""
+    import ctypes
+    from pmesh_b200 import _lib, nbody
+    from pmesh_b200.device import DeviceArray
+    from pmesh_b200.pm import ParticleMesh
+    M = 192
+    for window in ("cic", "tsc", "pcs"):
+        pm = ParticleMesh(BoxSize=float(M), Nmesh=[M, M, M], dtype="f8", resampler=window)
+        ctx = pm.ctx
+        n = M ** 3
+        X = DeviceArray.empty((n, 3), "f8")
+        box = (ctypes.c_double * 3)(float(M), float(M), float(M))
+        nn = (ctypes.c_int64 * 3)(M, M, M)
+        _lib.check(ctx.lib.pmb_particles_lattice(ctx.handle, X.ptr, 8, n, 3, nn, box, 0.5, 3.0, 44, 0))
+        rho = pm.paint(X)
+        assert abs(rho.csum() - n) < 1e-10 * n
+        F = nbody.force(pm, X)
+        rms = (sum(f.dot(f) for f in F) / (3.0 * n)) ** 0.5
+        assert rms > 0
+        for f in F:
+            assert abs(f.sum()) < 1e-9 * n * rms
