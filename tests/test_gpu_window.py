@@ -336,6 +336,15 @@ def test_scheduled_kernels_large_inputs(W, oracle, name, order):
                 mesh = DeviceArray.zeros(shape, dtype)
                 W.windows[name].paint(mesh, dpos, mass=dmass, diffdir=diffdir, transform=tr, mode="atomic")
                 assert_allclose(mesh.to_host(), want, rtol=tol, atol=tol * max(abs(want).max(), 1e-30))
+                # ... and the gather of a gradient window, bit for bit
+                r = W.windows[name].readout(DeviceArray.from_host(field), dpos, diffdir=diffdir, transform=tr)
+                assert_array_equal(r.to_host(), oracle.readout(field, pos, name, diffdir=diffdir, translate=translate, period=[N] * 3))
+            # value + all gradients from one sweep == the separate gathers
+            val, grad = W.windows[name].readout_grad(DeviceArray.from_host(field), dpos, transform=tr)
+            assert_array_equal(val.to_host(), oracle.readout(field, pos, name, translate=translate, period=[N] * 3))
+            gh = grad.to_host()
+            for d in range(3):
+                assert_array_equal(gh[:, d], oracle.readout(field, pos, name, diffdir=d, translate=translate, period=[N] * 3))
     # anisotropic scale, non-periodic canvas (points outside are dropped), float32 positions
     tr = W.Affine(3, scale=[0.9, 1.1, 0.5], translate=[1.0, -2.0, 3.5], period=0)
     shape = (60, 70, 40)
@@ -345,3 +354,6 @@ def test_scheduled_kernels_large_inputs(W, oracle, name, order):
     mesh = DeviceArray.zeros(shape, "f8")
     W.windows[name].paint(mesh, DeviceArray.from_host(p4), mass=dmass, transform=tr, mode="atomic")
     assert_allclose(mesh.to_host(), want, rtol=1e-6, atol=1e-6 * abs(want).max())
+    field = rng.uniform(-1, 1, shape)
+    r = W.windows[name].readout(DeviceArray.from_host(field), DeviceArray.from_host(p4), transform=tr)
+    assert_array_equal(r.to_host(), oracle.readout(field, p4, name, scale=[0.9, 1.1, 0.5], translate=[1.0, -2.0, 3.5], period=[0] * 3))
