@@ -655,58 +655,6 @@ extern "C" int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a)
                  : paint_deterministic<uint64_t, float>(ctx, a, g, w, p);
 }
 
-// y-carry gather (pmb_k_readout_carry32): large 3-D inputs, tuned windows, 32-bit addressable canvas.
-// Returns 1 when the kernel was launched, 0 when the caller should take the ordinary path.
-template <typename MeshT>
-static int readout_carry(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbParticles &p, int fam,
-                         void *grad, int64_t gs0, int64_t gs1, int *launched)
-{
-    *launched = 0;
-    const int want = pmb_env_flag("PMB_READOUT_CARRY", 1);    // 1: TSC / PCS / gradients, 2: CIC values too, 0: off
-    const int unit = pmb_env_flag("PMB_CARRY_UNIT", 128);
-    if (!want || unit <= 0 || fam < 2 || a->ndim != 3 || a->npart < ((int64_t) 1 << 18)) return PMB_OK;
-    const bool plain_cic = fam == 2 && !grad && !(a->order[0] | a->order[1] | a->order[2]);
-    if (plain_cic && want < 2) return PMB_OK;
-    int64_t span = 0;
-    for (int d = 0; d < 3; d++) {
-        if (a->strides[d] < 0 || a->strides[d] % (int64_t) sizeof(MeshT)) return PMB_OK;
-        span += (a->size[d] - 1) * (a->strides[d] / (int64_t) sizeof(MeshT));
-    }
-    if (span >= ((int64_t) 1 << 31) - 1) return PMB_OK;
-    const uint32_t *order;
-    int64_t nchunks;
-    PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks, 1));
-    const int64_t nunits = (nchunks + unit - 1) / unit;
-    const int64_t capu = (int64_t) ctx->sm_count * pmb_env_flag("PMB_GRID_MULT", 8);
-    const int gridu = (int) (nunits < capu ? nunits : capu);
-    PmbGeom32o go;
-    for (int d = 0; d < 3; d++) {
-        go.g.scale[d] = g.scale[d]; go.g.translate[d] = g.translate[d];
-        go.g.period[d] = (int) g.period[d]; go.g.size[d] = (int) g.size[d];
-        go.g.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
-        go.order[d] = a->order[d];
-    }
-    go.pcsfix = a->pcs_gradient_scale_fix;
-    const bool chk = pmb_geom_needs_check(g);
-    const bool pos8 = pmb_pos_is_f8_rows(p);
-#define PMB_CARRY_READ(FAMV, POSV, GRADV)                                                                       \
-    PMB_DISPATCH_CHECK(chk, (pmb_k_readout_carry32<MeshT, FAMV, CHECK, POSV, GRADV><<<gridu, PMB_CHUNK, 0, ctx->stream>>>( \
-        go, p, (const MeshT *) a->mesh, a->npart, a->out, a->out_elsize, a->out_stride, grad, gs0, gs1, order, nchunks, unit)))
-#define PMB_CARRY_READ_FAM(POSV, GRADV)                                                                         \
-    do {                                                                                                        \
-        if (fam == 2) { PMB_CARRY_READ(2, POSV, GRADV); }                                                       \
-        else if (fam == 3) { PMB_CARRY_READ(3, POSV, GRADV); }                                                  \
-        else { PMB_CARRY_READ(4, POSV, GRADV); }                                                                \
-    } while (0)
-    if (grad) { if (pos8) PMB_CARRY_READ_FAM(true, true); else PMB_CARRY_READ_FAM(false, true); }
-    else { if (pos8) PMB_CARRY_READ_FAM(true, false); else PMB_CARRY_READ_FAM(false, false); }
-#undef PMB_CARRY_READ_FAM
-#undef PMB_CARRY_READ
-    PMB_LAUNCH_CHECK(ctx);
-    *launched = 1;
-    return PMB_OK;
-}
-
 template <typename MeshT>
 static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
                         const PmbParticles &p)
@@ -718,11 +666,6 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
     // 13.6 (the schedule's indirection costs more than it saves for reads).  PMB_SCHED_READOUT=2
     // adds the spatial schedule, 0 falls back to the grid-stride kernel.
     const int sched_readout = pmb_env_flag("PMB_SCHED_READOUT", 1);
-    if (fam && sched_readout) {
-        int launched = 0;
-        PMB_CHECK(readout_carry<MeshT>(ctx, a, g, p, fam, NULL, 0, 0, &launched));
-        if (launched) return PMB_OK;
-    }
     if (fam && a->ndim == 3 && a->npart >= ((int64_t) 1 << 18) && sched_readout) {
         const uint32_t *order = NULL;
         int64_t nchunks = (a->npart + PMB_CHUNK - 1) / PMB_CHUNK;
@@ -746,17 +689,6 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.scale[d] = g.scale[d]; g32.translate[d] = g.translate[d];
                     g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
-                }
-                if (pmb_env_flag("PMB_READOUT_PIPE", 0)) {
-                    if (pmb_pos_is_f8_rows(p)) {
-                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_pipe<MeshT, CHECK, true><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
-                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
-                    } else {
-                        PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_pipe<MeshT, CHECK, false><<<grid, PMB_CHUNK, 0, ctx->stream>>>(
-                            g32, p, (const MeshT *) mesh, a->npart, a->out, a->out_elsize, a->out_stride, order, nchunks, ticket)));
-                    }
-                    PMB_LAUNCH_CHECK(ctx);
-                    return PMB_OK;
                 }
                 // resident CTAs per SM: measured at 1024^3 (ms): 5 -> 11.44, 6 -> 10.73 (the gather is
                 // latency-bound: more warps in flight beat more loads per warp, cf. the _pipe variant)
@@ -844,12 +776,6 @@ extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *
     PmbWindow w;
     PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
     const int fam = fixed_family(w, a);
-    if (fam && a->ndim == 3) {
-        int launched = 0;
-        if (a->mesh_elsize == 8) PMB_CHECK(readout_carry<double>(ctx, a, g, p, fam, out_grad, gs0, gs1, &launched));
-        else PMB_CHECK(readout_carry<float>(ctx, a, g, p, fam, out_grad, gs0, gs1, &launched));
-        if (launched) return PMB_OK;
-    }
     if (!fam) {
         // generic windows: value pass + one pass per axis through the ordinary readout kernel
         pmb_resample_args b = *a;

@@ -722,6 +722,12 @@ pmb_k_readout_sched(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, 
     }
 }
 
+// Rejected gather variants (measured on B200, kept in the git history, profiles/README.md):
+//  * three chunks in flight per CTA (positions of k+2, gathers of k+1, sums of k): 13.3 ms vs 11.4 at
+//    1024^3 -- the extra registers cost two resident CTAs and warps in flight matter more;
+//  * y-carry of the mesh rows in registers + z sharing by shuffle (the mirror image of the scatter's
+//    carry): CIC 1.96 vs 1.30 ms, TSC 4.38 vs 3.07, PCS 9.2 vs 5.5 at 512^3 -- the repeated loads of
+//    the plain gather hit L1 and are cheaper than the register traffic that avoids them.
 // ---- CIC gather with 32-bit element indices ---------------------------------------------------------
 // Same pipeline as pmb_k_readout_sched (dynamic tickets, positions of the next chunk prefetched) with
 // the lean index arithmetic of pmb_k_paint_cic_carry32.  Sums in the reference's point order:
@@ -788,235 +794,3 @@ pmb_k_readout_cic32(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh,
     }
 }
 
-// ---- CIC gather, three chunks in flight ------------------------------------------------------------
-// ncu on pmb_k_readout_cic32: DRAM traffic = algorithmic bytes, 58 % of peak, top stall long
-// scoreboard (11.5 of 19.7 cycles per instruction): a chunk issues its 8 mesh gathers and then sits
-// on them.  Here a CTA keeps three chunks in different stages: the positions of chunk k+2 are being
-// loaded, the mesh values of chunk k+1 are being gathered (addresses from positions that arrived
-// one iteration ago), and chunk k -- whose values arrived during the previous iteration -- is
-// weighted, summed (reference point order: bit-identical results) and stored.
-template <typename MeshT, bool CHECK, bool POS8>
-__global__ void __launch_bounds__(PMB_CHUNK, 3)
-pmb_k_readout_cic32_pipe(PmbGeom32 g, PmbParticles p, const MeshT *__restrict__ mesh, int64_t npart,
-                         void *out, int out_elsize, int64_t out_stride,
-                         const uint32_t *__restrict__ order, int64_t nchunks, unsigned long long *ticket)
-{
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    __shared__ long long s_chunk[4];
-    if (threadIdx.x == 0) {
-        s_chunk[0] = pmb_next_chunk(ticket, order, nchunks);
-        s_chunk[1] = pmb_next_chunk(ticket, order, nchunks);
-        s_chunk[2] = pmb_next_chunk(ticket, order, nchunks);
-    }
-    __syncthreads();
-    int64_t c0 = s_chunk[0], c1 = s_chunk[1], c2 = s_chunk[2];
-    // stage state of chunk c0: weights + gathered values; of chunk c1: positions
-    double V0[3][2];           // [axis][point] weights of the chunk being consumed
-    double mv[8];
-    bool ok0[8];
-    double x1[3] = {0, 0, 0};  // positions of the chunk whose gathers are issued next
-
-    auto gather = [&](double xa, double xb, double xc, double (&V)[3][2], double (&m)[8], bool (&ok)[8]) {
-        int ex[2], ey[2], ez[2];
-        pmb_cic_axis32<CHECK>(xa, g.scale[0], g.translate[0], g.period[0], g.size[0], g.estride[0], V[0][0], V[0][1], ex[0], ex[1]);
-        pmb_cic_axis32<CHECK>(xb, g.scale[1], g.translate[1], g.period[1], g.size[1], g.estride[1], V[1][0], V[1][1], ey[0], ey[1]);
-        pmb_cic_axis32<CHECK>(xc, g.scale[2], g.translate[2], g.period[2], g.size[2], g.estride[2], V[2][0], V[2][1], ez[0], ez[1]);
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int q = a * 4 + b * 2 + c;
-                    ok[q] = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0);
-                    m[q] = ok[q] ? pmb_mesh_load<MeshT, false>((const char *) mesh, (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), policy) : 0.0;
-                }
-    };
-
-    // prologue: chunk c0 gathered, positions of c1 in flight
-    {
-        double a0 = 0, a1 = 0, a2 = 0;
-        if (c0 >= 0 && c0 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c0 * PMB_CHUNK + threadIdx.x, a0, a1, a2);
-        if (c1 >= 0 && c1 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c1 * PMB_CHUNK + threadIdx.x, x1[0], x1[1], x1[2]);
-        gather(a0, a1, a2, V0, mv, ok0);
-    }
-    for (int it = 0; c0 >= 0; it++) {
-        unsigned long long tk = 0;
-        if (threadIdx.x == 0) tk = atomicAdd(ticket, 1ull);
-        // positions of c2
-        double x2[3] = {0, 0, 0};
-        if (c2 >= 0 && c2 * PMB_CHUNK + threadIdx.x < npart) pmb_load_pos3<POS8>(p, c2 * PMB_CHUNK + threadIdx.x, x2[0], x2[1], x2[2]);
-        // gathers of c1 (its positions arrived during the previous iteration)
-        double V1[3][2], mn[8];
-        bool ok1[8];
-        if (c1 >= 0) gather(x1[0], x1[1], x1[2], V1, mn, ok1);
-        // consume c0
-        const int64_t i = c0 * PMB_CHUNK + threadIdx.x;
-        if (i < npart) {
-            double value = 0;
-#pragma unroll
-            for (int a = 0; a < 2; a++)
-#pragma unroll
-                for (int b = 0; b < 2; b++)
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int q = a * 4 + b * 2 + c;
-                        if (!CHECK || ok0[q]) value += mv[q] * ((V0[0][a] * V0[1][b]) * V0[2][c]);
-                    }
-            pmb_st_real_stream(out, i * out_stride, out_elsize, value);
-        }
-        if (threadIdx.x == 0) s_chunk[(it + 3) & 3] = pmb_resolve_chunk(tk, order, nchunks);
-        __syncthreads();
-        c0 = c1; c1 = c2; c2 = s_chunk[(it + 3) & 3];
-#pragma unroll
-        for (int q = 0; q < 8; q++) { mv[q] = mn[q]; ok0[q] = ok1[q]; }
-#pragma unroll
-        for (int d = 0; d < 3; d++) { V0[d][0] = V1[d][0]; V0[d][1] = V1[d][1]; x1[d] = x2[d]; }
-    }
-}
-
-// ---- y-carry gather for every tuned window, optionally with all three gradients ----------------------
-// Mirror image of pmb_k_paint_carry32: the FAM - 1 mesh rows (FAM x FAM values each) a stencil shares
-// with the stencil of the thread's next particle along y stay in registers; only the new row is read,
-// and of that row each lane loads one z cell per x row and takes the other FAM - 1 from the lanes
-// above it by shuffle when they hold exactly the cells it needs (checked by index; otherwise it loads
-// them itself).  Mesh loads per particle: FAM^3 -> FAM (+ fallbacks).  The values are the same mesh
-// words and the weighted sum runs in the reference's point order, so results stay bit-identical to
-// the plain kernels.  GRAD: value and the three window gradients from one sweep (the vjp helper).
-template <typename MeshT, int FAM, bool CHECK, bool POS8, bool GRAD>
-__global__ void __launch_bounds__(PMB_CHUNK, (FAM == 2 ? 4 : (FAM == 3 ? 2 : 1)))
-pmb_k_readout_carry32(PmbGeom32o go, PmbParticles p, const MeshT *__restrict__ mesh, int64_t npart,
-                      void *out, int out_elsize, int64_t out_stride, void *grad, int64_t gs0, int64_t gs1,
-                      const uint32_t *__restrict__ order, int64_t nchunks, int unit)
-{
-    const PmbGeom32 &g = go.g;
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    const int lane = threadIdx.x & 31;
-    const int64_t nunits = (nchunks + unit - 1) / unit;
-    auto ld = [&](int e) -> double {
-        return pmb_mesh_load<MeshT, false>((const char *) mesh, (int64_t) e * sizeof(MeshT), policy);
-    };
-    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-        double rows[FAM][FAM][FAM];          // [y row b][x a][z c]; rows 0 .. FAM-2 carried between particles
-        int cex[FAM], cez[FAM], cey[FAM - 1];
-#pragma unroll
-        for (int a = 0; a < FAM; a++) { cex[a] = -2; cez[a] = -2; }
-#pragma unroll
-        for (int b = 0; b < FAM - 1; b++) cey[b] = -2;
-#pragma unroll
-        for (int b = 0; b < FAM; b++)
-#pragma unroll
-            for (int a = 0; a < FAM; a++)
-#pragma unroll
-                for (int c = 0; c < FAM; c++) rows[b][a][c] = 0;
-        bool have = false;
-        const int64_t cend = min((u + 1) * (int64_t) unit, nchunks);
-        int64_t chunk = order ? (int64_t) order[u * unit] : u * unit;
-        double xn0 = 0, xn1 = 0, xn2 = 0;
-        {
-            const int64_t i0 = chunk * PMB_CHUNK + threadIdx.x;
-            if (i0 < npart) pmb_load_pos3<POS8>(p, i0, xn0, xn1, xn2);
-        }
-        for (int64_t cb = u * unit; cb < cend; cb++) {
-            const int64_t i = chunk * PMB_CHUNK + threadIdx.x;
-            const bool active = i < npart;
-            const double x0 = xn0, x1 = xn1, x2 = xn2;
-            if (cb + 1 < cend) {
-                chunk = order ? (int64_t) order[cb + 1] : cb + 1;
-                const int64_t in = chunk * PMB_CHUNK + threadIdx.x;
-                if (in < npart) pmb_load_pos3<POS8>(p, in, xn0, xn1, xn2);
-            }
-            double Vx[FAM], Vy[FAM], Vz[FAM];
-            int ex[FAM], ey[FAM], ez[FAM];
-            pmb_axis32<FAM, CHECK>(x0, GRAD ? 0 : go.order[0], g.scale[0], g.translate[0], go.pcsfix, g.period[0], g.size[0], g.estride[0], Vx, ex);
-            pmb_axis32<FAM, CHECK>(x1, GRAD ? 0 : go.order[1], g.scale[1], g.translate[1], go.pcsfix, g.period[1], g.size[1], g.estride[1], Vy, ey);
-            pmb_axis32<FAM, CHECK>(x2, GRAD ? 0 : go.order[2], g.scale[2], g.translate[2], go.pcsfix, g.period[2], g.size[2], g.estride[2], Vz, ez);
-            bool same = have && active;
-#pragma unroll
-            for (int a = 0; a < FAM; a++) same = same && cex[a] == ex[a] && cez[a] == ez[a];
-#pragma unroll
-            for (int b = 0; b < FAM - 1; b++) same = same && cey[b] == ey[b];
-            if (active && !same) {
-                // nothing to reuse: read the FAM - 1 leading rows the ordinary way
-#pragma unroll
-                for (int b = 0; b < FAM - 1; b++)
-#pragma unroll
-                    for (int a = 0; a < FAM; a++)
-#pragma unroll
-                        for (int c = 0; c < FAM; c++) {
-                            const bool ok = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0);
-                            rows[b][a][c] = ok ? ld(ex[a] + ey[b] + ez[c]) : 0.0;
-                        }
-            }
-            // the new row b = FAM - 1: one load per x row, the other z cells from the lanes above
-            const bool rowok = active && (!CHECK || ey[FAM - 1] >= 0);
-#pragma unroll
-            for (int a = 0; a < FAM; a++) {
-                const bool aok = rowok && (!CHECK || ex[a] >= 0);
-                const int i0 = (aok && (!CHECK || ez[0] >= 0)) ? ex[a] + ey[FAM - 1] + ez[0] : -1;
-                const double v0 = i0 >= 0 ? ld(i0) : 0.0;
-                rows[FAM - 1][a][0] = v0;
-#pragma unroll
-                for (int c = 1; c < FAM; c++) {
-                    const int want = (aok && (!CHECK || ez[c] >= 0)) ? ex[a] + ey[FAM - 1] + ez[c] : -1;
-                    const int tidx = __shfl_down_sync(0xffffffffu, i0, c);
-                    const double tval = __shfl_down_sync(0xffffffffu, v0, c);
-                    const bool hit = lane + c < 32 && want >= 0 && tidx == want;
-                    rows[FAM - 1][a][c] = hit ? tval : (want >= 0 ? ld(want) : 0.0);
-                }
-            }
-            if (active) {
-                if (!GRAD) {
-                    double value = 0;
-#pragma unroll
-                    for (int a = 0; a < FAM; a++)
-#pragma unroll
-                        for (int b = 0; b < FAM; b++)
-#pragma unroll
-                            for (int c = 0; c < FAM; c++)
-                                if (!CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0))
-                                    value += rows[b][a][c] * ((Vx[a] * Vy[b]) * Vz[c]);
-                    pmb_st_real_stream(out, i * out_stride, out_elsize, value);
-                } else {
-                    double Dx[FAM], Dy[FAM], Dz[FAM];
-                    int scratch[FAM];
-                    pmb_axis32<FAM, CHECK>(x0, 1, g.scale[0], g.translate[0], go.pcsfix, g.period[0], g.size[0], g.estride[0], Dx, scratch);
-                    pmb_axis32<FAM, CHECK>(x1, 1, g.scale[1], g.translate[1], go.pcsfix, g.period[1], g.size[1], g.estride[1], Dy, scratch);
-                    pmb_axis32<FAM, CHECK>(x2, 1, g.scale[2], g.translate[2], go.pcsfix, g.period[2], g.size[2], g.estride[2], Dz, scratch);
-                    double value = 0, g0 = 0, g1 = 0, g2 = 0;
-#pragma unroll
-                    for (int a = 0; a < FAM; a++)
-#pragma unroll
-                        for (int b = 0; b < FAM; b++)
-#pragma unroll
-                            for (int c = 0; c < FAM; c++)
-                                if (!CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[c] >= 0)) {
-                                    const double mval = rows[b][a][c];
-                                    value += mval * ((Vx[a] * Vy[b]) * Vz[c]);
-                                    g0 += mval * ((Dx[a] * Vy[b]) * Vz[c]);
-                                    g1 += mval * ((Vx[a] * Dy[b]) * Vz[c]);
-                                    g2 += mval * ((Vx[a] * Vy[b]) * Dz[c]);
-                                }
-                    if (out) pmb_st_real_stream(out, i * out_stride, out_elsize, value);
-                    pmb_st_real_stream(grad, i * gs0, out_elsize, g0);
-                    pmb_st_real_stream(grad, i * gs0 + gs1, out_elsize, g1);
-                    pmb_st_real_stream(grad, i * gs0 + 2 * gs1, out_elsize, g2);
-                }
-            }
-            // slide the window: row b becomes row b - 1 of the next particle along y
-#pragma unroll
-            for (int b = 1; b < FAM; b++)
-#pragma unroll
-                for (int a = 0; a < FAM; a++)
-#pragma unroll
-                    for (int c = 0; c < FAM; c++) rows[b - 1][a][c] = rows[b][a][c];
-            have = active;
-#pragma unroll
-            for (int a = 0; a < FAM; a++) { cex[a] = ex[a]; cez[a] = ez[a]; }
-#pragma unroll
-            for (int b = 0; b < FAM - 1; b++) cey[b] = ey[b + 1];
-        }
-    }
-}
