@@ -147,9 +147,10 @@ def test_preview(PM):
     assert_allclose(comp1.preview(Nmesh=4, axes=(0, 2)), preview.sum(axis=1))
     assert_allclose(comp1.preview(Nmesh=4, axes=(2, 0)), preview.sum(axis=1).T)
     assert_allclose(comp1.preview(Nmesh=4, axes=(0,)), preview.sum(axis=(1, 2)))
+    comp1.value[...] += 2.0                       # a non-zero mean to look at
     p8 = comp1.preview(Nmesh=8, axes=(0,))
     assert p8.shape == (8,)
-    assert_allclose(p8.mean(), comp1.cmean() * 16, rtol=1e-10)      # keep_mean upsampling, summed over 4 x 4
+    assert_allclose(p8.mean(), comp1.cmean() * 64, rtol=1e-10)      # keep_mean upsampling, summed over 8 x 8
     p2 = comp1.preview(Nmesh=2, axes=(0, 1, 2))
     assert p2.shape == (2, 2, 2)
     assert_allclose(p2.mean(), comp1.cmean(), rtol=1e-10)
