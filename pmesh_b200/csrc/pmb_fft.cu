@@ -42,6 +42,7 @@ struct pmb_fft {
     int xcur;                     // landing buffer used by the next transform (they alternate)
     void *xbuf[2];                // my landing buffers (cudaMalloc, IPC-exported)
     void *peer_x[64][2];          // the same buffers of every rank, mapped into this process
+    void *pool;                   // the pool entry that owns them
     cudaEvent_t ev[FFT_NEV][2];
     int nev;
     float lib_ms;
@@ -80,68 +81,112 @@ static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long lo
 }
 
 // ---- peer-memory landing buffers -------------------------------------------------------------------
-// One process per GPU: the buffers are shared with cudaIpc handles, exchanged once per plan over the
-// communicator.  Any failure (IPC not permitted in the container, no peer access) leaves p2p = 0 on
-// EVERY rank -- the decision is agreed with an allgather -- and the transforms use NCCL send/recv.
+// One process per GPU: the buffers are shared with cudaIpc handles, exchanged over the communicator.
+// Any failure (IPC not permitted in the container, no peer access) leaves p2p = 0 on EVERY rank --
+// the decision is agreed with an allgather -- and the transforms use NCCL send/recv.
+//
+// Lifetime: buffers and mappings live in a process-wide pool and are never unmapped or freed before
+// the process exits.  CUDA leaves freeing an exported allocation that a peer still maps undefined,
+// and plans are destroyed at different moments on different ranks (garbage collection), so a plan
+// only RETURNS its pool entry when it dies; the next plan of the same mesh takes it again -- if every
+// rank has one to take (agreed with an allgather; otherwise all ranks create a fresh entry together).
+struct P2PEntry {
+    pmb_ctx *ctx;
+    int64_t n[3];
+    int elsize, P;
+    size_t bytes;
+    void *xbuf[2];
+    void *peer_x[64][2];
+    bool in_use;
+    P2PEntry *next;
+};
+static P2PEntry *g_p2p_pool = NULL;
+
 static int p2p_setup(pmb_fft *f)
 {
     pmb_ctx *ctx = f->ctx;
     f->p2p = 0;
     f->xcur = 0;
+    f->pool = NULL;
     const char *env = getenv("PMB_FFT_P2P");
-    const int want = env ? atoi(env) : 1;
-    struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad; } mine, all[64];
-    memset(&mine, 0, sizeof(mine));
-    mine.ok = want && f->P <= 64;
-    if (mine.ok) {
+    const int want = (env ? atoi(env) : 1) && f->P <= 64;
+    // 1. can everybody reuse an idle entry of this mesh?
+    P2PEntry *idle = NULL;
+    for (P2PEntry *e = g_p2p_pool; e && want; e = e->next)
+        if (!e->in_use && e->ctx == ctx && e->P == f->P && e->elsize == f->elsize && e->bytes >= f->work_bytes &&
+            e->n[0] == f->n[0] && e->n[1] == f->n[1] && e->n[2] == f->n[2]) { idle = e; break; }
+    int flags[2] = {want, idle != NULL}, allflags[64][2];
+    PMB_CHECK(pmb_allgather_host(ctx, flags, allflags, sizeof(flags)));
+    int all_want = 1, all_idle = 1;
+    for (int q = 0; q < f->P; q++) { all_want = all_want && allflags[q][0]; all_idle = all_idle && allflags[q][1]; }
+    if (!all_want) return PMB_OK;
+    if (all_idle) {
+        idle->in_use = true;
+        f->pool = idle;
+    } else {
+        // 2. a fresh entry, created by all ranks together
+        P2PEntry *e = (P2PEntry *) calloc(1, sizeof(P2PEntry));
+        if (!e) return PMB_ENOMEM;
+        struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad; } mine, all[64];
+        memset(&mine, 0, sizeof(mine));
+        mine.ok = 1;
         for (int b = 0; b < 2 && mine.ok; b++) {
-            if (cudaMalloc(&f->xbuf[b], f->work_bytes) != cudaSuccess) { f->xbuf[b] = NULL; mine.ok = 0; break; }
-            if (cudaIpcGetMemHandle(&mine.h[b], f->xbuf[b]) != cudaSuccess) mine.ok = 0;
+            if (cudaMalloc(&e->xbuf[b], f->work_bytes) != cudaSuccess) { e->xbuf[b] = NULL; mine.ok = 0; break; }
+            if (cudaIpcGetMemHandle(&mine.h[b], e->xbuf[b]) != cudaSuccess) mine.ok = 0;
         }
         cudaGetLastError();
-    }
-    PMB_CHECK(pmb_allgather_host(ctx, &mine, all, sizeof(Rec)));
-    int ok = 1;
-    for (int q = 0; q < f->P; q++) ok = ok && all[q].ok;
-    if (ok) {
+        PMB_CHECK(pmb_allgather_host(ctx, &mine, all, sizeof(Rec)));
+        int ok = 1;
+        for (int q = 0; q < f->P; q++) ok = ok && all[q].ok;
         for (int q = 0; q < f->P && ok; q++)
             for (int b = 0; b < 2 && ok; b++) {
-                if (q == f->rank) { f->peer_x[q][b] = f->xbuf[b]; continue; }
-                if (cudaIpcOpenMemHandle(&f->peer_x[q][b], all[q].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                    f->peer_x[q][b] = NULL;
+                if (q == f->rank) { e->peer_x[q][b] = e->xbuf[b]; continue; }
+                if (cudaIpcOpenMemHandle(&e->peer_x[q][b], all[q].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    e->peer_x[q][b] = NULL;
                     ok = 0;
                 }
             }
         cudaGetLastError();
-    }
-    // second agreement: every rank could map every buffer
-    int mine_ok = ok, all_ok[64];
-    PMB_CHECK(pmb_allgather_host(ctx, &mine_ok, all_ok, sizeof(int)));
-    for (int q = 0; q < f->P; q++) ok = ok && all_ok[q];
-    f->p2p = ok;
-    if (!ok) {
-        for (int q = 0; q < f->P; q++)
-            for (int b = 0; b < 2; b++)
-                if (q != f->rank && f->peer_x[q][b]) { cudaIpcCloseMemHandle(f->peer_x[q][b]); f->peer_x[q][b] = NULL; }
-        // peers may still be unmapping: nobody frees before everybody is done
+        // every rank could map every buffer?
+        int mine_ok = ok, all_ok[64];
         PMB_CHECK(pmb_allgather_host(ctx, &mine_ok, all_ok, sizeof(int)));
-        for (int b = 0; b < 2; b++) if (f->xbuf[b]) { cudaFree(f->xbuf[b]); f->xbuf[b] = NULL; }
-        cudaGetLastError();
+        for (int q = 0; q < f->P; q++) ok = ok && all_ok[q];
+        if (!ok) {
+            for (int q = 0; q < f->P; q++)
+                for (int b = 0; b < 2; b++)
+                    if (q != f->rank && e->peer_x[q][b]) cudaIpcCloseMemHandle(e->peer_x[q][b]);
+            // peers may still be unmapping: nobody frees before everybody is done
+            PMB_CHECK(pmb_allgather_host(ctx, &mine_ok, all_ok, sizeof(int)));
+            for (int b = 0; b < 2; b++) if (e->xbuf[b]) cudaFree(e->xbuf[b]);
+            cudaGetLastError();
+            free(e);
+            return PMB_OK;
+        }
+        e->ctx = ctx; e->P = f->P; e->elsize = f->elsize; e->bytes = f->work_bytes;
+        for (int d = 0; d < 3; d++) e->n[d] = f->n[d];
+        e->in_use = true;
+        e->next = g_p2p_pool;
+        g_p2p_pool = e;
+        f->pool = e;
     }
+    P2PEntry *e = (P2PEntry *) f->pool;
+    for (int b = 0; b < 2; b++) {
+        f->xbuf[b] = e->xbuf[b];
+        for (int q = 0; q < f->P; q++) f->peer_x[q][b] = e->peer_x[q][b];
+    }
+    f->p2p = 1;
     return PMB_OK;
 }
 
 static void p2p_teardown(pmb_fft *f)
 {
     if (!f->p2p) return;
-    for (int q = 0; q < f->P; q++)
-        for (int b = 0; b < 2; b++)
-            if (q != f->rank && f->peer_x[q][b]) cudaIpcCloseMemHandle(f->peer_x[q][b]);
-    // the owner frees only after every peer has unmapped (collective: plans are destroyed in the
-    // same order on every rank); if the communicator is already gone the process is exiting anyway
-    if (f->ctx->comm) pmb_stream_barrier(f->ctx);
+    // No collective and no unmapping here (see above): a peer stores into my buffers only inside a
+    // transform, and I cannot have passed that transform's barrier before its stores landed; the
+    // entry goes back to the pool for the next plan of this mesh.
     cudaStreamSynchronize(f->ctx->stream);
-    for (int b = 0; b < 2; b++) if (f->xbuf[b]) cudaFree(f->xbuf[b]);
+    ((P2PEntry *) f->pool)->in_use = false;
+    f->pool = NULL;
     f->p2p = 0;
 }
 

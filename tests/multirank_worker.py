@@ -118,6 +118,15 @@ def main():
         comm.Barrier()
         if r == 0:
             print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
+    # a second mesh of a configuration used before takes the pooled peer-memory landing buffers again
+    del pm
+    for rep in range(2):
+        pm = ParticleMesh(BoxSize=100.0, Nmesh=[16, 16, 16], dtype="f8", resampler="cic", comm=comm)
+        shape = pm._layout["i_shape"]
+        x = numpy.random.default_rng(7 + r).uniform(size=tuple(shape))
+        f = pm.create("real", value=x)
+        assert rel(f.r2c().c2r().value, x) < 1e-12
+        del f, pm
     comm.Barrier()
     print("rank %d done" % r)
 
