@@ -1,0 +1,56 @@
+"""Host-side logic that needs neither a GPU nor the oracle: index tables of the Fourier resample,
+the identity layout's lazy indices, offsets bookkeeping of Layout (reference domain.py:92-123)."""
+import numpy
+from numpy.testing import assert_array_equal
+
+
+def test_reindex_matches_the_reference_examples():
+    from pmesh_b200.pm import reindex
+    # the docstring examples of pm.py:1128-1144
+    assert_array_equal(reindex(8, 4), [0, 1, 2, 7])
+    assert_array_equal(reindex(4, 8), [0, 1, 2, -1, -1, -1, -1, 3])
+    # same mesh: identity; frequencies are preserved wherever the index is valid
+    assert_array_equal(reindex(6, 6), numpy.arange(6))
+    for ns, nd in ((8, 4), (4, 8), (16, 6), (6, 16)):
+        r = reindex(ns, nd)
+        fs = numpy.fft.fftfreq(ns) * ns
+        fd = numpy.fft.fftfreq(nd) * nd
+        ok = r >= 0
+        # apart from the Nyquist of the smaller mesh (sign ambiguous), indices map equal frequencies
+        nyq = min(ns, nd) // 2
+        sel = ok & (abs(fd) != nyq)
+        assert_array_equal(fs[r[sel]], fd[sel])
+
+
+def test_identity_layout_is_lazy_and_consistent():
+    from pmesh_b200.comm import SelfComm
+    from pmesh_b200.domain import Layout
+    lay = Layout(SelfComm(), 1000, numpy.array([1000], dtype='int32'), None, identity=True)
+    assert lay.identity and lay._indices_host is None and lay._indices_dev is None
+    assert_array_equal(lay.sendoffsets, [0])
+    assert_array_equal(lay.recvcounts, [1000])
+    assert lay.recvlength == 1000 and lay.sendlength == 1000
+    assert lay._indices_ptr() is None
+    ind = lay.indices
+    assert ind.dtype == numpy.dtype('int32')
+    assert_array_equal(ind, numpy.arange(1000))
+    assert_array_equal(lay.get_exchange_cost(), [0])
+
+
+def test_layout_offsets():
+    from pmesh_b200.domain import Layout
+
+    class Comm3(object):
+        rank, size = 1, 3
+
+        def Alltoall(self, send, recv):
+            recv[...] = [5, 7, 11]
+
+        def allgather(self, x):
+            return [x] * 3
+    lay = Layout(Comm3(), 10, numpy.array([2, 3, 4], dtype='int32'), numpy.arange(9, dtype='int32'))
+    assert_array_equal(lay.sendoffsets, [0, 2, 5])
+    assert_array_equal(lay.recvcounts, [5, 7, 11])
+    assert_array_equal(lay.recvoffsets, [0, 5, 12])
+    assert lay.recvlength == 23 and not lay.identity
+    assert_array_equal(lay.get_exchange_cost(), [6, 6, 6])
