@@ -51,7 +51,9 @@ def main():
     Q = DeviceArray.from_host(pm.generate_uniform_particle_grid(shift=0.0))
     DX1 = nbody.lpt1(pm, dlinear, Q)
     a0 = 0.1
-    S = DeviceArray.empty(Q.shape, "f8").assign_lincomb(DX1, a0)
+    # normalise the displacement field to 0.3 cells rms at the start (it grows ~ 10x to a = 1)
+    rms = (comm.allreduce(DX1.dot(DX1), op=C.SUM) / (3.0 * comm.allreduce(Q.shape[0], op=C.SUM))) ** 0.5
+    S = DeviceArray.empty(Q.shape, "f8").assign_lincomb(DX1, 0.3 / rms)
     V = DeviceArray.empty(Q.shape, "f8").assign_lincomb(S, a0 ** 2 * a0 ** -1.5)
     ctx.sync()
     t_ic = (time.perf_counter() - t0) * 1e3
