@@ -13,137 +13,7 @@
 // write cursor, and ballots inside the block keep the particle order stable.
 #include "pmb_internal.h"
 
-#define ROUTE_BLOCK 256
-#define ROUTE_MAXRANKS 64
-#define ROUTE_MAXEDGES 1024
-
-struct RouteGeom {
-    int ndim;
-    int periodic;
-    int nranks;
-    int ndomains;
-    int shape[3];
-    int dstride[3];
-    double scale[3];
-    double smoothing[3];
-    const double *edges[3];      // device
-    int nedges[3];
-    const int32_t *assign;       // device [ndomains]
-    const int16_t *degenerate;   // device [ndomains]
-    int all_trivial;             // every axis is a single periodic domain: the mask is a constant
-    uint64_t const_mask;
-};
-
-// numpy floored modulo for doubles (npy_divmod): result has the sign of b, may round up to b itself
-// (-1e-17 % 64.0 == 64.0); ref use: pmesh/domain.py:616-619
-__device__ __forceinline__ double pmb_pymod(double a, double b)
-{
-    double m = fmod(a, b);
-    if (m != 0.0) {
-        if ((b < 0) != (m < 0)) m += b;
-    } else {
-        m = copysign(0.0, b);
-    }
-    return m;
-}
-
-// numpy.digitize(x, bins, right=False) for increasing bins: number of bins <= x (len(bins) for NaN)
-__device__ __forceinline__ int pmb_digitize(double x, const double *bins, int n)
-{
-    if (x != x) return n;
-    int lo = 0, hi = n;            // first index with bins[idx] > x
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (bins[mid] <= x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// python non-negative integer modulo
-__device__ __forceinline__ int pmb_imod(int a, int n)
-{
-    int m = a % n;
-    return m < 0 ? m + n : m;
-}
-
-// c = x % box with numpy semantics; for 0 <= x < box fmod(x, box) == x exactly, so the (slow,
-// iterative) fmod is only taken by out-of-box coordinates.  -0.0 maps to +0.0 like npy_divmod.
-__device__ __forceinline__ double pmb_pymod_fast(double a, double b)
-{
-    if (a >= 0.0 && a < b) return a + 0.0;
-    return pmb_pymod(a, b);
-}
-
-// per-particle rank mask; ref: pmesh/domain.py:609-630 (sil/sir) + pmesh/_domain.pyx:62-100 (patch walk)
-// NDIM is a compile-time constant so that sil / sir / the patch odometer live in registers; `edges`
-// point into shared memory (the binary searches of digitize never leave the SM).
-template <int NDIM>
-__device__ __forceinline__ uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, const void *pos,
-                                                   int elsize, int64_t ps0, int64_t ps1, int64_t i)
-{
-    int sil[NDIM], sir[NDIM];
-#pragma unroll
-    for (int d = 0; d < NDIM; d++) {
-        if (g.periodic && g.shape[d] == 1) {
-            // one periodic domain on this axis: sil = p - 1, sir = p, and the single patch cell wraps
-            // to domain 0 whatever the coordinate is (also for NaN: digitize gives len(edges))
-            sil[d] = 0; sir[d] = 1;
-            continue;
-        }
-        const double x = g.scale[d] * pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize);
-        const double sm = g.smoothing[d];
-        const double *e = edges[d];
-        const int ne = g.nedges[d];
-        int l, r;
-        if (g.periodic) {
-            const double box = e[ne - 1];
-            const double c = pmb_pymod_fast(x, box);
-            l = pmb_digitize(pmb_pymod_fast(c - sm, box), e, ne);
-            r = pmb_digitize(pmb_pymod_fast(c + sm, box), e, ne);
-            const int p = pmb_digitize(c, e, ne);
-            l = p - pmb_imod(p - l, g.shape[d]) - 1;
-            r = p + pmb_imod(r - p, g.shape[d]);
-        } else {
-            l = pmb_digitize(x - sm, e, ne);
-            r = pmb_digitize(x + sm, e, ne);
-            l = l - 1;
-            l = l < 0 ? 0 : (l > g.shape[d] ? g.shape[d] : l);
-            r = r < 0 ? 0 : (r > g.shape[d] ? g.shape[d] : r);
-        }
-        sil[d] = (int) (int16_t) l;     // the reference stores sil/sir as int16 (domain.py:603-604)
-        sir[d] = (int) (int16_t) r;
-    }
-    long long patch = 1;
-    int p[NDIM];
-#pragma unroll
-    for (int d = 0; d < NDIM; d++) { patch *= (sir[d] - sil[d]); p[d] = sil[d]; }
-    uint64_t mask = 0;
-    for (long long q = 0; q < patch; q++) {
-        int target = 0;
-#pragma unroll
-        for (int d = 0; d < NDIM; d++) {
-            int t = p[d];
-            if (g.periodic) {      // sil >= -shape - 1 and sir <= 2 shape: a few conditional steps, no division
-                const int n = g.shape[d];
-                if (t >= n) { t -= n; if (t >= n) t = pmb_imod(t, n); }
-                else if (t < 0) { t += n; if (t < 0) t = pmb_imod(t, n); }
-            }
-            target += t * g.dstride[d];
-        }
-        if (target >= 0 && target < g.ndomains) {
-            const int rank = g.assign[target];
-            // quirk kept: the degenerate flag is looked up by RANK, not by domain (_domain.pyx:81-83)
-            const int deg = (rank >= 0 && rank < g.ndomains) ? g.degenerate[rank] : 0;
-            if (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) mask |= (uint64_t) 1 << rank;
-        }
-        p[NDIM - 1] += 1;
-#pragma unroll
-        for (int d = NDIM - 1; d > 0; d--) {
-            if (p[d] == sir[d]) { p[d] = sil[d]; p[d - 1] += 1; }
-        }
-    }
-    return mask;
-}
+#include "pmb_route.h"
 
 // WARP w owns the contiguous particles [w*per_unit, (w+1)*per_unit): no block-level synchronisation
 // anywhere.  Lane r (and r + 32) of a warp keeps the count / cursor of rank r in a register.

@@ -253,3 +253,48 @@ extern "C" int hh_whitenoise(void *canvas, int elsize, const int64_t *nmesh, con
         }
     return 0;
 }
+
+// ---- routing: the rank-mask arithmetic of pmb_domain.cu, walked serially on the host ----------------
+#include "../../pmesh_b200/csrc/pmb_route.h"
+
+// counts[nranks] and indices (grouped by rank ascending, particle ascending; capacity `cap`) of
+// GridND.decompose for host arrays; returns the number of indices written or -1
+extern "C" int64_t hh_decompose(const void *pos, int pos_elsize, int64_t npart, int64_t ps0, int64_t ps1, int ndim,
+                                const double *scale, const double *smoothing, const double *edges, const int *nedges,
+                                int periodic, const int32_t *assign, const int16_t *degenerate, int nranks,
+                                int32_t *counts, int32_t *indices, int64_t cap)
+{
+    if (ndim < 1 || ndim > 3 || nranks < 1 || nranks > ROUTE_MAXRANKS) return -1;
+    RouteGeom g;
+    memset(&g, 0, sizeof(g));
+    g.ndim = ndim; g.periodic = periodic; g.nranks = nranks;
+    int nd = 1, o = 0;
+    const double *e[3] = {NULL, NULL, NULL};
+    for (int d = 0; d < ndim; d++) {
+        g.shape[d] = nedges[d] - 1; g.nedges[d] = nedges[d];
+        g.scale[d] = scale[d]; g.smoothing[d] = smoothing[d];
+        e[d] = edges + o; g.edges[d] = e[d]; o += nedges[d];
+        nd *= g.shape[d];
+    }
+    g.ndomains = nd;
+    int st = 1;
+    for (int d = ndim - 1; d >= 0; d--) { g.dstride[d] = st; st *= g.shape[d]; }
+    g.assign = assign; g.degenerate = degenerate;
+    std::vector<uint64_t> masks((size_t) npart);
+    for (int64_t i = 0; i < npart; i++) {
+        if (ndim == 1) masks[i] = pmb_route_mask<1>(g, e, pos, pos_elsize, ps0, ps1, i);
+        else if (ndim == 2) masks[i] = pmb_route_mask<2>(g, e, pos, pos_elsize, ps0, ps1, i);
+        else masks[i] = pmb_route_mask<3>(g, e, pos, pos_elsize, ps0, ps1, i);
+    }
+    int64_t n = 0;
+    for (int r = 0; r < nranks; r++) {
+        counts[r] = 0;
+        for (int64_t i = 0; i < npart; i++)
+            if ((masks[i] >> r) & 1) {
+                if (n >= cap) return -1;
+                indices[n++] = (int32_t) i;
+                counts[r]++;
+            }
+    }
+    return n;
+}

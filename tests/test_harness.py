@@ -116,3 +116,80 @@ def test_pcs_gradient_scale_quirk(harness, oracle):
         _paint(harness, "pcs", -1, c, pos, diffdir=d, scale=scale, period=period, mode=1, pcsfix=1)
         assert_allclose(a * scale[d], b, rtol=1e-12, atol=1e-13)
         assert_allclose(c, b, rtol=1e-12, atol=1e-13)
+
+
+# ------------------------------------------------------------------ routing arithmetic (pmb_route.h)
+def _hh_decompose(h, pos, edges, P, smoothing, periodic=True, assign=None, scale=None):
+    nd = len(edges)
+    pos = numpy.ascontiguousarray(pos)
+    sm = numpy.empty(nd); sm[:] = smoothing
+    sc = numpy.ones(nd) if scale is None else numpy.asarray(scale, dtype="f8")[:nd].copy()
+    e = numpy.ascontiguousarray(numpy.concatenate([numpy.asarray(x, dtype="f8") for x in edges]))
+    ne = numpy.array([len(x) for x in edges], dtype="int32")
+    shape = [len(x) - 1 for x in edges]
+    ndom = int(numpy.prod(shape))
+    if assign is None:
+        if P >= ndom:
+            assign = numpy.arange(ndom, dtype="int32")
+        else:
+            assign = numpy.empty(ndom, dtype="int32")
+            for i in range(P):
+                assign[i * ndom // P:(i + 1) * ndom // P] = i
+    assign = numpy.ascontiguousarray(assign, dtype="int32")
+    dd = numpy.zeros(shape, dtype="int16")
+    for i, edge in enumerate(edges):
+        edge = numpy.asarray(edge)
+        d1 = (edge[1:] == edge[:-1]).reshape([-1 if ii == i else 1 for ii in range(nd)])
+        dd[...] |= d1
+    deg = numpy.ascontiguousarray(dd.ravel())
+    cap = len(pos) * max(P, 1) + 1
+    counts = numpy.zeros(P, dtype="int32")
+    indices = numpy.zeros(cap, dtype="int32")
+    h.hh_decompose.restype = ctypes.c_int64
+    n = h.hh_decompose(ctypes.c_void_p(pos.ctypes.data), ctypes.c_int(pos.dtype.itemsize), ctypes.c_int64(len(pos)),
+                       ctypes.c_int64(pos.strides[0]), ctypes.c_int64(pos.strides[1]), ctypes.c_int(nd),
+                       ctypes.c_void_p(sc.ctypes.data), ctypes.c_void_p(sm.ctypes.data), ctypes.c_void_p(e.ctypes.data),
+                       ctypes.c_void_p(ne.ctypes.data), ctypes.c_int(int(bool(periodic))),
+                       ctypes.c_void_p(assign.ctypes.data), ctypes.c_void_p(deg.ctypes.data), ctypes.c_int(P),
+                       ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(indices.ctypes.data), ctypes.c_int64(cap))
+    assert n >= 0
+    return counts, indices[:n]
+
+
+def test_routing_arithmetic_bit_exact(harness, oracle):
+    """the rank-set arithmetic the count kernel executes (pmb_route.h, host build) == the oracle ==
+    the reference's golden counts / indices, for every golden geometry and for fresh random ones"""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden as G
+    z = numpy.load(os.path.join(here, "golden", "domain_golden.npz"))
+    for case, (edges, P, smoothing, periodic) in enumerate(G.DOMAIN_CASES):
+        pos = G.domain_inputs(case)
+        for rank in (0, P - 1):
+            assign = z["assign_%d_%d" % (case, rank)]
+            counts, indices = _hh_decompose(harness, pos, edges, P, smoothing, periodic, assign)
+            assert_array_equal(counts, z["counts_%d_%d" % (case, rank)])
+            assert_array_equal(indices, z["indices_%d_%d" % (case, rank)])
+    rng = numpy.random.default_rng(77)
+    for trial in range(20):
+        nd = int(rng.integers(1, 4))
+        shape = [int(rng.integers(1, 5)) for d in range(nd)]
+        box = rng.uniform(4, 64, nd)
+        edges = [numpy.concatenate([[0.0], numpy.sort(rng.uniform(0, b, s - 1)), [b]]) for s, b in zip(shape, box)]
+        P = int(rng.integers(1, 9))
+        periodic = bool(trial % 4)
+        smoothing = rng.uniform(0, 3, nd)
+        scale = rng.uniform(0.5, 2.0, nd) if trial % 3 == 0 else None
+        pos = rng.uniform(-0.7, 1.7, (3000, nd)) * box
+        pos[:30] = 0.0
+        pos[30:40] = -1e-17
+        pos[40:50] = box
+        if scale is not None:
+            pos = pos / scale
+        pos = pos.astype("f4" if trial % 5 == 1 else "f8")
+        want_c, want_i = oracle.decompose(pos, edges, P, smoothing=smoothing, periodic=periodic, scale=scale)
+        got_c, got_i = _hh_decompose(harness, pos, edges, P, smoothing, periodic, scale=scale)
+        assert_array_equal(got_c, want_c, err_msg="trial %d" % trial)
+        assert_array_equal(got_i, want_i, err_msg="trial %d" % trial)
