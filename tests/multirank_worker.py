@@ -100,6 +100,20 @@ def main():
             assert abs(wn.value - wn_full[:, s1:s1 + m1, :]).max() < (1e-13 if dtype == "f8" else 5e-7)
 
         # 5. gather modes on real ghosts (tests/test_domain.py:229-266 semantics)
+        # vector weights: 'sum' of a 3-column array on the device == bincount over the returned ghosts
+        # what I hold after an exchange of per-ghost values is arbitrary data of length recvlength:
+        mine = numpy.random.default_rng(400 + r).uniform(-1, 1, (int(layout.recvlength), 3))
+        held = comm.allgather(mine)
+        # the ghosts of MY particles that rank q holds sit at its recv segment for source r
+        back = []
+        for q in range(P):
+            rc_q = numpy.array([lays[src][0][q] for src in range(P)])
+            off = int(rc_q[:r].sum())
+            back.append(held[q][off:off + int(rc_q[r])])
+        want3 = oracle.bincount_sum(lays[r][1], numpy.concatenate(back), len(allpos[r]))
+        got3 = layout.gather(mine, mode="sum")
+        assert numpy.array_equal(got3, want3), "device ghost sum of vector weights differs from bincount"
+        assert numpy.array_equal(layout.gather(DeviceArray.from_host(mine), mode="sum").to_host(), want3)
         ones = numpy.ones(layout.recvlength)
         nghost = layout.gather(ones, mode="sum")
         assert nghost.min() >= 1 and abs(nghost.sum() - lays[r][0].sum()) < 1e-9
