@@ -400,124 +400,27 @@ class Field(NDArrayLike):
         warnings.warn("Use pm.unravel instead of unsort", DeprecationWarning, stacklevel=2)
         return self.unravel(flatiter)
 
-    def _c_order_is_local(self):
-        """True when the global C-order ravel of the field, cut into pieces of the local sizes, is just
-        every rank's own values in local C order: one rank, or a field distributed along axis 0 only
-        (the real-space slabs of this engine).  The reference sorts with mpsort in general
-        (pm.py:418-420); here the only layout that would need the exchange is the transposed complex
-        field on P > 1 ranks."""
-        return self.pm.comm.size == 1 or isinstance(self, RealField)
-
+    # the field resampling / I/O-order operations are compositions of the hot-path operators and live
+    # in pmesh_b200/resample.py
     def ravel(self, out=None):
-        """ Ravel the field to 'C'-order, partitioned by ranks (reference pm.py:389-424).
-
-            out : numpy.flatiter / array (its .flat is used), or Ellipsis for in place
-        """
-        if out is None:
-            out = numpy.empty_like(self.value)
-        if is_inplace(out):
-            out = self.value
-        if not isinstance(out, numpy.flatiter):
-            out = out.flat
-        assert isinstance(out, numpy.flatiter)
-        assert len(out) == self.size
-        if not self._c_order_is_local():
-            raise NotImplementedError("ravel of a transposed complex field on more than one rank needs "
-                                      "the distributed sort (mpsort); not built")
-        out[...] = numpy.array(self.value.flat)
-        return out
+        """ Ravel the field to 'C'-order, partitioned by ranks (reference pm.py:389-424). """
+        from . import resample as _rs
+        return _rs.ravel(self, out)
 
     def unravel(self, flatiter):
-        """ Unsort c-ordered field values to the field (reference pm.py:426-448); self is updated. """
-        if not isinstance(flatiter, numpy.flatiter):
-            flatiter = flatiter.flat
-        assert isinstance(flatiter, numpy.flatiter)
-        assert self.pm.comm.allreduce(len(flatiter)) == self.csize
-        if not self._c_order_is_local():
-            raise NotImplementedError("unravel of a transposed complex field on more than one rank needs "
-                                      "the distributed sort (mpsort); not built")
-        v = numpy.array(flatiter)
-        self.value.flat[...] = v
+        """ Unsort c-ordered field values to the field; self is updated (reference pm.py:426-448). """
+        from . import resample as _rs
+        return _rs.unravel(self, flatiter)
 
     def resample(self, out):
-        """ Resample the Field by filling 0 or truncating modes; converts between Real / Complex
-            automatically (reference pm.py:479-547).  ``out`` lives on another ParticleMesh. """
-        assert isinstance(out, Field)
-        if all(out.Nmesh == self.Nmesh):
-            # no resampling needed. Just do Fourier transforms.
-            self.cast(type=_gettype(out), out=out)
-        if self.pm.comm.size > 1:
-            raise NotImplementedError("Fourier-space resample on more than one rank needs the distributed "
-                                      "take (mpsort); not built")
-        src = self.cast(type=TransposedComplexField)
-        dest = out.pm.create(type=TransposedComplexField, base=out._base, value=0)
-        sv = src.value
-        dv = numpy.zeros(dest.shape, dtype=dest.dtype)
-        # per axis: the index in the source mesh of the mode each destination index stands for, -1 if
-        # the source does not carry it (reindex, pm.py:1128-1144)
-        tables = [reindex(src.Nmesh[d], dest.Nmesh[d]) for d in range(self.ndim)]
-        tables = [t[numpy.r_[sl]] for t, sl in zip(tables, dest.slices)]
-        good = numpy.ones(dest.shape, dtype='?')
-        idx = []
-        for d, t in enumerate(tables):
-            shp = [-1 if dd == d else 1 for dd in range(self.ndim)]
-            inside = (t >= 0) & (t < src.cshape[d])
-            good &= inside.reshape(shp)
-            idx.append(numpy.where(inside, t, 0).reshape(shp))
-        dv[good] = sv[tuple(numpy.broadcast_arrays(*idx))][good]
-        # keep the result the transform of a real field, and drop the Nyquist planes of both meshes
-        # (pm.py:520-542)
-        i = dest.i
-        selfconj = functools.reduce(numpy.bitwise_and, [(n - ii) % n == ii for ii, n in zip(i, dest.Nmesh)])
-        dv.imag[numpy.broadcast_to(selfconj, dest.shape)] = 0
-        for mesh in (dest.Nmesh, src.Nmesh):
-            nyq = functools.reduce(numpy.bitwise_or, [ii == n // 2 for ii, n in zip(i, mesh)])
-            dv[numpy.broadcast_to(nyq, dest.shape)] = 0
-        dest.value = dv
-        if isinstance(out, RealField):
-            dest.c2r(out)
-        elif out is not dest:
-            out.value = dest.value
-        return out
+        """ Resample by filling 0 or truncating Fourier modes, onto the mesh of ``out`` (reference pm.py:479-547). """
+        from . import resample as _rs
+        return _rs.fourier_resample(self, out)
 
     def preview(self, Nmesh=None, axes=None, resampler=None, method=None):
-        """ gathers the mesh into a numpy array on every rank, optionally at reduced resolution and
-            summed over the axes not listed (reference pm.py:549-615). """
-        if axes is None:
-            axes = range(self.ndim)
-        if not hasattr(axes, '__iter__'):
-            axes = (axes,)
-        else:
-            axes = list(axes)
-        field = self
-        if isinstance(field, BaseComplexField):
-            field = field.c2r()
-        if Nmesh is not None:
-            if all(Nmesh == field.Nmesh):
-                Nmesh = None
-        if Nmesh is not None:
-            pm = field.pm.reshape(Nmesh)
-            if method is None:
-                method = 'downsample' if any(pm.Nmesh < field.Nmesh) else 'upsample'
-            if method == 'downsample':
-                res = pm.downsample(field, resampler=resampler, keep_mean=True)
-            elif method == 'upsample':
-                res = pm.upsample(field, resampler=resampler, keep_mean=True)
-            else:
-                raise ValueError("method can only be downsample or upsample")
-        else:
-            res = field
-        result = numpy.zeros([res.cshape[i] for i in axes], dtype=res.dtype)
-        local_slice = tuple([res.slices[i] for i in axes])
-        local = res[...]
-        if len(axes) != field.ndim:
-            dropped = [d for d in range(field.ndim) if d not in axes]
-            order = list(axes) + dropped
-            tail = tuple(range(len(axes), len(order)))
-            result[local_slice] += local.transpose(order).sum(axis=tail)
-        else:
-            result[local_slice] += local.transpose(list(axes))
-        return field.pm.comm.Allreduce_inplace(result)
+        """ the mesh as a numpy array on every rank, optionally resampled / projected (reference pm.py:549-615). """
+        from . import resample as _rs
+        return _rs.preview(self, Nmesh, axes, resampler, method)
 
     def cast(self, type=None, out=None):
         """ cast the field object to the given type, maintaining the meaning of the field: real <->
@@ -610,18 +513,9 @@ class RealField(Field):
         return out
 
     def ctranspose(self, axes):
-        """ Collectively transpose a RealField: the coordinates are permuted according to ``axes``, on
-            a new ParticleMesh with permuted BoxSize and Nmesh (reference pm.py:696-723; like there,
-            done with a nearest-point readout and paint). """
-        assert len(numpy.unique(axes)) == self.ndim
-        assert numpy.max(axes) == self.ndim - 1
-        axes = numpy.array(axes, dtype='intp')
-        pm = self.pm.reshape(BoxSize=self.BoxSize[axes], Nmesh=self.Nmesh[axes])
-        q = self.pm.generate_uniform_particle_grid(shift=0)
-        v = self.readout(q, resampler='nnb')
-        q = q[..., axes]
-        layout = pm.decompose(q, smoothing='nnb')
-        return pm.paint(q, mass=v, resampler='nnb', layout=layout)
+        """ Collectively transpose a RealField onto a ParticleMesh with permuted axes (reference pm.py:696-723). """
+        from . import resample as _rs
+        return _rs.ctranspose(self, axes)
 
     def csum(self, dtype=None):
         """ Collective sum of the entire mesh (reference pm.py:725-739). """
@@ -840,13 +734,9 @@ ComplexField = TransposedComplexField
 
 
 def reindex(Nsrc, Ndest):
-    """ for every index of a length-Ndest frequency axis, the index of the same frequency on a
-        length-Nsrc axis, -1 where the source does not carry it (reference pm.py:1128-1144):
-        reindex(8, 4) -> [0, 1, 2, 7];  reindex(4, 8) -> [0, 1, 2, -1, -1, -1, -1, 3] """
-    r = numpy.arange(Ndest)
-    r[Ndest // 2 + 1:] = numpy.arange(Nsrc - Ndest // 2 + 1, Nsrc, 1)
-    r[Nsrc // 2 + 1: Ndest - Nsrc // 2 + 1] = -1
-    return r
+    """ index table between frequency axes of different lengths (reference pm.py:1128-1144) """
+    from .resample import mode_table
+    return mode_table(Nsrc, Ndest)
 
 
 def exchange(layout, value):
@@ -1238,31 +1128,10 @@ class ParticleMesh(object):
     def upsample(self, source, resampler=None, keep_mean=False):
         """ Resample an image by reading the source out at the pixel positions of this pm
             (reference pm.py:1937-1989).  keep_mean: conserve the mean rather than the total mass. """
-        assert isinstance(source, RealField)
-        q = self.mesh_coordinates(dtype=self.dtype)
-        # my mesh -> the source's (local) mesh
-        transform = Affine(self.ndim,
-                           translate=-source.start,
-                           scale=1.0 * source.Nmesh / self.Nmesh,
-                           period=source.Nmesh)
-        # the reference builds the layout twice; the second, with its fixed 1.6 cells of smoothing,
-        # is the one used (pm.py:1971-1972, SURVEY quirk Q9)
-        layout = source.pm.decompose(q, smoothing=1.6, transform=transform)
-        f = source.readout(q, resampler=resampler, layout=layout, transform=transform)
-        if not keep_mean:
-            f *= (source.pm.Nmesh.prod() / source.pm.BoxSize.prod()) / (self.Nmesh.prod() / self.BoxSize.prod())
-        # all are on the grid: nearest-point paint, no need to decompose
-        return self.paint(q, mass=f, resampler='nnb', transform=self.affine_grid)
+        from . import resample as _rs
+        return _rs.upsample(self, source, resampler, keep_mean)
 
     def downsample(self, source, resampler=None, keep_mean=False):
-        """ Resample an image by painting the pixels of the source onto this pm
-            (reference pm.py:1991-2027). """
-        assert isinstance(source, RealField)
-        q = source.pm.mesh_coordinates(dtype=self.dtype)
-        f = source.readout(q, resampler='nnb', transform=source.pm.affine_grid)
-        # the source's mesh -> my mesh
-        transform = self.affine_grid.rescale(1.0 * self.Nmesh / source.Nmesh)
-        if keep_mean:
-            f /= (source.pm.Nmesh.prod() / source.pm.BoxSize.prod()) / (self.Nmesh.prod() / self.BoxSize.prod())
-        layout = self.decompose(q, smoothing=resampler, transform=transform)
-        return self.paint(q, mass=f, layout=layout, resampler=resampler, transform=transform)
+        """ Resample an image by painting the pixels of the source onto this pm (reference pm.py:1991-2027). """
+        from . import resample as _rs
+        return _rs.downsample(self, source, resampler, keep_mean)
