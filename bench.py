@@ -305,7 +305,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(ms_step, 3), "unit": "ms", "n_gpus": comm.size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f8" if args.dtype == "f8" else "f4", "data": "synthetic",
+            "dtype": "f64" if args.dtype == "f8" else "f32", "data": "synthetic",
             "config": {"workload": "CIC PM force step, %d^3 %s particles on a %d^3 mesh (BASELINE configs[2] shape)%s"
                                    % (M, args.particles, M, "" if comm.size > 1 else ", single GPU"),
                        "nmesh": M, "nparticles": ntot, "window": args.window, "paint_mode": args.paint_mode,
@@ -444,7 +444,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "ms", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["value"], "higher_is_better": False,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f8", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "CIC PM force step, %d^3 zeldovich particles on a %d^3 mesh (BASELINE configs[2] shape)" % (M, M),
                    "nmesh": M, "nparticles": M ** 3, "window": args.window},
         "cpu_baseline": r,
