@@ -108,6 +108,16 @@ class _Base(object):
     Stands in for pfft.LocalBuffer (reference pm.py:226)."""
     def __init__(self, pm):
         self.dev = DeviceArray.zeros((pm._alloc_elems,), pm.dtype)
+        # State of the MEMORY, shared by every Field that views it (a real field and its in-place
+        # complex partner, or two handles on the same base):
+        # pending -- a scalar factor not yet multiplied into the device values (value == pending *
+        #   memory).  scale() and the 1/prod(Nmesh) of r2c only update it; the linear consumers that
+        #   multiply anyway (r2c, c2r, the transfer kernels) fold it in, everything else multiplies
+        #   it in first;
+        # version -- bumped by every write to the device values, so that a view can tell that its host
+        #   mirror is older than the memory even if another view did the writing.
+        self.pending = 1.0
+        self.version = 0
 
     def __contains__(self, other):
         return other is self
@@ -195,11 +205,8 @@ class Field(NDArrayLike):
         # host mirror (lazily allocated); a fresh field is all zeros on the device
         self._host_arr = None
         self._host_valid = False
+        self._host_version = -1
         self._dev_valid = True
-        # a scalar factor not yet multiplied into the device values (value == _pending * memory).
-        # scale() and the 1/prod(Nmesh) of r2c only update it; the linear consumers that multiply
-        # anyway (r2c, c2r, the transfer kernels) fold it in, everything else materialises it first.
-        self._pending = 1.0
 
         self.x = pm.create_coords(type(self), return_indices=False)
         self.i = pm.create_coords(type(self), return_indices=True)
@@ -211,6 +218,14 @@ class Field(NDArrayLike):
     @property
     def dtype(self):
         return self._dtype
+
+    @property
+    def _pending(self):
+        return self._base.pending
+
+    @_pending.setter
+    def _pending(self, v):
+        self._base.pending = float(v)
 
     @property
     def _host(self):
@@ -231,10 +246,12 @@ class Field(NDArrayLike):
             _lib.check(ctx.lib.pmb_field_scale(ctx.handle, self._dev.ptr, es, 0, 1, n, st, float(factor)))
 
     def _sync_host(self):
-        if not self._host_valid:
+        # the device copy is authoritative unless this view handed its host array out (_dev_valid False)
+        if self._dev_valid and (not self._host_valid or self._host_version != self._base.version):
             self._materialize()
             self._host[...] = self._dev.to_host()
             self._host_valid = True
+            self._host_version = self._base.version
 
     @property
     def value(self):
@@ -249,7 +266,6 @@ class Field(NDArrayLike):
         self._host[...] = v
         self._host_valid = True
         self._dev_valid = False
-        self._pending = 1.0
 
     def readonly_value(self):
         """host copy of the values without invalidating the device copy"""
@@ -263,13 +279,16 @@ class Field(NDArrayLike):
         absorb=True: the caller folds ``self._pending`` into its own arithmetic; otherwise the pending
         factor is multiplied in first."""
         if not self._dev_valid:
-            assert self._pending == 1.0
             h = self._host
             if self.size:
                 extent = sum((n - 1) * s for n, s in zip(self.shape, self._layout_strides)) + self._dtype.itemsize
                 hull = numpy.zeros(extent, dtype='u1')
                 numpy.ndarray(self.shape, self._dtype, buffer=hull, strides=self._layout_strides)[...] = h
                 self.pm.ctx.h2d(self._dev.ptr, hull, extent)
+            # the memory now holds exactly the host values
+            self._base.pending = 1.0
+            self._base.version += 1
+            self._host_version = self._base.version
             self._dev_valid = True
         if not absorb:
             self._materialize()
@@ -278,7 +297,8 @@ class Field(NDArrayLike):
     def _mark_device_written(self, pending=1.0):
         self._dev_valid = True
         self._host_valid = False
-        self._pending = float(pending)
+        self._base.pending = float(pending)
+        self._base.version += 1
 
     @property
     def flat(self):

@@ -57,7 +57,7 @@ def test_operators(PM):
     real = real * real.value
     real = real * real
     assert isinstance(real, PM.RealField)
-    assert_array_equal(real.value, 16.0)
+    assert_array_equal(real.value, 256.0)
     complex = 1 + complex
     assert isinstance(complex, PM.ComplexField)
     complex = complex + 1
