@@ -68,3 +68,28 @@ def test_no_silent_fallback_without_gpu():
     from pmesh_b200 import window
     with pytest.raises(_lib.PmbError):
         window.CIC.paint(numpy.zeros((4, 4)), [[1.0, 1.0]])
+
+
+def test_header_is_plain_c_and_cites_the_reference():
+    """include/pmesh_b200.h compiles as C99 (no C++, no CUDA, no torch types in the boundary) and every
+    entry point group cites the reference interface it replaces (file:line)"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "pmesh_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    txt = open(hdr).read()
+    code = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    assert "torch" not in code.lower() and "tensor" not in code.lower()
+    for cite in ("pmesh/_window.pyx:", "pmesh/_window_imp.h:", "pmesh/domain.py:", "pmesh/_domain.pyx:", "pmesh/pm.py:",
+                 "examples/nbody.py:", "pmesh/_whitenoise.pyx:"):
+        assert cite in txt, cite
+
+
+def test_every_exported_entry_point_is_declared():
+    """the other direction: no pmb_* function is exported that the header does not declare"""
+    import subprocess
+    so = os.path.join(ROOT, "pmesh_b200", "csrc", "libpmesh_b200.so")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    exported = sorted(set(l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("pmb_")))
+    internal = {"pmb_set_error", "pmb_cuda_fail", "pmb_scratch", "pmb_resolve_window", "pmb_stream_barrier", "pmb_allgather_host"}
+    undeclared = [n for n in exported if n not in declared_symbols() and n not in internal]
+    assert not undeclared, undeclared
