@@ -7,10 +7,13 @@ Parity status: PINNED.  ``tests/test_oracle.py`` checks every function here
 against (a) the reference's own compiled C/Cython (``oracle/_ref``, built by
 ``oracle/build_ref.py`` from ``/root/reference``), bit for bit, and (b) the
 known-answer vectors of the reference's test-suite (``pmesh/tests/test_window.py``,
-``test_domain.py``) restated in ``tests/golden``.  The FFT legs have no golden
-values in the reference: they are defined by
-``numpy.fft.rfftn(x)/N`` and ``irfftn(y)*N`` -- "parity unpinned by the
-reference" for FFT values, pinned for normalisation and layout conventions.
+``test_domain.py``) restated in ``tests/golden``, and (c) whole-pipeline
+vectors computed by the reference's own ``pmesh/pm.py`` running on single-rank
+stand-ins for pfft / mpsort / mpi4py (``tests/golden/reference_pm.py``,
+``tests/test_reference_pipeline.py``): force step, k grids, white noise -> LPT,
+vjp / jvp.  Only the FFT arithmetic itself is "parity unpinned by the
+reference" (PFFT cannot be built here): ``numpy.fft.rfftn(x)/N`` and
+``irfftn(y)*N`` stand in for it on both sides.
 
 Layers
 ------

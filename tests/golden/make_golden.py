@@ -179,5 +179,117 @@ def main():
     print("domain_golden.npz:", len(out), "arrays")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--pipeline" not in sys.argv:
     main()
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-pipeline vectors from the reference's own pmesh/pm.py (run on the stand-ins of
+# tests/golden/reference_pm.py: numpy.fft behind pfft's interface, one rank)
+PIPELINE_CASES = [
+    # (window, Nmesh, BoxSize, dtype, number of particles, seed)
+    ("cic", 8, 100.0, "f8", 300, 1),
+    ("tsc", 12, 64.0, "f8", 500, 2),
+    ("pcs", 8, 8.0, "f8", 300, 3),
+    ("cic", 8, 100.0, "f4", 300, 4),
+]
+VJP_CASES = [("pcs", 8, 10.0, 200, 11), ("lanczos3", 8, 10.0, 120, 12), ("cic", 6, 6.0, 150, 13)]
+
+
+def pipeline_inputs(case):
+    window, n, L, dt, npart, seed = case
+    rng = numpy.random.default_rng(500 + seed)
+    return rng.uniform(-0.2 * L, 1.2 * L, (npart, 3))
+
+
+def vjp_inputs(case):
+    window, n, L, npart, seed = case
+    rng = numpy.random.default_rng(600 + seed)
+    pos = rng.uniform(0, L, (npart, 3))
+    mass = rng.uniform(0.5, 2.0, npart)
+    field = rng.uniform(-1, 1, (n, n, n))
+    v = rng.uniform(-1, 1, npart)
+    return pos, mass, field, v
+
+
+def fd4_force_transfer(direction):
+    """the force kernel of examples/nbody.py:162-170 as a python callable for the reference's apply()"""
+    def filt(k, v):
+        k2 = sum(ki ** 2 for ki in k)
+        k2[k2 == 0] = 1.0
+        C = (v.BoxSize / v.Nmesh)[direction]
+        w = k[direction] * C
+        kfinite = 1.0 / C * 1 / 6.0 * (8 * numpy.sin(w) - numpy.sin(2 * w))
+        return 1j * kfinite / k2 * v
+    return filt
+
+
+def make_pipeline_golden():
+    sys.path.insert(0, HERE)
+    import reference_pm
+    ns = reference_pm.load()
+    assert ns is not None, "needs /root/reference"
+    passed, failed = reference_pm.selftest(verbose=False)
+    assert not failed, failed            # the stand-ins carry the reference's own test-suite
+    PM = ns.pm
+    out = {"selftest_passed": numpy.array(len(passed))}
+    for ci, case in enumerate(PIPELINE_CASES):
+        window, n, L, dt, npart, seed = case
+        pos = pipeline_inputs(case)
+        pm = PM.ParticleMesh(BoxSize=L, Nmesh=[n, n, n], dtype=dt, resampler=window)
+        layout = pm.decompose(pos, smoothing=1.0 * pm.resampler.support)
+        rho = pm.create("real")
+        rho.paint(pos, layout=layout, hold=False)
+        out["rho_%d" % ci] = numpy.array(rho.value)
+        rho[...] *= 1.0 * pm.Nmesh.prod() / len(pos)
+        rhok = rho.r2c()
+        out["rhok_%d" % ci] = numpy.array(rhok.value)
+        F = numpy.empty((len(pos), 3))
+        for d in range(3):
+            F[:, d] = rhok.apply(fd4_force_transfer(d)).c2r().readout(pos, layout=layout)
+        out["force_%d" % ci] = F
+    # coordinates of a non-cubic mesh (pm.py:1178-1226)
+    pm = PM.ParticleMesh(BoxSize=[8.0, 12.0, 5.0], Nmesh=[8, 6, 10], dtype="f8")
+    c, r = pm.create("complex"), pm.create("real")
+    for d in range(3):
+        out["kx_%d" % d] = numpy.array(c.x[d]).ravel()
+        out["rx_%d" % d] = numpy.array(r.x[d]).ravel()
+    # white noise -> linear field -> 1-LPT displacement (examples/nbody.py:245-270)
+    pm = PM.ParticleMesh(BoxSize=64.0, Nmesh=[16, 16, 16], dtype="f8", resampler="cic")
+    wn = pm.generate_whitenoise(120577, unitary=True)
+    out["wn_unitary"] = numpy.array(wn.value)
+    dlinear = wn.apply(lambda k, v: numpy.exp(-0.5 * sum(ki ** 2 for ki in k) * 4.0 ** 2) * v)
+    out["dlinear"] = numpy.array(dlinear.value)
+    Q = pm.generate_uniform_particle_grid(shift=0.0)
+    layout = pm.decompose(Q)
+    DX1 = numpy.zeros_like(Q)
+
+    def dx1(direction):
+        def filt(k, v):
+            k2 = sum(ki ** 2 for ki in k)
+            k2[k2 == 0] = 1.0
+            return 1j * k[direction] / k2 * v
+        return filt
+    for d in range(3):
+        DX1[:, d] = dlinear.apply(dx1(d)).c2r().readout(Q, layout=layout)
+    out["dx1"] = DX1
+    out["wn_real_mean2"] = numpy.array(pm.generate_whitenoise(7, type="real", mean=2.0).value)
+    # back-propagation operators (pm.py:793-859, 1872-1935), BASELINE configs[3] windows
+    for ci, case in enumerate(VJP_CASES):
+        window, n, L, npart, seed = case
+        pos, mass, field, v = vjp_inputs(case)
+        pm = PM.ParticleMesh(BoxSize=L, Nmesh=[n, n, n], dtype="f8", resampler=window)
+        vf = pm.create("real", value=2 * field)
+        gpos, gmass = pm.paint_vjp(vf, pos, mass=mass)
+        out["paint_vjp_pos_%d" % ci], out["paint_vjp_mass_%d" % ci] = gpos, gmass
+        f = pm.create("real", value=field)
+        gself, gpos = f.readout_vjp(pos, v=2 * v)
+        out["readout_vjp_self_%d" % ci], out["readout_vjp_pos_%d" % ci] = numpy.array(gself.value), gpos
+        out["paint_jvp_%d" % ci] = numpy.array(pm.paint_jvp(pos, mass=mass, v_pos=numpy.ones_like(pos) * [0.1, -0.2, 0.3], v_mass=v).value)
+        out["readout_jvp_%d" % ci] = f.readout_jvp(pos, v_self=vf, v_pos=numpy.ones_like(pos) * [0.1, -0.2, 0.3])
+    numpy.savez_compressed(os.path.join(HERE, "pipeline_golden.npz"), **out)
+    print("pipeline_golden.npz:", len(out), "arrays; reference tests passed on the stand-ins:", len(passed))
+
+
+if __name__ == "__main__" and "--pipeline" in sys.argv:
+    make_pipeline_golden()
