@@ -123,3 +123,18 @@ def test_backpropagation_operators(oracle, Z, ci):
         rj = rj + oracle.readout(field, pos, window, diffdir=d, **kw) * vpos[:, d]
     rj = rj + oracle.readout(vf, pos, window, **kw)
     assert_allclose(rj, Z["readout_jvp_%d" % ci], rtol=0, atol=1e-13 * abs(rj).max())
+
+
+def test_reference_suite_passes_on_the_standins():
+    """the stand-ins for pfft / mpsort / mpi4py are good enough to carry the reference's OWN tests
+    (test_pm.py, test_whitenoise.py, test_gradient.py minus c2c / process-mesh cases); only where
+    /root/reference exists (the build container)"""
+    import subprocess
+    if not os.path.isdir("/root/reference/pmesh"):
+        pytest.skip("no /root/reference on this machine")
+    p = subprocess.run([sys.executable, os.path.join(HERE, "golden", "reference_pm.py"), "--selftest"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd="/tmp")
+    tail = [l for l in p.stdout.splitlines() if "passed" in l and "failed" in l]
+    assert p.returncode == 0 and tail, p.stdout[-3000:]
+    passed, failed = int(tail[-1].split()[0]), int(tail[-1].split()[2])
+    assert failed == 0 and passed >= 48, tail[-1]
