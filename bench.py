@@ -26,7 +26,15 @@ import numpy
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "PM force step ms (1024^3 CIC: decompose, paint, r2c, gravity transfer, c2r x3, readout x3)"
+WINDOW_NAMES = {"cic": "CIC", "tsc": "TSC", "pcs": "PCS", "nnb": "NNB"}
+INPUTS = ("zeldovich", "uniform", "lattice")
+INPUT_LABEL = {"zeldovich": "zeldovich_gaussian", "uniform": "uniform_random", "lattice": "lattice_sine"}
+
+
+def metric_name(args):
+    """BASELINE.json's metric, spelled with the mesh and window actually run"""
+    return ("PM force step ms (%d^3 %s: decompose, paint, r2c, gravity transfer, c2r x3, readout x3)"
+            % (args.nmesh, WINDOW_NAMES.get(args.window, args.window)))
 
 
 def parse():
@@ -38,7 +46,13 @@ def parse():
     ap.add_argument("--nmesh", type=int, default=1024)
     ap.add_argument("--window", default="cic")
     ap.add_argument("--dtype", default="f8")
-    ap.add_argument("--particles", default="zeldovich", choices=["zeldovich", "uniform"])
+    ap.add_argument("--particles", default="zeldovich", choices=list(INPUTS),
+                    help="input of the timed force step: zeldovich = lattice displaced by a Gaussian random field "
+                         "(P(k) ~ k^-2, rms 3 cells; SURVEY cfg3), uniform = uniform random (no order at all), "
+                         "lattice = lattice displaced by one sine mode per axis (order fully preserved)")
+    ap.add_argument("--inputs", default="zeldovich,uniform,lattice",
+                    help="inputs for which paint / readout are timed alone (comma separated)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-size parity check against the oracle")
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -99,27 +113,59 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ ours
-def make_particles(pm, args, comm):
-    """device-resident positions of this rank: the rank's slab of the Nmesh^3 lattice (shift 0.5),
-    displaced by a smooth periodic field of ~3 cells rms ('zeldovich'), or uniform random."""
-    import ctypes
-    from pmesh_b200 import _lib
-    from pmesh_b200.device import DeviceArray
-    M = args.nmesh
-    ntot = M ** 3
-    per = (ntot + comm.size - 1) // comm.size
-    # whole lattice planes per rank so that particles start (mostly) inside their own slab
+def _slab_rows(M, comm):
+    """rows [first, first + n) of the C-order M^3 lattice owned by this rank: whole planes"""
     planes = (M + comm.size - 1) // comm.size
     first = min(comm.rank * planes, M) * M * M
     n = min((comm.rank + 1) * planes, M) * M * M - first
+    return first, n
+
+
+def make_particles(pm, args, comm, kind=None):
+    """device-resident positions of this rank (rank r starts with the particles of lattice slab r):
+
+    zeldovich : the lattice (shift 0.5) displaced by a Gaussian random displacement field generated with
+                the engine's own operators, the reference's 1-LPT recipe (examples/nbody.py:253-274):
+                white noise (seed 44) -> |k|^-1 (P(k) ~ k^-2) -> i k_d / k^2 -> c2r -> readout at the
+                lattice, normalised to rms |psi| = 3 cells; x = (q + psi) mod L.
+    uniform   : uniform random in the whole box (counter-based generator, seed 45): no order.
+    lattice   : the lattice displaced by one sine mode per axis, amplitude 3 cells: lattice order kept."""
+    import ctypes
+    from pmesh_b200 import _lib, comm as C
+    from pmesh_b200 import transfer as T
+    from pmesh_b200.device import DeviceArray
+    kind = kind or args.particles
+    M = args.nmesh
+    ntot = M ** 3
+    first, n = _slab_rows(M, comm)
     X = DeviceArray.empty((n, 3), "f8")
     ctx = X.ctx
     box = (ctypes.c_double * 3)(*[float(b) for b in pm.BoxSize])
-    if args.particles == "uniform":
+    nn = (ctypes.c_int64 * 3)(M, M, M)
+    if kind == "uniform":
         _lib.check(ctx.lib.pmb_particles_uniform(ctx.handle, X.ptr, 8, n, 3, box, 45, first))
-    else:
-        nn = (ctypes.c_int64 * 3)(M, M, M)
+    elif kind == "lattice":
         _lib.check(ctx.lib.pmb_particles_lattice(ctx.handle, X.ptr, 8, n, 3, nn, box, 0.5, 3.0, 44, first))
+    else:
+        _lib.check(ctx.lib.pmb_particles_lattice(ctx.handle, X.ptr, 8, n, 3, nn, box, 0.5, 0.0, 44, first))   # q
+        delta = pm.generate_whitenoise(44, type="complex")
+        delta = delta.apply(T.PowerLaw(-1.0), out=Ellipsis)
+        layout = pm.decompose(X)
+        lq = layout.exchange(X)
+        tmp = pm.create("complex")
+        psi = []
+        for d in range(3):
+            f = delta.apply(T.GradientK(d), out=tmp).c2r(out=Ellipsis)
+            psi.append(layout.gather(f.readout(lq)))
+            del f
+        del tmp, delta, lq, layout
+        sq = comm.allreduce(sum(p.dot(p) for p in psi), op=C.SUM)
+        cell = float(pm.BoxSize[0]) / M
+        fac = 3.0 * cell / max((sq / ntot) ** 0.5, 1e-300)
+        for d in range(3):
+            X.column(d).iadd_scaled(psi[d], fac)
+            X.column(d).imod(float(pm.BoxSize[d]))
+        del psi
     ctx.sync()
     return X, ntot
 
@@ -171,6 +217,132 @@ def _strided_sum(ctx, a):
     return out.value
 
 
+def kernel_names(args, nl):
+    """names of the paint / readout kernels the dispatch of pmb_resample.cu picks (for the roofline block)"""
+    big = nl >= (1 << 18)
+    if args.window == "cic" and big:
+        return {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32"}
+    if args.window in ("nnb", "cic", "tsc", "pcs"):
+        return {"paint": ("pmb_k_paint_carry32" if args.window in ("tsc", "pcs") else "pmb_k_paint_sched") if big else "pmb_k_paint_tuned",
+                "readout": "pmb_k_readout_sched" if big else "pmb_k_readout_tuned"}
+    return {"paint": "pmb_k_paint_dyn", "readout": "pmb_k_readout_dyn"}
+
+
+def time_paint_readout(pm, args, comm, X, peak, R=5):
+    """paint and readout alone on the local (exchanged) particles of input X: ms per launch from CUDA
+    events on the library's stream, algorithmic bytes and the roofline fractions"""
+    from pmesh_b200 import comm as C
+    from pmesh_b200.device import DeviceArray
+    ctx = pm.ctx
+    es = pm.dtype.itemsize
+    layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
+    lpos = layout.exchange(X)
+    nl = lpos.shape[0]
+    ncell_local = int(numpy.prod(pm._layout['i_shape']))
+    rho = pm.create("real")
+    for _ in range(2):
+        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+    ctx.timer_start(2)
+    for _ in range(R):
+        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+    t_paint = ctx.timer_stop(2) / R
+    out = DeviceArray.empty((nl,), "f8")
+    for _ in range(2):
+        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
+    ctx.timer_start(2)
+    for _ in range(R):
+        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
+    t_read = ctx.timer_stop(2) / R
+    ab_paint = nl * 24.0 + ncell_local * es          # pos (3 x f8) read + one mesh write pass
+    ab_read = nl * (24.0 + 8.0) + ncell_local * es   # pos read + f8 result write + one mesh read pass
+    nsum = comm.allreduce(nl, op=C.SUM)
+    tp, tr = comm.allreduce(t_paint, op=C.MAX), comm.allreduce(t_read, op=C.MAX)
+    row = {"paint_ms": round(tp, 4), "readout_ms": round(tr, 4),
+           "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),
+           "readout_frac": round(ab_read / (t_read * 1e-3) / 1e9 / peak, 4),
+           "paint_readout_gparticles_per_s": round(nsum / ((tp + tr) * 1e-3) / 1e9, 3),
+           "paint_readout_frac": round((ab_paint + ab_read) / ((t_paint + t_read) * 1e-3) / 1e9 / peak, 4),
+           "local_particles": int(nl)}
+    return row, (t_paint, ab_paint, t_read, ab_read, nl)
+
+
+def replica_parity(pm, args, comm, step):
+    """Parity of the WHOLE pipeline at the full benchmark size against the CPU oracle.
+
+    The benchmark-size problem is built as rep^3 periodic replicas of a small problem (ns^3 uniform
+    random particles on an ns^3 mesh, same cell size).  Density and force of the big problem are then
+    the periodic repetition of the small one's, which the CPU oracle (oracle/: the reference's paint /
+    readout arithmetic + numpy FFT) computes in seconds.  Coordinates are multiples of 2^-20 cells, so
+    the stencil weights of a replica and of its original are bit-identical; what differs is the order
+    of additions and the size of the FFT.  Returns relative errors (max over ranks):
+    paint: max |rho - rho_oracle| / max |rho_oracle| on a sub-block of every rank's slab;
+    force: max |F - F_oracle| / max |F_oracle| over ~1e5 sampled particles."""
+    import ctypes
+    from pmesh_b200 import _lib, comm as C
+    from pmesh_b200.device import DeviceArray
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    M = args.nmesh
+    ns = 128 if M % 128 == 0 and M >= 256 else (M // 2 if M % 2 == 0 else 0)
+    if ns < 8 or pm.BoxSize[0] != float(M):
+        return {"skipped": "mesh %d has no periodic sub-division" % M}
+    rep = M // ns
+    nblocks = rep ** 3
+    b_first = comm.rank * nblocks // comm.size
+    b_n = (comm.rank + 1) * nblocks // comm.size - b_first
+    nsm = ns ** 3
+    rng = numpy.random.default_rng(46)
+    xs = rng.integers(0, ns << 20, size=(nsm, 3)).astype("f8") / float(1 << 20)      # cell units = box units
+    ctx = pm.ctx
+    dxs = DeviceArray.from_host(xs)
+    X = DeviceArray.empty((b_n * nsm, 3), "f8")
+    nrep = (ctypes.c_int64 * 3)(rep, rep, rep)
+    per = (ctypes.c_double * 3)(float(ns), float(ns), float(ns))
+    _lib.check(ctx.lib.pmb_particles_replicate(ctx.handle, X.ptr, 8, dxs.ptr, nsm, 3, nrep, per, b_first, b_n))
+    del dxs
+    n = X.shape[0]
+    ntot = nblocks * nsm
+    F = [DeviceArray.empty((n,), "f8") for d in range(3)]
+    step(X, ntot, F)
+    # ---- oracle of the small problem ----
+    t0 = time.perf_counter()
+    rho_s = numpy.zeros((ns, ns, ns))
+    oracle.paint(rho_s, xs, args.window, scale=1.0, period=[ns] * 3)
+    ck = oracle.r2c(rho_s * (float(ns) ** 3 / nsm))
+    # ---- force of sampled particles ----
+    nsamp = max(1, min(n, 100000 // comm.size))
+    pick = numpy.sort(numpy.random.default_rng(47 + comm.rank).choice(n, size=nsamp, replace=False)).astype("i4") if n else numpy.zeros(0, "i4")
+    dpick = DeviceArray.from_host(pick)
+    ferr, fmax = 0.0, 0.0
+    for d in range(3):
+        fr = oracle.c2r(oracle.transfer(ck, [ns] * 3, [float(ns)] * 3, "gravity_fd4", d), [ns] * 3)
+        ref = oracle.readout(fr, xs[pick % nsm], args.window, scale=1.0, period=[ns] * 3)
+        got = DeviceArray.empty((len(pick),), "f8")
+        if len(pick):
+            _lib.check(ctx.lib.pmb_take(ctx.handle, F[d].ptr, 8, dpick.ptr, len(pick), got.ptr))
+            got = got.to_host()
+            ferr = max(ferr, float(abs(got - ref).max()))
+            fmax = max(fmax, float(abs(ref).max()))
+    ferr = comm.allreduce(ferr, op=C.MAX) / max(comm.allreduce(fmax, op=C.MAX), 1e-300)
+    # ---- density on a sub-block of this rank's slab ----
+    layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
+    lpos = layout.exchange(X)
+    rho = pm.paint(lpos, mode=args.paint_mode)
+    mesh = rho._device()
+    i0 = int(pm._layout['i_start'][0])
+    nb = min(32, int(mesh.shape[0]))
+    perr = 0.0
+    if nb > 0:
+        sub = DeviceArray((nb, ns, ns), mesh.dtype, ptr=mesh.ptr, strides=mesh.strides, base=mesh, ctx=ctx).to_host()
+        want = rho_s[(numpy.arange(nb) + i0) % ns]
+        perr = float(abs(sub - want).max() / abs(rho_s).max())
+    perr = comm.allreduce(perr, op=C.MAX)
+    return {"paint_rel_err": perr, "force_rel_err": ferr, "replicas": "%d^3 of a %d^3 problem" % (rep, ns),
+            "sampled_particles": int(comm.allreduce(len(pick), op=C.SUM)),
+            "oracle_seconds": round(time.perf_counter() - t0, 2)}
+
+
 def run_ours(args):
     from pmesh_b200 import _lib, comm as C
     from pmesh_b200.device import DeviceArray, PinnedArray
@@ -207,70 +379,54 @@ def run_ours(args):
     ms_step = comm.allreduce(ms / args.steps, op=C.MAX)
     fft_step = comm.allreduce(fft_ms / args.steps, op=C.MAX)
 
-    # ---- dominant kernels alone: paint and readout on the local particles (roofline) ----
-    peak, peak_src = peaks()
-    es = pm.dtype.itemsize
-    layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
-    lpos = layout.exchange(X)
-    nl = lpos.shape[0]
-    ncell_local = int(numpy.prod(pm._layout['i_shape']))
-    rho = pm.create("real")
-    R = 5
-    for _ in range(2):
-        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
-    ctx.timer_start(2)
-    for _ in range(R):
-        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
-    t_paint = ctx.timer_stop(2) / R
-    out = DeviceArray.empty((nl,), "f8")
-    for _ in range(2):
-        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
-    ctx.timer_start(2)
-    for _ in range(R):
-        pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
-    t_read = ctx.timer_stop(2) / R
-    ab_paint = nl * 24.0 + ncell_local * es          # pos (3 x f8) read + one mesh write pass
-    ab_read = nl * (24.0 + 8.0) + ncell_local * es   # pos read + f8 result write + one mesh read pass
-    gp_s = comm.allreduce(nl, op=C.SUM) / ((comm.allreduce(t_paint, op=C.MAX) + comm.allreduce(t_read, op=C.MAX)) * 1e-3) / 1e9
-    dom = ("paint", t_paint, ab_paint) if t_paint >= t_read else ("readout", t_read, ab_read)
-    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
-    # which kernel that is (dispatch of pmb_resample.cu) and its DRAM traffic per launch from the
-    # committed ncu --set full capture of the same launch (profiles/traffic_r1.json), when there is one
-    big = nl >= (1 << 18)
-    if args.window == "cic" and big:
-        kname = {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32"}[dom[0]]
-    elif args.window in ("nnb", "cic", "tsc", "pcs"):
-        kname = {"paint": ("pmb_k_paint_carry32" if args.window in ("tsc", "pcs") else "pmb_k_paint_sched") if big else "pmb_k_paint_tuned",
-                 "readout": "pmb_k_readout_sched" if big else "pmb_k_readout_tuned"}[dom[0]]
-    else:
-        kname = "pmb_k_%s_dyn" % dom[0]
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        traffic = tj.get("%s:%s:%d:%d:%s" % (kname, args.window, M, comm.size, args.particles))
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "ms_per_launch": round(dom[1], 4),
-                "algorithmic_bytes_per_launch": dom[2],
-                "paint_ms": round(t_paint, 4), "readout_ms": round(t_read, 4),
-                "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),
-                "readout_frac": round(ab_read / (t_read * 1e-3) / 1e9 / peak, 4)}
-    # ---- size-independent properties at the full benchmark size (outside every timed region) ----
+    # ---- size-independent properties of the timed input at full size (outside every timed region) ----
     # mass conservation of the scatter: sum(rho) == number of particles; momentum conservation of
     # the whole force step (same window for paint and readout, antisymmetric transfer):
     # |sum_p F_d(p)| << N * rms(F)
-    rho.fill(0.0)
-    pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
-    mass = _strided_sum(ctx, rho._device())
-    mass = comm.allreduce(mass, op=C.SUM)
+    es = pm.dtype.itemsize
     fsum = [comm.allreduce(F[d].sum(), op=C.SUM) for d in range(3)]
     fsq = comm.allreduce(sum(F[d].dot(F[d]) for d in range(3)), op=C.SUM)
     frms = (fsq / (3.0 * ntot)) ** 0.5
-    verify = {"mass_conservation_rel_err": abs(mass - ntot) / ntot,
-              "net_force_over_n_rms_force": max(abs(f) for f in fsum) / (ntot * max(frms, 1e-300))}
-    del lpos, layout, rho, out
+    verify = {"net_force_over_n_rms_force": max(abs(f) for f in fsum) / (ntot * max(frms, 1e-300))}
+
+    # ---- dominant kernels alone: paint and readout on the local particles, per input (roofline) ----
+    peak, peak_src = peaks()
+    inputs = {}
+    dom_stats = None
+    todo = [args.particles] + [k for k in args.inputs.split(",") if k and k != args.particles]
+    for kind in todo:
+        Xk = X if kind == args.particles else make_particles(pm, args, comm, kind)[0]
+        row, stats = time_paint_readout(pm, args, comm, Xk, peak)
+        inputs[INPUT_LABEL[kind]] = row
+        if kind == args.particles:
+            dom_stats = stats
+        if Xk is not X:
+            del Xk
+    t_paint, ab_paint, t_read, ab_read, nl = dom_stats
+    main = inputs[INPUT_LABEL[args.particles]]
+    dom = ("paint", t_paint, ab_paint) if t_paint >= t_read else ("readout", t_read, ab_read)
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    kname = kernel_names(args, nl)[dom[0]]
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("%s:%s:%d:%d:%s" % (kname, args.window, M, comm.size, args.particles))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kname, "input": INPUT_LABEL[args.particles], "achieved": round(achieved, 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "ms_per_launch": round(dom[1], 4),
+                "algorithmic_bytes_per_launch": dom[2],
+                "paint_ms": main["paint_ms"], "readout_ms": main["readout_ms"],
+                "paint_frac": main["paint_frac"], "readout_frac": main["readout_frac"]}
+
+    # mass conservation on the timed input
+    layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
+    lpos = layout.exchange(X)
+    rho = pm.paint(lpos, mode=args.paint_mode)
+    mass = comm.allreduce(_strided_sum(ctx, rho._device()), op=C.SUM)
+    verify["mass_conservation_rel_err"] = abs(mass - ntot) / ntot
+    del lpos, layout, rho
 
     # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timing ----
     e2e = None
@@ -296,27 +452,37 @@ def run_ours(args):
                "d2h_bytes_per_step": int(3 * F[0].nbytes), "steps": ke}
         del Xh, Fh
 
+    # ---- parity at full size against the oracle (periodic replicas of a small problem) ----
+    del X, F
+    if not args.no_verify:
+        par = replica_parity(pm, args, comm, step)
+        verify["parity"] = par
+        if "force_rel_err" in par:
+            verify["parity_rel_err"] = max(par["force_rel_err"], par["paint_rel_err"])
+
     cpu = None
     if comm.rank == 0 and comm.size == 1 and not args.no_cpu:
         cpu = cpu_force_step(args, cores=1, steps=1)
 
     if comm.rank == 0:
         line = {
-            "metric": METRIC, "value": round(ms_step, 3), "unit": "ms", "n_gpus": comm.size,
+            "metric": metric_name(args), "value": round(ms_step, 3), "unit": "ms", "n_gpus": comm.size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.dtype == "f8" else "f32", "data": "synthetic",
-            "config": {"workload": "CIC PM force step, %d^3 %s particles on a %d^3 mesh (BASELINE configs[2] shape)%s"
-                                   % (M, args.particles, M, "" if comm.size > 1 else ", single GPU"),
+            "config": {"workload": "%s PM force step, %d^3 %s particles on a %d^3 mesh (BASELINE configs[2] shape)%s"
+                                   % (WINDOW_NAMES.get(args.window, args.window), M, INPUT_LABEL[args.particles], M,
+                                      "" if comm.size > 1 else ", single GPU"),
                        "nmesh": M, "nparticles": ntot, "window": args.window, "paint_mode": args.paint_mode,
+                       "particles": INPUT_LABEL[args.particles],
                        "decomposition": "slab np=[%d]" % comm.size,
                        "l2": "inputs (%.1f GB positions + %.1f GB mesh per rank) are larger than L2"
-                             % (X.nbytes / 1e9, ncell_local * es / 1e9)},
-            "paint_readout_gparticles_per_s": round(gp_s, 3),
+                             % (n * 24 / 1e9, int(numpy.prod(pm._layout['i_shape'])) * es / 1e9)},
+            "paint_readout_gparticles_per_s": main["paint_readout_gparticles_per_s"],
             "particles_per_s_force_step": round(ntot / (ms_step * 1e-3), 1),
             "cufft_library_ms_per_step": round(fft_step, 3),
             "gpu_launches": int(launches),
-            "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roofline, "inputs": inputs, "e2e": e2e, "cpu_baseline": cpu,
             "verify": verify,
         }
         if args.breakdown:
@@ -442,7 +608,7 @@ def run_reference(args):
     r = cpu_force_step(args, cores=cores, steps=max(1, min(args.steps, 3)))
     M = args.nmesh
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "ms", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": r["value"], "unit": "ms", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["value"], "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "CIC PM force step, %d^3 zeldovich particles on a %d^3 mesh (BASELINE configs[2] shape)" % (M, M),

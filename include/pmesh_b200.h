@@ -139,6 +139,8 @@ int pmb_axpy(pmb_ctx *ctx, void *y, int64_t y_stride, const void *x, int64_t x_s
 /* out = a * x + b * y   (y == NULL: out = a * x) */
 int pmb_lincomb(pmb_ctx *ctx, void *out, int64_t out_stride, const void *x, int64_t x_stride, double a,
                 const void *y, int64_t y_stride, double b, int elsize, int64_t n);
+/* x = x mod period with numpy's floored modulo: the `X % BoxSize` wrap of a driver */
+int pmb_column_mod(pmb_ctx *ctx, void *x, int64_t x_stride, double period, int elsize, int64_t n);
 /* fused kick + drift in one pass: V += F * kick; S += V * drift.  V, S are contiguous (npart, ncol)
  * rows; the force is column-wise, F_cols_h[d] = dense device column (npart,) as readout / gather
  * produce it (host array of ncol device pointers).  S == NULL: kick only. */
@@ -159,6 +161,12 @@ int pmb_particles_uniform(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart
 int pmb_particles_lattice(pmb_ctx *ctx, void *pos, int pos_elsize, int64_t npart, int ndim,
                           const int64_t *n, const double *box, double shift, double amp,
                           uint64_t seed, int64_t first);
+
+/* periodic replicas of a small particle set (bench / tests): rows of block b = (b0, b1, b2), C order over
+ * nrep[0..ndim), are small[j] + b * period; blocks [first_block, first_block + nblocks) are written. */
+int pmb_particles_replicate(pmb_ctx *ctx, void *pos, int pos_elsize, const void *small_pos, int64_t nsmall,
+                            int ndim, const int64_t *nrep, const double *period,
+                            int64_t first_block, int64_t nblocks);
 
 /* ---- domain routing ------------------------------------------------------------- */
 typedef struct pmb_decompose_args {
@@ -242,6 +250,7 @@ int pmb_fft_library_ms(pmb_fft *plan, float *ms, int reset);
 #define PMB_TF_GAUSS_LOWPASS 4    /* exp(-0.5 k^2 r^2), params[0] = r, examples/nbody.py:177-181 */
 #define PMB_TF_COMPENSATE 5       /* 1/prod_d fwindow(w_d), window.py:65-80; params[0] = kind, params[1] = support */
 #define PMB_TF_IK 6               /* i*k_d (plain gradient) */
+#define PMB_TF_POWERLAW 7         /* |k|^p, 0 at k = 0; params[0] = p (shapes white noise into P(k) ~ k^(2p)) */
 int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
                  const void *in, void *out);
 /* out = prefactor * T(k) * in: the same kernel with a scalar folded into the multiplier, so that a

@@ -19,7 +19,7 @@ c_dbl_3 = ctypes.c_double * 3
 PMB_MODE_ATOMIC = 0
 PMB_MODE_DETERMINISTIC = 1
 
-TF_SCALE, TF_GRAVITY_FD4, TF_GRADIENT_K, TF_INV_LAPLACE, TF_GAUSS_LOWPASS, TF_COMPENSATE, TF_IK = range(7)
+TF_SCALE, TF_GRAVITY_FD4, TF_GRADIENT_K, TF_INV_LAPLACE, TF_GAUSS_LOWPASS, TF_COMPENSATE, TF_IK, TF_POWERLAW = range(8)
 
 
 class PmbError(RuntimeError):
@@ -63,8 +63,8 @@ SYMBOLS = [
     "pmb_memcpy_d2d", "pmb_memset", "pmb_mem_info", "pmb_timer_start", "pmb_timer_stop", "pmb_launch_count",
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
     "pmb_paint", "pmb_readout", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum",
-    "pmb_axpy", "pmb_lincomb", "pmb_kick_drift", "pmb_dot",
-    "pmb_particles_uniform", "pmb_particles_lattice",
+    "pmb_axpy", "pmb_lincomb", "pmb_column_mod", "pmb_kick_drift", "pmb_dot",
+    "pmb_particles_uniform", "pmb_particles_lattice", "pmb_particles_replicate",
     "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
@@ -92,10 +92,12 @@ _ARGTYPES = {
     "pmb_field_sum": [_P, _P, _I, _I, _P, _P, _P],
     "pmb_axpy": [_P, _P, _L, _P, _L, _D, _I, _L],
     "pmb_lincomb": [_P, _P, _L, _P, _L, _D, _P, _L, _D, _I, _L],
+    "pmb_column_mod": [_P, _P, _L, _D, _I, _L],
     "pmb_kick_drift": [_P, _P, _P, _P, _I, _D, _D, _I, _L],
     "pmb_dot": [_P, _P, _L, _P, _L, _I, _L, _P],
     "pmb_particles_uniform": [_P, _P, _I, _L, _I, _P, ctypes.c_uint64, _L],
     "pmb_particles_lattice": [_P, _P, _I, _L, _I, _P, _P, _D, _D, ctypes.c_uint64, _L],
+    "pmb_particles_replicate": [_P, _P, _I, _P, _L, _I, _P, _P, _L, _L],
     "pmb_decompose_count": [_P, _P, _P, _P], "pmb_decompose_fill": [_P, _P, _P],
     "pmb_decompose_identity": [_P, _P],
     "pmb_take": [_P, _P, _L, _P, _L, _P],

@@ -583,6 +583,51 @@ extern "C" int pmb_particles_lattice(pmb_ctx *ctx, void *pos, int pos_elsize, in
     return PMB_OK;
 }
 
+// periodic replicas of a small particle set: block b = (b0, b1, b2) (C order over nrep) holds
+// small[j] + b * period, for the blocks [first_block, first_block + nblocks).  The field of the tiled
+// problem is the periodic repetition of the small one, so the force on replica particle (b, j) equals
+// the force on particle j of the small problem: bench.py checks the full-size pipeline against the CPU
+// oracle of the small problem this way.
+__global__ void pmb_k_replicate(void *pos, int elsize, const void *small, int64_t nsmall, int ndim,
+                                int64_t r1, int64_t r2, double p0, double p1, double p2,
+                                int64_t first_block, int64_t nblocks)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t n = nblocks * nsmall;
+    const double per[3] = {p0, p1, p2};
+    for (; i < n; i += stride) {
+        const int64_t bl = i / nsmall;
+        const int64_t j = i - bl * nsmall;
+        int64_t b = bl + first_block;
+        int64_t bb[3];
+        bb[2] = b % r2; b /= r2;
+        bb[1] = b % r1; b /= r1;
+        bb[0] = b;
+        for (int d = 0; d < ndim; d++) {
+            const int64_t bd = bb[3 - ndim + d];
+            if (elsize == 8) ((double *) pos)[i * ndim + d] = ((const double *) small)[j * ndim + d] + (double) bd * per[d];
+            else ((float *) pos)[i * ndim + d] = (float) ((double) ((const float *) small)[j * ndim + d] + (double) bd * per[d]);
+        }
+    }
+}
+
+extern "C" int pmb_particles_replicate(pmb_ctx *ctx, void *pos, int pos_elsize, const void *small, int64_t nsmall,
+                                       int ndim, const int64_t *nrep, const double *period,
+                                       int64_t first_block, int64_t nblocks)
+{
+    PMB_REQUIRE(ctx && pos && small && nrep && period, "null argument");
+    PMB_REQUIRE(ndim >= 1 && ndim <= 3 && (pos_elsize == 4 || pos_elsize == 8), "bad ndim/elsize");
+    if (nsmall <= 0 || nblocks <= 0) return PMB_OK;
+    int64_t r[3] = {1, 1, 1};
+    double p[3] = {0, 0, 0};
+    for (int d = 0; d < ndim; d++) { r[3 - ndim + d] = nrep[d]; p[d] = period[d]; }
+    pmb_k_replicate<<<pmb_grid(ctx, nsmall * nblocks, 256, 8), 256, 0, ctx->stream>>>(
+        pos, pos_elsize, small, nsmall, ndim, r[1], r[2], p[0], p[1], p[2], first_block, nblocks);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
 // ---- particle columns: the element-wise updates of a KDK (leap-frog) step ---------------------------
 // The reference's integrator (examples/nbody.py:84-102, `symp2`) is numpy in place: V += F * K;
 // S += V * D; X = S + Q.  Same arithmetic, same rounding order (one multiply, one add per element, no
@@ -648,6 +693,36 @@ extern "C" int pmb_lincomb(pmb_ctx *ctx, void *out, int64_t out_stride, const vo
                            const void *y, int64_t y_stride, double b, int elsize, int64_t n)
 {
     return lincomb(ctx, out, out_stride, x, x_stride, y, y_stride, a, b, y ? 1 : 2, elsize, n);
+}
+
+// x = x mod period, numpy's floored modulo (x - floor(x / period) * period, result in [0, period]):
+// the periodic wrap `X % BoxSize` a driver applies to positions (examples/nbody.py:200 area)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pmb_k_column_mod(char *x, int64_t sx, double period, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double v = (double) *(T *) (x + i * sx);
+        double r = fmod(v, period);
+        if (r != 0 && ((r < 0) != (period < 0))) r += period;
+        *(T *) (x + i * sx) = (T) r;
+    }
+}
+
+extern "C" int pmb_column_mod(pmb_ctx *ctx, void *x, int64_t x_stride, double period, int elsize, int64_t n)
+{
+    PMB_REQUIRE(ctx && n >= 0, "bad arguments");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "columns must be float32 or float64");
+    PMB_REQUIRE(period != 0, "zero period");
+    if (n == 0) return PMB_OK;
+    PMB_REQUIRE(x, "null column");
+    const int grid = pmb_grid(ctx, n, 256, 8);
+    if (elsize == 8) pmb_k_column_mod<double><<<grid, 256, 0, ctx->stream>>>((char *) x, x_stride, period, n);
+    else pmb_k_column_mod<float><<<grid, 256, 0, ctx->stream>>>((char *) x, x_stride, period, n);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
 }
 
 template <typename T>

@@ -736,6 +736,9 @@ __device__ __forceinline__ void pmb_tf_apply(const C *__restrict__ in, C *__rest
     case PMB_TF_IK:
         re = 0; im = a.mtab[idir];
         break;
+    case PMB_TF_POWERLAW:
+        re = k2 == 0 ? 0.0 : pow(k2, 0.5 * a.p0);
+        break;
     }
     re = re * a.pre;
     im = im * a.pre;
@@ -788,7 +791,7 @@ extern "C" int pmb_transfer_scaled(pmb_fft *f, int kind, int dir, const double *
                                    double prefactor, const void *in, void *out)
 {
     PMB_REQUIRE(f && boxsize_h && in && out, "null argument");
-    PMB_REQUIRE(kind >= PMB_TF_SCALE && kind <= PMB_TF_IK, "unknown transfer kind %d", kind);
+    PMB_REQUIRE(kind >= PMB_TF_SCALE && kind <= PMB_TF_POWERLAW, "unknown transfer kind %d", kind);
     PMB_REQUIRE(dir >= 0 && dir < f->ndim, "bad direction %d", dir);
     pmb_ctx *ctx = f->ctx;
     const int pad = 3 - f->ndim;

@@ -154,6 +154,13 @@ class DeviceArray(object):
                                             self.dtype.itemsize, n))
         return self
 
+    def imod(self, period):
+        """self %= period (numpy's floored modulo), in place"""
+        assert self.dtype.kind == 'f'
+        px, sx, n = self._flat()
+        _lib.check(self.ctx.lib.pmb_column_mod(self.ctx.handle, px, sx, float(period), self.dtype.itemsize, n))
+        return self
+
     def sum(self):
         """sum of all elements in float64 (device reduction; float32 / float64 arrays)"""
         import ctypes

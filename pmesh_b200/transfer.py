@@ -94,6 +94,23 @@ class GaussianLowpass(Transfer):
         return numpy.exp(-0.5 * k2 * self.r ** 2) * v
 
 
+class PowerLaw(Transfer):
+    """|k|^p (0 at k = 0): shapes white noise into a power-law spectrum P(k) ~ k^(2p)."""
+    kind = _lib.TF_POWERLAW
+
+    def __init__(self, p):
+        self.p = float(p)
+
+    def params(self):
+        return (self.p, 0.0, 0.0, 0.0)
+
+    def __call__(self, k, v):
+        k2 = sum(ki ** 2 for ki in k)
+        with numpy.errstate(divide='ignore'):
+            f = numpy.where(k2 == 0, 0.0, k2 ** (0.5 * self.p))
+        return f * v
+
+
 class GradientIK(Transfer):
     """i * k_d (plain spectral derivative)."""
     kind = _lib.TF_IK
