@@ -118,6 +118,12 @@ typedef struct pmb_resample_args {
 
 int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a);
 int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a);
+/* readout of nfields (1..3) canvases of IDENTICAL geometry (a->size, strides, dtype) at the same positions
+ * in one sweep over the particles: cell indices and weights are computed once and used for every field
+ * (the three force components of the PM step, examples/nbody.py:211-216, share one pass over the
+ * positions).  a->mesh / a->out / a->out_stride are ignored; results are those of nfields pmb_readout calls. */
+int pmb_readout_multi(pmb_ctx *ctx, const pmb_resample_args *a, int nfields, const void *const *meshes_h,
+                      void *const *outs_h, const int64_t *out_strides_h);
 /* fused value + ndim gradients in one neighbour sweep (paint_vjp / readout_vjp helper).
  * out_value may be NULL; out_grad is (npart, ndim) with byte strides gs0, gs1, element size out_elsize. */
 int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1);

@@ -80,6 +80,7 @@ extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
     if (ctx->route_masks) cudaFree(ctx->route_masks);
     if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
     if (ctx->sched_buf) cudaFree(ctx->sched_buf);
+    if (ctx->perm_ids) cudaFree(ctx->perm_ids);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
     return PMB_OK;

@@ -53,6 +53,13 @@ struct pmb_ctx {
     int64_t sched_nchunks;
     uint64_t sched_sig;
     int sched_uses;
+    // particle permutation (tile order) for particle arrays without spatial order (pmb_perm.cuh)
+    void *perm_ids;
+    size_t perm_bytes;
+    int64_t perm_npart;
+    uint64_t perm_sig;
+    int perm_uses;
+    int perm_state;          // verdict of the last probe: 0 chunks are compact, 1 scattered (permutation in perm_ids)
 };
 
 void pmb_set_error(const char *fmt, ...);

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 
 #include "pmb_sched.cuh"
+#include "pmb_ring.cuh"
+#include "pmb_perm.cuh"
 
 // ------------------------------------------------------------------ atomic paint
 // L2 residency control: mesh cells are re-touched by particles of neighbouring lattice rows /
@@ -400,6 +402,21 @@ static int fixed_family(const PmbWindow &w, const pmb_resample_args *a)
     default: { constexpr int NDIM = 3; CALL; } break;       \
     }
 
+// 32-bit element-index geometry of a canvas (false: strides / extent do not allow it)
+template <typename MeshT>
+static bool geom32(const pmb_resample_args *a, const PmbGeom &g, PmbGeom32 *g32)
+{
+    int64_t span = 0;
+    for (int d = 0; d < 3; d++) {
+        if (a->strides[d] < 0 || a->strides[d] % (int64_t) sizeof(MeshT)) return false;
+        span += (a->size[d] - 1) * (a->strides[d] / (int64_t) sizeof(MeshT));
+        g32->scale[d] = g.scale[d]; g32->translate[d] = g.translate[d];
+        g32->period[d] = (int) g.period[d]; g32->size[d] = (int) g.size[d];
+        g32->estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
+    }
+    return span < ((int64_t) 1 << 31) - 1;
+}
+
 template <typename MeshT>
 static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
                         const PmbParticles &p)
@@ -412,6 +429,21 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         int64_t nchunks;
         const bool chk = pmb_geom_needs_check(g);
         const int unit = pmb_env_flag("PMB_CARRY_UNIT", 128);
+        // particle arrays without spatial order: walk them through a tile-binned permutation (pmb_perm.cuh)
+        const uint32_t *perm;
+        PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
+        if (perm) {
+            const int gridp = pmb_grid(ctx, a->npart, 256, 8);
+            PmbGeom32 g32;
+            if (fam == 2 && !(a->order[0] | a->order[1] | a->order[2]) && geom32<MeshT>(a, g, &g32)) {
+                PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic32_perm<MeshT, CHECK><<<gridp, 256, 0, ctx->stream>>>(g32, p, (MeshT *) mesh, a->npart, perm)));
+            } else {
+                PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3,
+                    (pmb_k_paint_perm<MeshT, FAM, CHECK><<<gridp, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix, perm))));
+            }
+            PMB_LAUNCH_CHECK(ctx);
+            return PMB_OK;
+        }
         if (fam == 2 && unit > 0 && !(a->order[0] | a->order[1] | a->order[2])) {
             // CIC: y-carry in registers + z aggregation in the warp (pmb_k_paint_cic_carry)
             PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks, 1));
@@ -434,6 +466,18 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
                 }
                 const int pminb = pmb_env_flag("PMB_PAINT_MINB", 4);
+                if (pmb_env_flag("PMB_RING", 1) && pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) {
+                    // particle stream through the bulk-copy ring (pmb_ring.cuh)
+                    const int rminb = pmb_env_flag("PMB_RING_PAINT_MINB", 4);
+                    const int64_t capr = (int64_t) ctx->sm_count * rminb;
+                    const int gridr = (int) (nunits < capr ? nunits : capr);
+#define PMB_RING_PAINT(MB) PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32_ring<MeshT, CHECK, MB><<<gridr, PMB_RING_THREADS, 0, ctx->stream>>>( \
+                        g32, (const double *) p.pos, p, (MeshT *) mesh, a->npart, order, nchunks, unit)))
+                    if (rminb <= 3) { PMB_RING_PAINT(3); } else if (rminb == 4) { PMB_RING_PAINT(4); } else { PMB_RING_PAINT(5); }
+#undef PMB_RING_PAINT
+                    PMB_LAUNCH_CHECK(ctx);
+                    return PMB_OK;
+                }
                 if (pminb >= 5 && pmb_pos_is_f8_rows(p)) {
                     if (pminb == 5) {
                         PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic_carry32<MeshT, CHECK, true, 5><<<gridu, PMB_CHUNK, 0, ctx->stream>>>(
@@ -655,6 +699,32 @@ extern "C" int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a)
                  : paint_deterministic<uint64_t, float>(ctx, a, g, w, p);
 }
 
+// CIC gather of nf canvases in one sweep, particle stream through the bulk-copy ring (pmb_ring.cuh)
+template <typename MeshT>
+static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &p, const PmbFields &f, int nf,
+                        int64_t npart, bool chk)
+{
+    const int64_t nchunks = (npart + PMB_CHUNK - 1) / PMB_CHUNK;
+    unsigned long long *ticket;
+    PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
+    const int minb = pmb_env_flag(nf == 1 ? "PMB_RING_READOUT_MINB" : "PMB_RING_READOUT3_MINB", nf == 1 ? 5 : 3);
+    const int64_t cap = (int64_t) ctx->sm_count * minb;
+    const int grid = (int) (nchunks < cap ? nchunks : cap);
+    const double *pos = (const double *) p.pos;
+#define PMB_RING_READ(NFV, MB) PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_ring<MeshT, CHECK, NFV, MB><<<grid, PMB_RING_THREADS, 0, ctx->stream>>>( \
+        g32, pos, f, npart, nchunks, ticket)))
+    if (nf == 1) {
+        if (minb <= 4) { PMB_RING_READ(1, 4); } else if (minb == 5) { PMB_RING_READ(1, 5); } else { PMB_RING_READ(1, 6); }
+    } else if (nf == 2) {
+        if (minb <= 3) { PMB_RING_READ(2, 3); } else { PMB_RING_READ(2, 4); }
+    } else {
+        if (minb <= 2) { PMB_RING_READ(3, 2); } else if (minb == 3) { PMB_RING_READ(3, 3); } else { PMB_RING_READ(3, 4); }
+    }
+#undef PMB_RING_READ
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
 template <typename MeshT>
 static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
                         const PmbParticles &p)
@@ -669,6 +739,28 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
     if (fam && a->ndim == 3 && a->npart >= ((int64_t) 1 << 18) && sched_readout) {
         const uint32_t *order = NULL;
         int64_t nchunks = (a->npart + PMB_CHUNK - 1) / PMB_CHUNK;
+        {
+            // particle arrays without spatial order: tile-binned permutation (pmb_perm.cuh)
+            const uint32_t *perm;
+            PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
+            if (perm) {
+                const int gridp = pmb_grid(ctx, a->npart, 256, 8);
+                const bool chkp = pmb_geom_needs_check(g);
+                PmbGeom32 g32;
+                if (fam == 2 && !(a->order[0] | a->order[1] | a->order[2]) && geom32<MeshT>(a, g, &g32)) {
+                    PmbFields f;
+                    memset(&f, 0, sizeof(f));
+                    f.mesh[0] = mesh; f.out[0] = a->out; f.out_stride[0] = a->out_stride; f.out_elsize = a->out_elsize;
+                    PMB_DISPATCH_CHECK(chkp, (pmb_k_readout_cic32_perm<MeshT, CHECK, 1><<<gridp, 256, 0, ctx->stream>>>(g32, p, f, a->npart, perm)));
+                } else {
+                    PMB_DISPATCH_CHECK(chkp, PMB_DISPATCH_FAM(fam, 3,
+                        (pmb_k_readout_perm<MeshT, FAM, CHECK><<<gridp, 256, 0, ctx->stream>>>(
+                            g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, perm))));
+                }
+                PMB_LAUNCH_CHECK(ctx);
+                return PMB_OK;
+            }
+        }
         if (sched_readout >= 2) PMB_CHECK(pmb_sched_prepare(ctx, g, p, a->npart, &order, &nchunks));
         unsigned long long *ticket;
         PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
@@ -689,6 +781,12 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.scale[d] = g.scale[d]; g32.translate[d] = g.translate[d];
                     g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
+                }
+                if (pmb_env_flag("PMB_RING", 1) && pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) {
+                    PmbFields f;
+                    memset(&f, 0, sizeof(f));
+                    f.mesh[0] = mesh; f.out[0] = a->out; f.out_stride[0] = a->out_stride; f.out_elsize = a->out_elsize;
+                    return readout_ring<MeshT>(ctx, g32, p, f, 1, a->npart, chk);
                 }
                 // resident CTAs per SM: measured at 1024^3 (ms): 5 -> 11.44, 6 -> 10.73 (the gather is
                 // latency-bound: more warps in flight beat more loads per warp, cf. the _pipe variant)
@@ -757,6 +855,70 @@ extern "C" int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a)
     PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
     if (a->mesh_elsize == 8) return readout_impl<double>(ctx, a, g, w, p);
     return readout_impl<float>(ctx, a, g, w, p);
+}
+
+// readout of up to 3 canvases of identical geometry at the same positions
+template <typename MeshT>
+static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, const void *const *meshes,
+                              void *const *outs, const int64_t *out_strides, bool *done)
+{
+    *done = false;
+    PmbGeom g;
+    fill_geom(a, &g);
+    PmbParticles p;
+    fill_particles(a, &p);
+    PmbWindow w;
+    PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
+    const int fam = fixed_family(w, a);
+    if (!(fam == 2 && a->ndim == 3 && !(a->order[0] | a->order[1] | a->order[2]) && a->npart >= ((int64_t) 1 << 18))) return PMB_OK;
+    PmbGeom32 g32;
+    if (!geom32<MeshT>(a, g, &g32)) return PMB_OK;
+    PmbFields f;
+    memset(&f, 0, sizeof(f));
+    for (int q = 0; q < nf; q++) { f.mesh[q] = meshes[q]; f.out[q] = outs[q]; f.out_stride[q] = out_strides[q]; }
+    f.out_elsize = a->out_elsize;
+    const uint32_t *perm;
+    PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
+    if (perm) {
+        const int gridp = pmb_grid(ctx, a->npart, 256, 8);
+        const bool chk = pmb_geom_needs_check(g);
+        if (nf == 1) { PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_perm<MeshT, CHECK, 1><<<gridp, 256, 0, ctx->stream>>>(g32, p, f, a->npart, perm))); }
+        else if (nf == 2) { PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_perm<MeshT, CHECK, 2><<<gridp, 256, 0, ctx->stream>>>(g32, p, f, a->npart, perm))); }
+        else { PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_perm<MeshT, CHECK, 3><<<gridp, 256, 0, ctx->stream>>>(g32, p, f, a->npart, perm))); }
+        PMB_LAUNCH_CHECK(ctx);
+        *done = true;
+        return PMB_OK;
+    }
+    if (!pmb_env_flag("PMB_RING", 1) || !pmb_pos_is_f8_rows(p) || ((uintptr_t) p.pos & 15)) return PMB_OK;
+    *done = true;
+    return readout_ring<MeshT>(ctx, g32, p, f, nf, a->npart, pmb_geom_needs_check(g));
+}
+
+extern "C" int pmb_readout_multi(pmb_ctx *ctx, const pmb_resample_args *a, int nfields, const void *const *meshes_h,
+                                 void *const *outs_h, const int64_t *out_strides_h)
+{
+    PMB_REQUIRE(ctx && a && meshes_h && outs_h && out_strides_h, "null argument");
+    PMB_REQUIRE(nfields >= 1 && nfields <= 3, "1..3 fields");
+    pmb_resample_args b = *a;
+    b.mesh = (void *) meshes_h[0];
+    b.out = outs_h[0];
+    b.out_stride = out_strides_h[0];
+    PMB_CHECK(check_args(ctx, &b, 1));
+    for (int q = 0; q < nfields; q++) PMB_REQUIRE(a->npart == 0 || (meshes_h[q] && outs_h[q]), "null mesh / out %d", q);
+    if (a->npart == 0) return PMB_OK;
+    bool done = false;
+    if (a->mesh_elsize == 8) PMB_CHECK(readout_multi_impl<double>(ctx, a, nfields, meshes_h, outs_h, out_strides_h, &done));
+    else PMB_CHECK(readout_multi_impl<float>(ctx, a, nfields, meshes_h, outs_h, out_strides_h, &done));
+    if (done) return PMB_OK;
+    // any other window / geometry: one ordinary readout per field
+    for (int q = 0; q < nfields; q++) {
+        b = *a;
+        b.mesh = (void *) meshes_h[q];
+        b.out = outs_h[q];
+        b.out_stride = out_strides_h[q];
+        PMB_CHECK(pmb_readout(ctx, &b));
+    }
+    return PMB_OK;
 }
 
 extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1)

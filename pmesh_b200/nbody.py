@@ -75,12 +75,11 @@ def force(pm, Q, S=None, factor=1.0):
     N = pm.comm.allreduce(len(X))
     rho.scale(1.0 * pm.Nmesh.prod() / N * factor)
     rhok = rho.r2c(out=Ellipsis)
-    tmp = pm.create('complex')
-    F = []
-    for d in range(pm.ndim):
-        f = rhok.apply(force_transfer(d), out=tmp).c2r(out=Ellipsis)
-        F.append(layout.gather(f.readout(lpos)))
-    return F
+    # the ndim force fields are kept side by side so that ONE sweep over the particles reads them all
+    # (pm.readout_fields): positions, cell indices and weights are shared by the components
+    from .pm import readout_fields
+    f = [rhok.apply(force_transfer(d), out=pm.create('complex')).c2r(out=Ellipsis) for d in range(pm.ndim)]
+    return [layout.gather(col) for col in readout_fields(f, lpos)]
 
 
 def lpt1(pm, dlinear, Q):

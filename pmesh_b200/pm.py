@@ -468,8 +468,9 @@ class Field(NDArrayLike):
             out = self
 
         tf = find_transfer(func)
-        if tf is not None and isinstance(self, BaseComplexField) and isinstance(out, BaseComplexField) \
-                and kind == tf.apply_kind:
+        if tf is not None and isinstance(self, BaseComplexField) and kind != tf.apply_kind:
+            raise ValueError("transfer %s expects apply(kind=%r), got kind=%r" % (type(tf).__name__, tf.apply_kind, kind))
+        if tf is not None and isinstance(self, BaseComplexField) and isinstance(out, BaseComplexField):
             ctx = self.pm.ctx
             src = self._device(absorb=True)
             params = (ctypes.c_double * 4)(*tf.params())
@@ -751,6 +752,28 @@ class TransposedComplexField(BaseComplexField):
 
 # backward-compatbility, alias TranposedComplexField to ComplexField
 ComplexField = TransposedComplexField
+
+
+def readout_fields(fields, pos, resampler=None, transform=None, layout=None):
+    """
+    Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles
+    (engine extension; the force step's three components, examples/nbody.py:211-216, share the pass
+    over the positions).  Equals ``[f.readout(pos, layout=layout) for f in fields]`` value for value.
+
+    pos : DeviceArray (N, ndim);  returns a list of DeviceArray (N,)
+    """
+    pm = fields[0].pm
+    if not transform:
+        transform = pm.affine
+    resampler = FindResampler(pm.resampler if resampler is None else resampler)
+    if layout is not None:
+        pos = layout.exchange(pos)
+    out = []
+    for i in range(0, len(fields), 3):
+        out += resampler.readout_multi([f._device() for f in fields[i:i + 3]], pos, transform=transform)
+    if layout is not None:
+        out = [layout.gather(o) for o in out]
+    return out
 
 
 def reindex(Nsrc, Ndest):

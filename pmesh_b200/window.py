@@ -269,6 +269,31 @@ class ResampleWindow(object):
             return host_out
         return dout
 
+    def readout_multi(self, reals, pos, hsml=None, outs=None, transform=None):
+        """readout of up to three canvases of identical shape / strides / dtype at the same positions in one
+        sweep over the particles (pmb_readout_multi): cell indices and weights are computed once.  Each
+        result equals ``readout(real, pos)`` bit for bit.  Returns a list of DeviceArray."""
+        meshes = [self._device_mesh(r)[0] for r in reals]
+        m0 = meshes[0]
+        nf = len(meshes)
+        assert 1 <= nf <= 3
+        for m in meshes[1:]:
+            assert m.shape == m0.shape and m.strides == m0.strides and m.dtype == m0.dtype, "canvases must share one geometry"
+        a, keep, n = self._args(m0, pos, hsml, None, transform)
+        if outs is None:
+            outs = [DeviceArray.empty((n,), 'f8') for _ in meshes]
+        for o in outs:
+            assert is_device(o) and o.ndim == 1 and o.shape[0] == n and o.dtype == outs[0].dtype
+        a.out_elsize = outs[0].dtype.itemsize
+        mp = (ctypes.c_void_p * nf)(*[m.ptr for m in meshes])
+        op = (ctypes.c_void_p * nf)(*[o.ptr for o in outs])
+        os_ = (ctypes.c_int64 * nf)(*[o.strides[0] for o in outs])
+        ctx = m0.ctx
+        ctx.ensure_tables()
+        _lib.check(ctx.lib.pmb_readout_multi(ctx.handle, ctypes.byref(a), nf, mp, op, os_))
+        del keep
+        return list(outs)
+
     def readout_grad(self, real, pos, hsml=None, transform=None, want_value=True):
         """value and all ndim gradients in one neighbour sweep (device arrays): (value | None, grad (N, ndim)).
         Each column equals readout(diffdir=d) bit for bit; this is the paint_vjp / readout_vjp helper."""

@@ -357,3 +357,36 @@ def test_scheduled_kernels_large_inputs(W, oracle, name, order):
     field = rng.uniform(-1, 1, shape)
     r = W.windows[name].readout(DeviceArray.from_host(field), DeviceArray.from_host(p4), transform=tr)
     assert_array_equal(r.to_host(), oracle.readout(field, p4, name, scale=[0.9, 1.1, 0.5], translate=[1.0, -2.0, 3.5], period=[0] * 3))
+
+
+@pytest.mark.parametrize("order", ["lattice", "random"])
+def test_readout_multi_equals_single_readouts(W, oracle, order):
+    """pmb_readout_multi: up to three canvases read in one sweep over the particles (bulk-copy ring
+    kernel on lattice order, tile-binned permutation on random order) == one readout per canvas == the
+    oracle, bit for bit; full periodic canvas and a translated slab; odd particle count (tail chunk)."""
+    from pmesh_b200.device import DeviceArray
+    N = 72
+    rng = numpy.random.default_rng(23)
+    q = numpy.indices((N, N, N)).reshape(3, -1).T + 0.5
+    pos = (q + 2.5 * numpy.sin(2 * numpy.pi * q[:, ::-1] / N) + rng.uniform(-0.2, 0.2, q.shape)) % N
+    if order == "random":
+        pos = pos[rng.permutation(len(pos))]
+    pos = pos[:len(pos) - 37]
+    dpos = DeviceArray.from_host(pos)
+    for shape, translate in (((N, N, N), [0.0, 0.0, 0.0]), ((20, N, N), [-30.0, 0.0, 0.0])):
+        tr = W.Affine(3, scale=1.0, translate=translate, period=N)
+        for dtype in ("f8", "f4"):
+            fields = [rng.uniform(-1, 1, shape).astype(dtype) for _ in range(3)]
+            dfields = [DeviceArray.from_host(f) for f in fields]
+            for nf in (1, 2, 3):
+                outs = W.windows["cic"].readout_multi(dfields[:nf], dpos, transform=tr)
+                for f, df, o in zip(fields, dfields, outs):
+                    want = oracle.readout(f, pos, "cic", translate=translate, period=[N] * 3)
+                    assert_array_equal(o.to_host(), want)
+                    assert_array_equal(W.windows["cic"].readout(df, dpos, transform=tr).to_host(), want)
+    # any other window falls back to one readout per canvas
+    tr = W.Affine(3, scale=1.0, translate=[0.0] * 3, period=N)
+    fields = [rng.uniform(-1, 1, (N, N, N)) for _ in range(2)]
+    outs = W.windows["tsc"].readout_multi([DeviceArray.from_host(f) for f in fields], dpos, transform=tr)
+    for f, o in zip(fields, outs):
+        assert_array_equal(o.to_host(), oracle.readout(f, pos, "tsc", period=[N] * 3))
