@@ -57,7 +57,10 @@ def parse():
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=128, help="side of the CPU-baseline sample problem")
+    ap.add_argument("--cpu-sample", type=int, default=256,
+                    help="side of the sample problem of the cpu_baseline leg of the default arm (a few seconds on all cores)")
+    ap.add_argument("--cpu-sample-reference", type=int, default=512,
+                    help="side of the sample problem each step of `--impl reference` measures (~10 s per step on 16 cores)")
     return ap.parse_args()
 
 
@@ -466,7 +469,7 @@ def run_ours(args):
 
     cpu = None
     if comm.rank == 0 and comm.size == 1 and not args.no_cpu:
-        cpu = cpu_force_step(args, cores=1, steps=1)
+        cpu = cpu_force_step(args, n=min(args.cpu_sample, args.nmesh), steps=2)
 
     if comm.rank == 0:
         line = {
@@ -496,127 +499,42 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def _cpu_kernels():
-    """(paint, readout, kind): the compiled reference (oracle/_ref) when present, else the oracle port"""
+def cpu_force_step(args, n, steps, warmup=0, cores=None):
+    """The reference's CPU implementation of the same force step on the host cores (oracle/cpu_arm.py:
+    the reference's own compiled C paint / readout from oracle/_ref -- the oracle port when it is absent --,
+    its routing arithmetic, numpy transfer, scipy.fft standing in for PFFT; one slab of the mesh per worker
+    process as the reference's MPI ranks would hold it, communication free).  A full n^3 / n^3 step is
+    MEASURED on all host cores; the value reported for the bench workload scales it by particle count."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import build_ref
-    import oracle
-    oracle.build()
-    mods = build_ref.load()
-    if mods is not None:
-        w = mods[0]
-
-        class RW(w.ResampleWindow):
-            pass
-
-        def paint(real, pos, kind, scale, period):
-            nd = real.ndim
-            RW(oracle.NAMES[kind]).paint(real, pos, None, numpy.ones(len(pos)), numpy.zeros(nd, dtype=int),
-                                         numpy.full(nd, scale), numpy.zeros(nd), numpy.full(nd, period, dtype=numpy.intp))
-
-        def readout(real, pos, kind, scale, period):
-            nd = real.ndim
-            out = numpy.zeros(len(pos))
-            RW(oracle.NAMES[kind]).readout(real, pos, None, out, numpy.zeros(nd, dtype=int),
-                                           numpy.full(nd, scale), numpy.zeros(nd), numpy.full(nd, period, dtype=numpy.intp))
-            return out
-        return paint, readout, "reference", oracle
-
-    def paint(real, pos, kind, scale, period):
-        oracle.paint(real, pos, kind, scale=scale, period=period)
-
-    def readout(real, pos, kind, scale, period):
-        return oracle.readout(real, pos, kind, scale=scale, period=period)
-    return paint, readout, "port", oracle
-
-
-def _cpu_sample(args, steps, fft_workers=1):
-    """seconds per CIC force step of the reference's CPU path on ONE core for the bounded sample:
-    `--cpu-sample`^3 particles / mesh (BoxSize = side, so scale = 1): the oracle's decompose (numpy
-    digitize + gridnd_fill), the reference's own C paint / readout (oracle/_ref; the oracle port if
-    it is absent), numpy transfer functions and numpy/scipy FFT as the labelled stand-in for PFFT."""
-    paint, readout, kind, oracle = _cpu_kernels()
-    n = args.cpu_sample
-    q = (numpy.indices((n, n, n)).reshape(3, -1).T + 0.5)
-    X = (q + 3.0 * numpy.sin(2 * numpy.pi * 4 * q[:, ::-1] / n)) % n
-    edges = [numpy.array([0.0, n])] * 3
-    try:
-        import scipy.fft as sfft
-        rfftn = lambda a: sfft.rfftn(a, workers=fft_workers)
-        irfftn = lambda a, sh: sfft.irfftn(a, s=sh, workers=fft_workers)
-    except Exception:
-        rfftn, irfftn = numpy.fft.rfftn, (lambda a, sh: numpy.fft.irfftn(a, s=sh))
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        counts, indices = oracle.decompose(X, edges, 1, smoothing=2.0)
-        lpos = X.take(indices, axis=0)
-        mesh = numpy.zeros((n, n, n))
-        paint(mesh, lpos, args.window, 1.0, n)
-        mesh *= 1.0
-        ck = rfftn(mesh) / mesh.size
-        for d in range(3):
-            fr = irfftn(oracle.transfer(ck, [n] * 3, [float(n)] * 3, "gravity_fd4", d), (n, n, n)) * mesh.size
-            f = readout(fr, lpos, args.window, 1.0, n)
-            oracle.bincount_sum(indices, f, len(X))
-        times.append(time.perf_counter() - t0)
-    return float(numpy.mean(times)), kind
-
-
-def _cpu_rank(job):
-    args, steps, barrier = job
-    barrier.wait()
-    t0 = time.perf_counter()
-    _cpu_sample(args, steps)
-    return time.perf_counter() - t0
-
-
-def cpu_force_step(args, cores, steps):
-    """The reference's CPU path on `cores` host cores.  The reference is SPMD with one serial process
-    per rank, so `cores` > 1 is modelled the way BASELINE.md section 3 prescribes: `cores` forked
-    processes, each running the force step of its own sample block at the same time (no MPI exists in
-    the image); the aggregate rate is cores x samples per wall-clock time, i.e. perfect-scaling
-    communication and a shared memory system.  Reported scaled to the 1024^3 workload by particle count."""
-    n = args.cpu_sample
-    if cores == 1:
-        t, kind = _cpu_sample(args, steps)
-        per_sample = t
-        how = "one CIC force step in %.2f s on 1 core" % t
-    else:
-        import multiprocessing as mp
-        ctx = mp.get_context("fork")
-        kind = _cpu_kernels()[2]
-        mgr = ctx.Manager()
-        barrier = mgr.Barrier(cores)
-        with ctx.Pool(cores) as pool:
-            walls = pool.map(_cpu_rank, [(args, steps, barrier)] * cores)
-        mgr.shutdown()
-        wall = max(walls) / steps
-        per_sample = wall / cores
-        how = ("%d rank processes, one sample block each, concurrently: %.2f s per step wall = %.3f s per sample"
-               % (cores, wall, per_sample))
+    import cpu_arm
+    r = cpu_arm.force_step(n=n, window=args.window, cores=cores, steps=steps, warmup=warmup)
     factor = (args.nmesh / float(n)) ** 3
-    return {"value": round(per_sample * 1e3 * factor, 1), "unit": "ms", "cores": cores, "kind": kind,
-            "sample": "%d^3 particles on a %d^3 mesh; %s; scaled x%.0f by particle count to %d^3; FFT = "
-                      "numpy/scipy stand-in for PFFT (no MPI/PFFT in the image)" % (n, n, how, factor, args.nmesh),
-            "sample_seconds": round(per_sample, 4)}
+    return {"value": round(r["seconds_per_step"] * 1e3 * factor, 1), "unit": "ms", "cores": r["cores"], "kind": r["kind"],
+            "sample": "a full %s force step of %d^3 lattice_sine particles on a %d^3 mesh measured on %d host cores "
+                      "(one slab per worker process, %s as the PFFT stand-in, no MPI cost): %.2f s per step, mean of %d; "
+                      "scaled x%.0f by particle count to %d^3"
+                      % (args.window.upper(), n, n, r["cores"], r["fft"], r["seconds_per_step"], r["steps"], factor, args.nmesh),
+            "sample_seconds": round(r["seconds_per_step"], 4), "sample_nmesh": n, "scale_factor": factor}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_force_step(args, cores=cores, steps=1)
-    r = cpu_force_step(args, cores=cores, steps=max(1, min(args.steps, 3)))
+    n = min(args.cpu_sample_reference, args.nmesh)
+    # each timed step is one full force step of the sample problem; the count is bounded so that the arm
+    # ends within a few minutes whatever --steps / --warmup the driver passes
+    steps = max(1, min(args.steps, 3))
+    r = cpu_force_step(args, n=n, steps=steps, warmup=min(args.warmup, 1))
     M = args.nmesh
     line = {
         "impl": "reference", "metric": metric_name(args), "value": r["value"], "unit": "ms", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["value"], "higher_is_better": False,
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": steps, "ms_per_step": r["value"], "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "CIC PM force step, %d^3 zeldovich particles on a %d^3 mesh (BASELINE configs[2] shape)" % (M, M),
-                   "nmesh": M, "nparticles": M ** 3, "window": args.window},
+        "config": {"workload": "%s PM force step, %d^3 particles on a %d^3 mesh (BASELINE configs[2] shape)"
+                               % (WINDOW_NAMES.get(args.window, args.window), M, M),
+                   "nmesh": M, "nparticles": M ** 3, "window": args.window,
+                   "measured": "%d^3 sample, scaled x%.0f" % (n, r["scale_factor"])},
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -42,16 +42,19 @@ def _kernels():
     if mods is not None:
         w = mods[0]
 
+        class RW(w.ResampleWindow):      # the cdef class stores attributes: it needs a Python subclass (as pmesh/window.py has)
+            pass
+
         def paint(real, pos, window, translate, period):
             nd = real.ndim
-            w.ResampleWindow(oracle.NAMES[window]).paint(
+            RW(oracle.NAMES[window]).paint(
                 real, pos, None, numpy.ones(len(pos)), numpy.zeros(nd, dtype=int), numpy.ones(nd),
                 numpy.asarray(translate, dtype="f8"), numpy.asarray(period, dtype=numpy.intp))
 
         def readout(real, pos, window, translate, period):
             nd = real.ndim
             out = numpy.zeros(len(pos))
-            w.ResampleWindow(oracle.NAMES[window]).readout(
+            RW(oracle.NAMES[window]).readout(
                 real, pos, None, out, numpy.zeros(nd, dtype=int), numpy.ones(nd),
                 numpy.asarray(translate, dtype="f8"), numpy.asarray(period, dtype=numpy.intp))
             return out
@@ -80,7 +83,15 @@ def _shared(shape, dtype):
     return numpy.frombuffer(raw, dtype=dtype).reshape(shape)
 
 
-def _worker(r, K, n, window, steps, barrier, rho, ck, tk, fr, support):
+def _worker(r, K, n, window, steps, barrier, rho, ck, tk, fr, support, fsq):
+    try:
+        _worker_body(r, K, n, window, steps, barrier, rho, ck, tk, fr, support, fsq)
+    except BaseException:
+        barrier.abort()                             # let everybody fail instead of waiting for ever
+        raise
+
+
+def _worker_body(r, K, n, window, steps, barrier, rho, ck, tk, fr, support, fsq):
     paint, readout, kind, oracle = _kernels()
     edges = [numpy.linspace(0, n, K + 1), numpy.array([0.0, n]), numpy.array([0.0, n])]
     s0, s1 = r * n // K, (r + 1) * n // K
@@ -121,7 +132,9 @@ def _worker(r, K, n, window, steps, barrier, rho, ck, tk, fr, support):
             barrier.wait()                          # -> parent: c2r
             barrier.wait()                          # parent finished c2r
             f = readout(fr[s0:s1], lpos, window, translate, period)
-            oracle.bincount_sum(mine, f[:len(mine)], len(X))      # Layout.gather('sum') of the self block
+            F = oracle.bincount_sum(mine, f[:len(mine)], len(X))  # Layout.gather('sum') of the self block
+            # diagnostic only (tests): the ghosts' share would come back through the reverse Alltoallv
+            fsq[r, d] = float((F * F).sum())
         barrier.wait()                              # step end
 
 
@@ -146,11 +159,12 @@ def force_step(n=512, window="cic", cores=None, steps=1, warmup=0):
     fr = _shared((n, n, n), "f8")
     ck = _shared((n, n, n // 2 + 1), "c16")
     tk = _shared((n, n, n // 2 + 1), "c16")
+    fsq = _shared((K, 3), "f8")
     for a in (rho, fr, ck, tk):
         a[...] = 0                                   # first touch outside the timed region
     total = steps + warmup
     barrier = ctx.Barrier(K + 1)
-    procs = [ctx.Process(target=_worker, args=(r, K, n, window, total, barrier, rho, ck, tk, fr, support)) for r in range(K)]
+    procs = [ctx.Process(target=_worker, args=(r, K, n, window, total, barrier, rho, ck, tk, fr, support, fsq)) for r in range(K)]
     for p in procs:
         p.start()
     times = []
@@ -177,7 +191,7 @@ def force_step(n=512, window="cic", cores=None, steps=1, warmup=0):
             if p.is_alive():
                 p.terminate()
     return {"seconds_per_step": float(numpy.mean(times)), "kind": kind, "cores": K, "n": n, "fft": fft_name,
-            "steps": steps}
+            "steps": steps, "rho_sum": float(rho.sum()), "force_sq_self_blocks": fsq.sum(axis=0).tolist()}
 
 
 if __name__ == "__main__":

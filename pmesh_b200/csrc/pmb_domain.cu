@@ -178,6 +178,12 @@ static int route_setup(pmb_ctx *ctx, const pmb_decompose_args *a, RouteGeom *g, 
         g->nedges[d] = a->nedges[d];
         g->scale[d] = a->scale[d];
         g->smoothing[d] = a->smoothing[d];
+        {
+            // guess of pmb_digitize_near: domains per unit length (0 on a degenerate grid: the fix-up loops decide)
+            const double *ed = a->edges_h + tot_edges;
+            const double span = ed[a->nedges[d] - 1] - ed[0];
+            g->inv_width[d] = span > 0 ? (double) (a->nedges[d] - 1) / span : 0.0;
+        }
         ndomains *= g->shape[d];
         tot_edges += a->nedges[d];
     }

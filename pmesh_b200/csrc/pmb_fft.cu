@@ -98,9 +98,12 @@ struct P2PEntry {
     void *xbuf[2];
     void *peer_x[64][2];
     bool in_use;
+    long long serial;     // creation number: entries are created collectively, so it is the same on every rank
     P2PEntry *next;
 };
 static P2PEntry *g_p2p_pool = NULL;
+static long long g_p2p_serial = 0;
+#define P2P_NCAND 16
 
 static int p2p_setup(pmb_fft *f)
 {
@@ -110,21 +113,43 @@ static int p2p_setup(pmb_fft *f)
     f->pool = NULL;
     const char *env = getenv("PMB_FFT_P2P");
     const int want = (env ? atoi(env) : 1) && f->P <= 64;
-    // 1. can everybody reuse an idle entry of this mesh?
-    P2PEntry *idle = NULL;
+    // 1. can everybody reuse THE SAME idle entry of this mesh?  Plans die at rank-dependent moments (garbage
+    // collection), so the sets of idle entries differ between ranks: every rank publishes the serials of its
+    // idle candidates and all take the smallest serial that is idle everywhere; otherwise a fresh entry is
+    // created collectively.  (Agreeing only on "everybody has some idle entry" would let rank A store into
+    // an entry that rank B has handed to another live plan.)
+    struct Cand { int want; int n; long long serial[P2P_NCAND]; } mine_c, all_c[64];
+    memset(&mine_c, 0, sizeof(mine_c));
+    mine_c.want = want;
     for (P2PEntry *e = g_p2p_pool; e && want; e = e->next)
         if (!e->in_use && e->ctx == ctx && e->P == f->P && e->elsize == f->elsize && e->bytes >= f->work_bytes &&
-            e->n[0] == f->n[0] && e->n[1] == f->n[1] && e->n[2] == f->n[2]) { idle = e; break; }
-    int flags[2] = {want, idle != NULL}, allflags[64][2];
-    PMB_CHECK(pmb_allgather_host(ctx, flags, allflags, sizeof(flags)));
-    int all_want = 1, all_idle = 1;
-    for (int q = 0; q < f->P; q++) { all_want = all_want && allflags[q][0]; all_idle = all_idle && allflags[q][1]; }
+            e->n[0] == f->n[0] && e->n[1] == f->n[1] && e->n[2] == f->n[2] && mine_c.n < P2P_NCAND)
+            mine_c.serial[mine_c.n++] = e->serial;
+    PMB_CHECK(pmb_allgather_host(ctx, &mine_c, all_c, sizeof(Cand)));
+    int all_want = 1;
+    for (int q = 0; q < f->P; q++) all_want = all_want && all_c[q].want;
     if (!all_want) return PMB_OK;
+    long long common = -1;
+    for (int i = 0; i < all_c[0].n; i++) {
+        const long long cand = all_c[0].serial[i];
+        bool everywhere = true;
+        for (int q = 1; q < f->P && everywhere; q++) {
+            bool found = false;
+            for (int j = 0; j < all_c[q].n; j++) found = found || all_c[q].serial[j] == cand;
+            everywhere = found;
+        }
+        if (everywhere && (common < 0 || cand < common)) common = cand;
+    }
+    P2PEntry *idle = NULL;
+    for (P2PEntry *e = g_p2p_pool; e && common >= 0; e = e->next)
+        if (e->serial == common) { idle = e; break; }
+    const int all_idle = idle != NULL;
     if (all_idle) {
         idle->in_use = true;
         f->pool = idle;
     } else {
-        // 2. a fresh entry, created by all ranks together
+        // 2. a fresh entry, created by all ranks together (the serial counts attempts: same on every rank)
+        g_p2p_serial++;
         P2PEntry *e = (P2PEntry *) calloc(1, sizeof(P2PEntry));
         if (!e) return PMB_ENOMEM;
         struct Rec { cudaIpcMemHandle_t h[2]; int ok; int pad; } mine, all[64];
@@ -165,6 +190,7 @@ static int p2p_setup(pmb_fft *f)
         e->ctx = ctx; e->P = f->P; e->elsize = f->elsize; e->bytes = f->work_bytes;
         for (int d = 0; d < 3; d++) e->n[d] = f->n[d];
         e->in_use = true;
+        e->serial = g_p2p_serial;
         e->next = g_p2p_pool;
         g_p2p_pool = e;
         f->pool = e;

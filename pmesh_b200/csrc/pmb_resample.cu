@@ -466,7 +466,11 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
                 }
                 const int pminb = pmb_env_flag("PMB_PAINT_MINB", 4);
-                if (pmb_env_flag("PMB_RING", 1) && pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) {
+                // measured at 1024^3 (B200, ms; profiles/r2_kernels_ring.jsonl): the ring does not help the
+                // scatter (11.7 vs 11.3 lattice order, 16.2 vs 15.7 Gaussian Zel'dovich): it is bound by the
+                // red.global issue rate and the L2's read-for-update traffic, not by the position latency.
+                // PMB_RING_PAINT=1 selects it for A/B runs.
+                if (pmb_env_flag("PMB_RING_PAINT", 0) && pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) {
                     // particle stream through the bulk-copy ring (pmb_ring.cuh)
                     const int rminb = pmb_env_flag("PMB_RING_PAINT_MINB", 4);
                     const int64_t capr = (int64_t) ctx->sm_count * rminb;
@@ -611,8 +615,10 @@ static int paint_deterministic(pmb_ctx *ctx, const pmb_resample_args *a, const P
     int64_t npts = 1;
     for (int d = 0; d < a->ndim; d++) npts *= smax;
 
-    // bits of the sort key actually used (sentinel = all ones sorts last as long as end_bit covers it)
-    int key_bits = (int) sizeof(KeyT) * 8;
+    // bits of the sort key actually used: the width of ncell.  Every real key is < ncell < 2^key_bits and the
+    // sentinel (all ones) truncated to key_bits bits is 2^key_bits - 1 >= ncell, so it still sorts last.
+    int key_bits = 1;
+    while (key_bits < (int) sizeof(KeyT) * 8 && ((int64_t) 1 << key_bits) <= ncell) key_bits++;
 
     // chunk size from the workspace budget: 2x keys + 2x values + cub temp
     const size_t per_pair = 2 * sizeof(KeyT) + 2 * sizeof(double);
@@ -707,7 +713,9 @@ static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &
     const int64_t nchunks = (npart + PMB_CHUNK - 1) / PMB_CHUNK;
     unsigned long long *ticket;
     PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
-    const int minb = pmb_env_flag(nf == 1 ? "PMB_RING_READOUT_MINB" : "PMB_RING_READOUT3_MINB", nf == 1 ? 5 : 3);
+    // resident CTAs per SM, measured at 1024^3 (ms): one field 4 -> 8.99, 5 -> 9.34, 6 -> 9.57 (11.13 without
+    // the ring); three fields 2 -> 21.0, 3 -> 20.0, 4 -> 28.6 (spills) (33.4 as three separate gathers)
+    const int minb = pmb_env_flag(nf == 1 ? "PMB_RING_READOUT_MINB" : "PMB_RING_READOUT3_MINB", nf == 1 ? 4 : 3);
     const int64_t cap = (int64_t) ctx->sm_count * minb;
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     const double *pos = (const double *) p.pos;

@@ -25,6 +25,7 @@ struct RouteGeom {
     int dstride[3];
     double scale[3];
     double smoothing[3];
+    double inv_width[3];         // (nedges - 1) / (edges[-1] - edges[0]): the guess of pmb_digitize_near
     const double *edges[3];      // device
     int nedges[3];
     const int32_t *assign;       // device [ndomains]
@@ -56,6 +57,23 @@ PMB_HD int pmb_digitize(double x, const double *bins, int n)
         if (bins[mid] <= x) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// the same count found from a guess: edges of a GridND are (nearly) equally spaced, so
+// (int)(x * inv_width) + 1 is the answer or next to it; the two loops move it until
+// bins[g - 1] <= x < bins[g] holds, which is exactly what the binary search returns for increasing bins.
+PMB_HD int pmb_digitize_near(double x, const double *bins, int n, double inv_width)
+{
+    if (x != x) return n;
+    const double t = (x - bins[0]) * inv_width;
+    int g;
+    if (!(t >= 0.0)) g = 0;                 // also NaN (degenerate grids: 0 * inf)
+    else if (t >= (double) n) g = n;
+    else g = (int) t + 1;
+    if (g > n) g = n;
+    while (g < n && bins[g] <= x) g++;
+    while (g > 0 && bins[g - 1] > x) g--;
+    return g;
 }
 
 // python non-negative integer modulo
@@ -94,17 +112,25 @@ PMB_HD uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, c
         const double *e = edges[d];
         const int ne = g.nedges[d];
         int l, r;
+        const double inv_w = g.inv_width[d];
         if (g.periodic) {
             const double box = e[ne - 1];
             const double c = pmb_pymod_fast(x, box);
-            l = pmb_digitize(pmb_pymod_fast(c - sm, box), e, ne);
-            r = pmb_digitize(pmb_pymod_fast(c + sm, box), e, ne);
-            const int p = pmb_digitize(c, e, ne);
+            const int p = pmb_digitize_near(c, e, ne, inv_w);
+            // particles well inside their domain (the common case): c - sm and c + sm stay in [0, box)
+            // and between the same two edges, so l = r = p without two more searches
+            const double cl = c - sm, cr = c + sm;
+            if (sm >= 0.0 && p >= 1 && p < ne && cl >= 0.0 && cr < box && e[p - 1] <= cl && cr < e[p]) {
+                l = p; r = p;
+            } else {
+                l = pmb_digitize_near(pmb_pymod_fast(cl, box), e, ne, inv_w);
+                r = pmb_digitize_near(pmb_pymod_fast(cr, box), e, ne, inv_w);
+            }
             l = p - pmb_imod(p - l, g.shape[d]) - 1;
             r = p + pmb_imod(r - p, g.shape[d]);
         } else {
-            l = pmb_digitize(x - sm, e, ne);
-            r = pmb_digitize(x + sm, e, ne);
+            l = pmb_digitize_near(x - sm, e, ne, inv_w);
+            r = pmb_digitize_near(x + sm, e, ne, inv_w);
             l = l - 1;
             l = l < 0 ? 0 : (l > g.shape[d] ? g.shape[d] : l);
             r = r < 0 ? 0 : (r > g.shape[d] ? g.shape[d] : r);

@@ -274,6 +274,10 @@ extern "C" int64_t hh_decompose(const void *pos, int pos_elsize, int64_t npart, 
         g.shape[d] = nedges[d] - 1; g.nedges[d] = nedges[d];
         g.scale[d] = scale[d]; g.smoothing[d] = smoothing[d];
         e[d] = edges + o; g.edges[d] = e[d]; o += nedges[d];
+        {
+            const double span = e[d][nedges[d] - 1] - e[d][0];
+            g.inv_width[d] = span > 0 ? (double) (nedges[d] - 1) / span : 0.0;
+        }
         nd *= g.shape[d];
     }
     g.ndomains = nd;

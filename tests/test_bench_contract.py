@@ -12,7 +12,7 @@ def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ)
     env.pop("RANK", None)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0", "--cpu-sample", "16"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                        "--warmup", "0", "--cpu-sample-reference", "16", "--nmesh", "64"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
@@ -29,7 +29,7 @@ def test_reference_arm_prints_the_contract_line():
     # ranks other than 0 stay silent under torchrun
     env["RANK"] = "1"
     q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0", "--cpu-sample", "16"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                        "--warmup", "0", "--cpu-sample-reference", "16", "--nmesh", "64"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600, env=env)
     assert q.returncode == 0 and q.stdout.strip() == ""
 
