@@ -66,6 +66,16 @@ int pmb_memcpy_h2d(pmb_ctx *ctx, void *dst, const void *src_h, size_t nbytes);
 int pmb_memcpy_d2h(pmb_ctx *ctx, void *dst_h, const void *src, size_t nbytes);
 int pmb_memcpy_d2d(pmb_ctx *ctx, void *dst, const void *src, size_t nbytes);
 int pmb_memset(pmb_ctx *ctx, void *dst, int byte, size_t nbytes);
+/* Copies on the context's two COPY streams (1: host -> device, 2: device -> host; pinned host memory),
+ * which run concurrently with each other and with the kernels of the compute stream (0).  Ordering is
+ * explicit: pmb_stream_record(stream, e) marks a point of a stream in event slot e (0..15),
+ * pmb_stream_wait(stream, e) makes everything submitted to `stream` afterwards wait for it.  The host
+ * never blocks except in pmb_stream_sync / pmb_ctx_sync. */
+int pmb_memcpy_h2d_async(pmb_ctx *ctx, void *dst, const void *src_h, size_t nbytes);
+int pmb_memcpy_d2h_async(pmb_ctx *ctx, void *dst_h, const void *src, size_t nbytes);
+int pmb_stream_record(pmb_ctx *ctx, int stream_id, int event);
+int pmb_stream_wait(pmb_ctx *ctx, int stream_id, int event);
+int pmb_stream_sync(pmb_ctx *ctx, int stream_id);
 int pmb_mem_info(pmb_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
 /* CUDA-event stopwatch on the context's stream (slots 0..15) */
 int pmb_timer_start(pmb_ctx *ctx, int slot);
@@ -135,6 +145,11 @@ int pmb_field_scale(pmb_ctx *ctx, void *mesh, int elsize, int is_complex, int nd
                     const int64_t *strides, double factor);
 int pmb_field_sum(pmb_ctx *ctx, const void *mesh, int elsize, int ndim, const int64_t *size,
                   const int64_t *strides, double *sum_h);
+
+/* sum of a[i] * b[i] over two (strided, up to 3-D) views of identical shape and strides, float64 accumulation:
+ * the rank-local term of RealField.cdot / cnorm (pm.py:897-905) */
+int pmb_field_dot(pmb_ctx *ctx, const void *a, const void *b, int elsize, int ndim, const int64_t *size,
+                  const int64_t *strides, double *dot_h);
 
 /* ---- particle columns: the element-wise updates of a KDK step -------------------------------------
  * <- the numpy in-place arithmetic of the reference's integrator, examples/nbody.py:84-102 (symp2:
@@ -229,11 +244,17 @@ int pmb_allreduce_f64(pmb_ctx *ctx, double *buf, int64_t n, int op /*0 sum, 1 ma
 int pmb_allgather_bytes(pmb_ctx *ctx, const void *send, void *recv, int64_t nbytes_per_rank);
 int pmb_barrier(pmb_ctx *ctx);
 
-/* ---- FFT (slab decomposition over the ctx communicator; cuFFT for the local 1-D/2-D FFTs) ---- */
+/* ---- FFT (slab or pencil decomposition over the ctx communicator; cuFFT for the local 1-D/2-D FFTs) ---- */
 /* real layout: padded, C order, local shape (n0_local, n1, 2*(n2/2+1)) [ndim 3];
  * complex "transposed" layout for nranks > 1: distributed along axis 1, memory order (1,2,0);
  * for nranks == 1: natural order (0,1,2).  dtype_elsize 4 (float) or 8 (double). */
 int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, pmb_fft **out);
+/* the same with an explicit process mesh np[0] x np[1] (np[0] * np[1] = ranks; rank = c0 * np[1] + c1, the C
+ * order of pfft.ProcMesh, pm.py:1319-1327).  np[1] == 1: slabs (pmb_fft_create).  np[1] > 1: pencils --
+ * real space split along axes (0, 1), complex space along axes (1, 2) with memory order (1, 2, 0)
+ * (PFFT_TRANSPOSED_OUT on a 2-D process mesh); two global transposes per transform, each inside one row /
+ * column of the process mesh, stored straight into peer memory (needs CUDA IPC between the GPUs). */
+int pmb_fft_create_np(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, const int *np, pmb_fft **out);
 int pmb_fft_destroy(pmb_fft *plan);
 /* real-space and transposed complex-space partition of THIS rank (starts/shapes per logical axis,
  * complex strides in elements) */
@@ -264,6 +285,11 @@ int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const
  * costs no pass of its own. */
 int pmb_transfer_scaled(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
                         double prefactor, const void *in, void *out);
+
+/* result_h[0..1] = (re, im) of sum over the LOCAL stored half-complex modes of conj(b) * a * w, w = 2 for
+ * modes that stand for themselves and their Hermitian conjugate (0 < k_last < N/2), else 1 -- the rank-local
+ * term of ComplexField.cdot / cnorm (pm.py:911-974, default metric and norm); float64 accumulation. */
+int pmb_cdot(pmb_fft *plan, const void *a, const void *b, double *result_h);
 
 /* ---- white noise (initial conditions) ----------------------------------------------------------- */
 /* <- pmesh._whitenoise.generate (pmesh/_whitenoise.pyx:25-45) -> pmesh_whitenoise_generator_fill

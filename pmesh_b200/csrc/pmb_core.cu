@@ -81,8 +81,78 @@ extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
     if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
     if (ctx->sched_buf) cudaFree(ctx->sched_buf);
     if (ctx->perm_ids) cudaFree(ctx->perm_ids);
+    if (ctx->streams_ready) {
+        for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->copy_stream[i]); cudaStreamDestroy(ctx->copy_stream[i]); }
+        for (int i = 0; i < PMB_NTIMERS; i++) cudaEventDestroy(ctx->sev[i]);
+    }
     cudaStreamDestroy(ctx->stream);
     free(ctx);
+    return PMB_OK;
+}
+
+// ---- copy streams: overlap of PCIe transfers with compute ------------------------------------------
+// Stream ids of this API: 0 = the compute stream every kernel of the context runs on, 1 = host -> device
+// copies, 2 = device -> host copies (PCIe is full duplex: an upload and a download can run together and
+// under a kernel).  Ordering between streams is explicit: record an event on one, wait for it on another.
+static int streams_init(pmb_ctx *ctx)
+{
+    if (ctx->streams_ready) return PMB_OK;
+    PMB_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; i++) PMB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < PMB_NTIMERS; i++) PMB_CUDA(cudaEventCreateWithFlags(&ctx->sev[i], cudaEventDisableTiming));
+    ctx->streams_ready = 1;
+    return PMB_OK;
+}
+static int stream_of(pmb_ctx *ctx, int id, cudaStream_t *s)
+{
+    PMB_REQUIRE(id >= 0 && id <= 2, "stream id %d (0 compute, 1 upload, 2 download)", id);
+    PMB_CHECK(streams_init(ctx));
+    *s = id == 0 ? ctx->stream : ctx->copy_stream[id - 1];
+    return PMB_OK;
+}
+
+extern "C" int pmb_memcpy_h2d_async(pmb_ctx *ctx, void *dst, const void *src_h, size_t nbytes)
+{
+    PMB_REQUIRE(ctx && (nbytes == 0 || (dst && src_h)), "null argument");
+    cudaStream_t s;
+    PMB_CHECK(stream_of(ctx, 1, &s));
+    if (nbytes) PMB_CUDA(cudaMemcpyAsync(dst, src_h, nbytes, cudaMemcpyHostToDevice, s));
+    return PMB_OK;
+}
+
+extern "C" int pmb_memcpy_d2h_async(pmb_ctx *ctx, void *dst_h, const void *src, size_t nbytes)
+{
+    PMB_REQUIRE(ctx && (nbytes == 0 || (dst_h && src)), "null argument");
+    cudaStream_t s;
+    PMB_CHECK(stream_of(ctx, 2, &s));
+    if (nbytes) PMB_CUDA(cudaMemcpyAsync(dst_h, src, nbytes, cudaMemcpyDeviceToHost, s));
+    return PMB_OK;
+}
+
+extern "C" int pmb_stream_record(pmb_ctx *ctx, int stream_id, int event)
+{
+    PMB_REQUIRE(ctx && event >= 0 && event < PMB_NTIMERS, "bad event slot");
+    cudaStream_t s;
+    PMB_CHECK(stream_of(ctx, stream_id, &s));
+    PMB_CUDA(cudaEventRecord(ctx->sev[event], s));
+    return PMB_OK;
+}
+
+extern "C" int pmb_stream_wait(pmb_ctx *ctx, int stream_id, int event)
+{
+    PMB_REQUIRE(ctx && event >= 0 && event < PMB_NTIMERS, "bad event slot");
+    cudaStream_t s;
+    PMB_CHECK(stream_of(ctx, stream_id, &s));
+    PMB_CUDA(cudaStreamWaitEvent(s, ctx->sev[event], 0));
+    return PMB_OK;
+}
+
+extern "C" int pmb_stream_sync(pmb_ctx *ctx, int stream_id)
+{
+    PMB_REQUIRE(ctx, "null context");
+    cudaStream_t s;
+    PMB_CHECK(stream_of(ctx, stream_id, &s));
+    PMB_CUDA(cudaStreamSynchronize(s));
     return PMB_OK;
 }
 
@@ -455,6 +525,56 @@ __global__ void pmb_k_sum(const char *mesh, FieldView v, double *out)
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) out[blockIdx.x] = acc;
     }
+}
+
+// sum_i a[i] * b[i] over two views of the same shape and strides (RealField.cdot / cnorm, pm.py:897-905)
+template <typename T>
+__global__ void pmb_k_fdot(const char *a, const char *b, FieldView v, double *out)
+{
+    __shared__ double sh[32];
+    double acc = 0;
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < v.n; i += stride) {
+        const int64_t o = view_offset(v, i);
+        acc += (double) *(const T *) (a + o) * (double) *(const T *) (b + o);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[blockIdx.x] = acc;
+    }
+}
+
+extern "C" int pmb_field_dot(pmb_ctx *ctx, const void *a, const void *b, int elsize, int ndim, const int64_t *size,
+                             const int64_t *strides, double *dot_h)
+{
+    PMB_REQUIRE(ctx && a && b && dot_h, "null argument");
+    PMB_REQUIRE(elsize == 4 || elsize == 8, "elsize must be 4 or 8");
+    FieldView v;
+    PMB_CHECK(make_view(ndim, size, strides, &v));
+    *dot_h = 0;
+    if (v.n == 0) return PMB_OK;
+    int grid = pmb_grid(ctx, v.n, 256, 4);
+    void *partial;
+    PMB_CHECK(pmb_scratch(ctx, sizeof(double) * grid, &partial));
+    if (elsize == 8) pmb_k_fdot<double><<<grid, 256, 0, ctx->stream>>>((const char *) a, (const char *) b, v, (double *) partial);
+    else pmb_k_fdot<float><<<grid, 256, 0, ctx->stream>>>((const char *) a, (const char *) b, v, (double *) partial);
+    PMB_LAUNCH_CHECK(ctx);
+    double *h = (double *) malloc(sizeof(double) * grid);
+    if (!h) return PMB_ENOMEM;
+    cudaError_t e = cudaMemcpyAsync(h, partial, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); return pmb_cuda_fail(e, "dot copy", __FILE__, __LINE__); }
+    double sum = 0;
+    for (int i = 0; i < grid; i++) sum += h[i];
+    free(h);
+    *dot_h = sum;
+    return PMB_OK;
 }
 
 // not bit-reproducible against numpy's pairwise sum; used for csum/cmean style diagnostics (pm.py:725-743)

@@ -31,9 +31,16 @@ struct pmb_fft {
     int64_t s0, m0, blk0;   // real-space slab of this rank along the first distributed axis
     int64_t s1, m1, blk1;   // complex-space slab along axis 1
     int dist_axis;          // index in n[] of the real-space distributed axis (P > 1): 0
+    // process mesh P0 x P1 (rank = c0 * P1 + c1, C order like pfft.ProcMesh); slabs are P1 == 1.
+    // Pencils (P1 > 1): real space split along axes (0, 1) over (P0, P1); complex space ("transposed out")
+    // along axes (1, 2) over (P0, P1), memory order (1, 2, 0)
+    int P0, P1, c0, c1;
+    int64_t r1s, r1m;       // real space: my block of axis 1 (over P1); slabs: the whole axis
+    int64_t s2, mc;         // complex space: my block of the half-complex axis 2 (over P1); slabs: 0, nc
     cufftHandle full_r2c, full_c2r;         // P == 1
-    cufftHandle slab_r2c, slab_c2r, line;   // P > 1
-    bool have_full, have_slab;
+    cufftHandle slab_r2c, slab_c2r, line;   // slabs
+    cufftHandle pen_r2c, pen_c2r, pen_l1, pen_l0;   // pencils: 1-D transforms along axes 2, 1, 0
+    bool have_full, have_slab, have_pen;
     void *work0, *work1;
     size_t work_bytes;
     // direct peer-memory global transpose (P > 1): every rank exposes two landing buffers through
@@ -93,7 +100,7 @@ static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long lo
 struct P2PEntry {
     pmb_ctx *ctx;
     int64_t n[3];
-    int elsize, P;
+    int elsize, P, P1;
     size_t bytes;
     void *xbuf[2];
     void *peer_x[64][2];
@@ -122,7 +129,7 @@ static int p2p_setup(pmb_fft *f)
     memset(&mine_c, 0, sizeof(mine_c));
     mine_c.want = want;
     for (P2PEntry *e = g_p2p_pool; e && want; e = e->next)
-        if (!e->in_use && e->ctx == ctx && e->P == f->P && e->elsize == f->elsize && e->bytes >= f->work_bytes &&
+        if (!e->in_use && e->ctx == ctx && e->P == f->P && e->P1 == f->P1 && e->elsize == f->elsize && e->bytes >= f->work_bytes &&
             e->n[0] == f->n[0] && e->n[1] == f->n[1] && e->n[2] == f->n[2] && mine_c.n < P2P_NCAND)
             mine_c.serial[mine_c.n++] = e->serial;
     PMB_CHECK(pmb_allgather_host(ctx, &mine_c, all_c, sizeof(Cand)));
@@ -187,7 +194,7 @@ static int p2p_setup(pmb_fft *f)
             free(e);
             return PMB_OK;
         }
-        e->ctx = ctx; e->P = f->P; e->elsize = f->elsize; e->bytes = f->work_bytes;
+        e->ctx = ctx; e->P = f->P; e->P1 = f->P1; e->elsize = f->elsize; e->bytes = f->work_bytes;
         for (int d = 0; d < 3; d++) e->n[d] = f->n[d];
         e->in_use = true;
         e->serial = g_p2p_serial;
@@ -218,7 +225,14 @@ static void p2p_teardown(pmb_fft *f)
 
 extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, pmb_fft **out)
 {
-    PMB_REQUIRE(ctx && nmesh && out, "null argument");
+    const int np[2] = {ctx ? ctx->nranks : 1, 1};
+    return pmb_fft_create_np(ctx, ndim, nmesh, dtype_elsize, np, out);
+}
+
+extern "C" int pmb_fft_create_np(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int dtype_elsize, const int *np, pmb_fft **out)
+{
+    PMB_REQUIRE(ctx && nmesh && out && np, "null argument");
+    PMB_REQUIRE(np[0] >= 1 && np[1] >= 1 && np[0] * np[1] == ctx->nranks, "process mesh %d x %d does not match %d ranks", np[0], np[1], ctx->nranks);
     PMB_REQUIRE(ndim >= 1 && ndim <= 3, "FFT supports 1..3 dimensions");
     PMB_REQUIRE(dtype_elsize == 4 || dtype_elsize == 8, "FFT dtype must be float32 or float64");
     for (int d = 0; d < ndim; d++) PMB_REQUIRE(nmesh[d] >= 1, "bad mesh size");
@@ -233,6 +247,10 @@ extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int 
     f->elsize = dtype_elsize;
     f->P = ctx->nranks;
     f->rank = ctx->rank;
+    f->P0 = np[0]; f->P1 = np[1];
+    f->c0 = f->rank / f->P1; f->c1 = f->rank % f->P1;
+    f->r1s = 0; f->r1m = f->n[1];
+    f->s2 = 0; f->mc = f->nc;
     PMB_CUDA(cudaSetDevice(ctx->device));
     for (int i = 0; i < FFT_NEV; i++) {
         PMB_CUDA(cudaEventCreate(&f->ev[i][0]));
@@ -255,6 +273,47 @@ extern "C" int pmb_fft_create(pmb_ctx *ctx, int ndim, const int64_t *nmesh, int 
         PMB_CHECK(make_plan(f, &f->full_r2c, r, n, inr, rdist, inc, cdist, dbl ? CUFFT_D2Z : CUFFT_R2C, 1));
         PMB_CHECK(make_plan(f, &f->full_c2r, r, n, inc, cdist, inr, rdist, dbl ? CUFFT_Z2D : CUFFT_C2R, 1));
         f->have_full = true;
+    } else if (f->P1 > 1) {
+        // ---- pencils ----
+        int64_t blk;
+        block_partition(f->n[0], f->P0, f->c0, &f->blk0, &f->s0, &f->m0);     // real axis 0 over P0
+        block_partition(f->n[1], f->P1, f->c1, &blk, &f->r1s, &f->r1m);        // real axis 1 over P1
+        block_partition(f->n[1], f->P0, f->c0, &f->blk1, &f->s1, &f->m1);     // complex axis 1 over P0
+        block_partition(f->nc, f->P1, f->c1, &blk, &f->s2, &f->mc);            // complex axis 2 over P1
+        if (f->m0 * f->r1m > 0) {
+            long long n1[1] = {f->n[2]};
+            long long er[1] = {2 * f->nc}, ec[1] = {f->nc};
+            PMB_CHECK(make_plan(f, &f->pen_r2c, 1, n1, er, 2 * f->nc, ec, f->nc, dbl ? CUFFT_D2Z : CUFFT_R2C, f->m0 * f->r1m));
+            PMB_CHECK(make_plan(f, &f->pen_c2r, 1, n1, ec, f->nc, er, 2 * f->nc, dbl ? CUFFT_Z2D : CUFFT_C2R, f->m0 * f->r1m));
+        }
+        if (f->m0 * f->mc > 0) {
+            long long n1[1] = {f->n[1]};
+            PMB_CHECK(make_plan(f, &f->pen_l1, 1, n1, n1, f->n[1], n1, f->n[1], dbl ? CUFFT_Z2Z : CUFFT_C2C, f->m0 * f->mc));
+        }
+        if (f->m1 * f->mc > 0) {
+            long long n1[1] = {f->n[0]};
+            PMB_CHECK(make_plan(f, &f->pen_l0, 1, n1, n1, f->n[0], n1, f->n[0], dbl ? CUFFT_Z2Z : CUFFT_C2C, f->m1 * f->mc));
+        }
+        f->have_pen = true;
+        int64_t celems = f->m0 * f->r1m * f->nc;
+        if (f->m0 * f->mc * f->n[1] > celems) celems = f->m0 * f->mc * f->n[1];
+        if (f->m1 * f->mc * f->n[0] > celems) celems = f->m1 * f->mc * f->n[0];
+        // every rank allocates the largest block of any rank: peers store into my landing buffers with THEIR strides
+        {
+            int64_t mx[4] = {(f->n[0] + f->P0 - 1) / f->P0, (f->n[1] + f->P1 - 1) / f->P1, (f->n[1] + f->P0 - 1) / f->P0, (f->nc + f->P1 - 1) / f->P1};
+            int64_t a = mx[0] * mx[1] * f->nc, b = mx[0] * mx[3] * f->n[1], c = mx[2] * mx[3] * f->n[0];
+            celems = a > b ? a : b;
+            if (c > celems) celems = c;
+        }
+        f->work_bytes = (size_t) celems * 2 * dtype_elsize + 256;
+        PMB_CUDA(cudaMalloc(&f->work0, f->work_bytes));
+        PMB_CHECK(p2p_setup(f));
+        if (!f->p2p) {
+            pmb_set_error("pencil (2-D process mesh) transforms need CUDA IPC peer access between the GPUs of the node; "
+                          "it is not available here (or PMB_FFT_P2P=0): use np=[P] slabs");
+            pmb_fft_destroy(f);
+            return PMB_EUNSUPPORTED;
+        }
     } else {
         block_partition(f->n[0], f->P, f->rank, &f->blk0, &f->s0, &f->m0);
         block_partition(f->n[1], f->P, f->rank, &f->blk1, &f->s1, &f->m1);
@@ -295,6 +354,11 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
         if (f->m0 > 0) { cufftDestroy(f->slab_r2c); cufftDestroy(f->slab_c2r); }
         if (f->m1 > 0) cufftDestroy(f->line);
     }
+    if (f->have_pen) {
+        if (f->m0 * f->r1m > 0) { cufftDestroy(f->pen_r2c); cufftDestroy(f->pen_c2r); }
+        if (f->m0 * f->mc > 0) cufftDestroy(f->pen_l1);
+        if (f->m1 * f->mc > 0) cufftDestroy(f->pen_l0);
+    }
     p2p_teardown(f);
     if (f->work0) cudaFree(f->work0);
     if (f->work1) cudaFree(f->work1);
@@ -309,24 +373,24 @@ extern "C" int pmb_fft_layout(pmb_fft *f, int64_t *i_start, int64_t *i_shape, in
 {
     PMB_REQUIRE(f && i_start && i_shape && i_strides && o_start && o_shape && o_strides, "null argument");
     const int nd = f->ndim, pad = 3 - nd;
-    int64_t is[3] = {f->s0, 0, 0}, ish[3] = {f->m0, f->n[1], f->n[2]};
-    int64_t ist[3] = {f->n[1] * 2 * f->nc, 2 * f->nc, 1};
+    int64_t is[3] = {f->s0, f->r1s, 0}, ish[3] = {f->m0, f->r1m, f->n[2]};
+    int64_t ist[3] = {f->r1m * 2 * f->nc, 2 * f->nc, 1};
     int64_t os[3], osh[3], ost[3];
     if (f->P == 1) {
         os[0] = os[1] = os[2] = 0;
         osh[0] = f->n[0]; osh[1] = f->n[1]; osh[2] = f->nc;
         ost[0] = f->n[1] * f->nc; ost[1] = f->nc; ost[2] = 1;
     } else {
-        os[0] = 0; os[1] = f->s1; os[2] = 0;
-        osh[0] = f->n[0]; osh[1] = f->m1; osh[2] = f->nc;
-        ost[0] = 1; ost[1] = f->nc * f->n[0]; ost[2] = f->n[0];
+        os[0] = 0; os[1] = f->s1; os[2] = f->s2;
+        osh[0] = f->n[0]; osh[1] = f->m1; osh[2] = f->mc;
+        ost[0] = 1; ost[1] = f->mc * f->n[0]; ost[2] = f->n[0];
     }
     for (int d = 0; d < nd; d++) {
         i_start[d] = is[pad + d]; i_shape[d] = ish[pad + d]; i_strides[d] = ist[pad + d];
         o_start[d] = os[pad + d]; o_shape[d] = osh[pad + d]; o_strides[d] = ost[pad + d];
     }
-    int64_t relems = f->m0 * f->n[1] * 2 * f->nc;
-    int64_t celems = f->P == 1 ? f->n[0] * f->n[1] * f->nc : f->m1 * f->nc * f->n[0];
+    int64_t relems = f->m0 * f->r1m * 2 * f->nc;
+    int64_t celems = f->P == 1 ? f->n[0] * f->n[1] * f->nc : f->m1 * f->mc * f->n[0];
     // either buffer may serve as the in-place partner of the other
     int64_t both = relems > 2 * celems ? relems : 2 * celems;
     if (real_alloc_elems) *real_alloc_elems = both > 0 ? both : 2;
@@ -469,36 +533,43 @@ static int slab_pack(pmb_fft *f, const void *src, void *dst, int dir)
 // dealt round-robin over the destinations, starting at my right neighbour, so that at any moment the
 // traffic is spread over all links / peers.
 struct XDest {
-    void *out[64];        // landing buffer of rank q, already offset to my first output column
-    int64_t col0[64];     // first source column of the block for rank q
+    void *out[64];        // landing buffer of destination q, already offset to my first output column
+    int64_t col0[64];     // first source column of the block for destination q
     int64_t ncols[64];    // columns of that block
+    int64_t obstride[64]; // elements between consecutive batches in the landing buffer of q
 };
 
+// The same kernel serves the pencil transposes: `nbatch` independent (R x columns) matrices, `in_bs`
+// elements apart in the source and d.obstride[q] apart in the landing buffer of destination q; P is then
+// the number of destinations (the ranks of my row or column of the process mesh) and `me` my index in it.
 template <typename C>
 __global__ void __launch_bounds__(256)
 pmb_k_xpose_scatter(const C *__restrict__ in, int64_t in_ld, int64_t R, int64_t out_ld, XDest d, int P, int me,
-                    double s, int64_t tiles_r, int64_t tiles_c_max)
+                    double s, int64_t tiles_r, int64_t tiles_c_max, int64_t nbatch, int64_t in_bs)
 {
     __shared__ C tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const int64_t per_dest = tiles_r * tiles_c_max;
+    const int64_t per_batch = tiles_r * tiles_c_max;
+    const int64_t per_dest = per_batch * nbatch;
     const int64_t ntiles = per_dest * P;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int q = (int) (t % P) + me + 1;
         if (q >= P) q -= P;
-        const int64_t lt = t / P;
+        int64_t lt = t / P;
+        const int64_t bt = lt / per_batch;
+        lt -= bt * per_batch;
         const int64_t tc = lt / tiles_r, tr = lt - tc * tiles_r;
         const int64_t r0 = tr * 32, c0 = tc * 32;
         const int64_t nc = d.ncols[q];
         if (c0 >= nc) continue;          // uniform over the block
-        const C *src = in + d.col0[q];
+        const C *src = in + bt * in_bs + d.col0[q];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
             if (r < R && c < nc) tile[ty + 8 * k][tx] = src[r * in_ld + c];
         }
         __syncthreads();
-        C *dst = (C *) d.out[q];
+        C *dst = (C *) d.out[q] + bt * d.obstride[q];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int64_t c = c0 + ty + 8 * k, r = r0 + tx;
@@ -514,18 +585,26 @@ pmb_k_xpose_scatter(const C *__restrict__ in, int64_t in_ld, int64_t R, int64_t 
 }
 
 template <typename C>
-static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, int64_t out_ld, const XDest &d, double s)
+static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, int64_t out_ld, const XDest &d, double s,
+                         int ndest = -1, int me = -1, int64_t nbatch = 1, int64_t in_bs = 0)
 {
+    if (ndest < 0) { ndest = f->P; me = f->rank; }
     int64_t cmax = 0;
-    for (int q = 0; q < f->P; q++) if (d.ncols[q] > cmax) cmax = d.ncols[q];
-    if (R == 0 || cmax == 0) return PMB_OK;
+    for (int q = 0; q < ndest; q++) if (d.ncols[q] > cmax) cmax = d.ncols[q];
+    if (R == 0 || cmax == 0 || nbatch == 0) return PMB_OK;
     const int64_t tr = (R + 31) / 32, tc = (cmax + 31) / 32;
-    int64_t grid = tr * tc * f->P;
+    int64_t grid = tr * tc * ndest * nbatch;
     const int64_t cap = (int64_t) f->ctx->sm_count * 8;
     if (grid > cap) grid = cap;
-    pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, in_ld, R, out_ld, d, f->P, f->rank, s, tr, tc);
+    pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
     PMB_LAUNCH_CHECK(f->ctx);
     return PMB_OK;
+}
+template <typename C>
+static int xpose_scatter_e(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, int64_t out_ld, const XDest &d, double s,
+                           int ndest, int me, int64_t nbatch, int64_t in_bs)
+{
+    return xpose_scatter<C>(f, in, in_ld, R, out_ld, d, s, ndest, me, nbatch, in_bs);
 }
 
 // forward: work0 (m0, n1*nc) -> rank q gets the columns of its j-range, transposed, as rows
@@ -539,6 +618,7 @@ static void xdest_fwd(const pmb_fft *f, int b, XDest *d)
         d->out[q] = (char *) f->peer_x[q][b] + (size_t) f->s0 * csz;
         d->col0[q] = s1q * f->nc;
         d->ncols[q] = m1q * f->nc;
+        d->obstride[q] = 0;
     }
 }
 // backward: work0 (m1*nc, n0) -> rank p gets the columns of its plane range, transposed, as rows
@@ -552,7 +632,109 @@ static void xdest_bwd(const pmb_fft *f, int b, XDest *d)
         d->out[p] = (char *) f->peer_x[p][b] + (size_t) (f->s1 * f->nc) * csz;
         d->col0[p] = s0p;
         d->ncols[p] = m0p;
+        d->obstride[p] = 0;
     }
+}
+
+static int exec_r2c(pmb_fft *f, cufftHandle h, const void *in, void *out);
+static int exec_c2r(pmb_fft *f, cufftHandle h, void *in, void *out);
+static int exec_c2c(pmb_fft *f, cufftHandle h, void *in, void *out, int dir);
+
+// ---- pencil transposes (P1 > 1) -----------------------------------------------------------------------
+// Landing buffers: X0 = xbuf[0] holds (m0, mc, n1) -- axis 1 contiguous, X1 = xbuf[1] holds (m1, mc, n0) --
+// axis 0 contiguous -- on the way forward, and (m0, r1m, nc) -- real-space planes -- on the way back.
+// Forward:  A r2c along 2 -> work0 (m0, r1m, nc)
+//           B scatter inside my ROW of the process mesh (fixed c0): rank (c0, c1') gets k in its block,
+//             stored as X0[(i * mc' + kl) * n1 + r1s + jl]                         -> barrier
+//           C c2c along 1, in place in X0
+//           D scatter inside my COLUMN (fixed c1): rank (c0', c1) gets j in its block,
+//             stored as X1[((j - s1') * mc + kl) * n0 + s0 + il]  (x scale)          -> barrier
+//           E c2c along 0: X1 -> result (m1, mc, n0)
+// Backward: the mirror image (E' into work0, D' into X0, C' in place, B' into X1, A' c2r X1 -> real).
+// X0 is last read before the second barrier of a transform and X1 after it, and a rank can only store into
+// a peer's X0 (X1) after the second barrier of the previous transform (the first barrier of this one), so
+// the two buffers never need to alternate.
+static void pen_dest_row(const pmb_fft *f, int b, int back, XDest *d)
+{
+    const size_t csz = 2 * (size_t) f->elsize;
+    for (int q = 0; q < f->P1; q++) {
+        const int rank = f->c0 * f->P1 + q;
+        int64_t blk, s, m;
+        if (!back) {
+            // forward B: columns k of destination q's block; my rows j land at column offset r1s
+            block_partition(f->nc, f->P1, q, &blk, &s, &m);
+            d->out[q] = (char *) f->peer_x[rank][b] + (size_t) f->r1s * csz;
+            d->col0[q] = s; d->ncols[q] = m; d->obstride[q] = m * f->n[1];
+        } else {
+            // backward B': columns j of destination q's real-space block; my rows kl land at column offset s2
+            block_partition(f->n[1], f->P1, q, &blk, &s, &m);
+            d->out[q] = (char *) f->peer_x[rank][b] + (size_t) f->s2 * csz;
+            d->col0[q] = s; d->ncols[q] = m; d->obstride[q] = m * f->nc;
+        }
+    }
+}
+static void pen_dest_col(const pmb_fft *f, int b, int back, XDest *d)
+{
+    const size_t csz = 2 * (size_t) f->elsize;
+    for (int q = 0; q < f->P0; q++) {
+        const int rank = q * f->P1 + f->c1;
+        int64_t blk, s, m;
+        if (!back) {
+            // forward D: columns j of destination q's complex block; my rows il land at column offset s0
+            block_partition(f->n[1], f->P0, q, &blk, &s, &m);
+            d->out[q] = (char *) f->peer_x[rank][b] + (size_t) f->s0 * csz;
+            d->col0[q] = s; d->ncols[q] = m; d->obstride[q] = f->n[0];
+        } else {
+            // backward D': columns i of destination q's plane block; my rows jl land at column offset s1
+            block_partition(f->n[0], f->P0, q, &blk, &s, &m);
+            d->out[q] = (char *) f->peer_x[rank][b] + (size_t) f->s1 * csz;
+            d->col0[q] = s; d->ncols[q] = m; d->obstride[q] = f->n[1];
+        }
+    }
+}
+
+template <typename C>
+static int pencil_r2c(pmb_fft *f, const void *real, void *cplx, double scale)
+{
+    pmb_ctx *ctx = f->ctx;
+    XDest d;
+    // A
+    if (f->m0 * f->r1m > 0) PMB_CHECK(exec_r2c(f, f->pen_r2c, real, f->work0));
+    // B: per plane i a (r1m x nc) matrix; destination q takes columns [s2_q, s2_q + mc_q)
+    pen_dest_row(f, 0, 0, &d);
+    PMB_CHECK(xpose_scatter_e<C>(f, f->work0, f->nc, f->r1m, f->n[1], d, 1.0, f->P1, f->c1, f->m0, f->r1m * f->nc));
+    PMB_CHECK(pmb_stream_barrier(ctx));
+    // C
+    if (f->m0 * f->mc > 0) PMB_CHECK(exec_c2c(f, f->pen_l1, f->xbuf[0], f->xbuf[0], CUFFT_FORWARD));
+    // D: per kl a (m0 x n1) matrix with row stride mc * n1; destination q takes columns [s1_q, s1_q + m1_q)
+    pen_dest_col(f, 1, 0, &d);
+    PMB_CHECK(xpose_scatter_e<C>(f, f->xbuf[0], f->mc * f->n[1], f->m0, f->mc * f->n[0], d, scale, f->P0, f->c0, f->mc, f->n[1]));
+    PMB_CHECK(pmb_stream_barrier(ctx));
+    // E
+    if (f->m1 * f->mc > 0) PMB_CHECK(exec_c2c(f, f->pen_l0, f->xbuf[1], cplx, CUFFT_FORWARD));
+    return PMB_OK;
+}
+
+template <typename C>
+static int pencil_c2r(pmb_fft *f, const void *cplx, void *real)
+{
+    pmb_ctx *ctx = f->ctx;
+    XDest d;
+    // E': (m1, mc, n0) lines along 0 -> work0 (the input is preserved)
+    if (f->m1 * f->mc > 0) PMB_CHECK(exec_c2c(f, f->pen_l0, (void *) cplx, f->work0, CUFFT_INVERSE));
+    // D': per kl a (m1 x n0) matrix with row stride mc * n0; destination q takes columns [s0_q, s0_q + m0_q)
+    pen_dest_col(f, 0, 1, &d);
+    PMB_CHECK(xpose_scatter_e<C>(f, f->work0, f->mc * f->n[0], f->m1, f->mc * f->n[1], d, 1.0, f->P0, f->c0, f->mc, f->n[0]));
+    PMB_CHECK(pmb_stream_barrier(ctx));
+    // C'
+    if (f->m0 * f->mc > 0) PMB_CHECK(exec_c2c(f, f->pen_l1, f->xbuf[0], f->xbuf[0], CUFFT_INVERSE));
+    // B': per plane i a (mc x n1) matrix; destination q takes columns [r1s_q, r1s_q + r1m_q)
+    pen_dest_row(f, 1, 1, &d);
+    PMB_CHECK(xpose_scatter_e<C>(f, f->xbuf[0], f->n[1], f->mc, f->nc, d, 1.0, f->P1, f->c1, f->m0, f->mc * f->n[1]));
+    PMB_CHECK(pmb_stream_barrier(ctx));
+    // A'
+    if (f->m0 * f->r1m > 0) PMB_CHECK(exec_c2r(f, f->pen_c2r, f->xbuf[1], real));
+    return PMB_OK;
 }
 
 // counts / offsets (in complex elements) of the global transpose.
@@ -610,6 +792,7 @@ extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scal
         }
         return PMB_OK;
     }
+    if (f->P1 > 1) return f->elsize == 8 ? pencil_r2c<double2>(f, real, cplx, scale) : pencil_r2c<float2>(f, real, cplx, scale);
     // 1. local planes: 2-D r2c over (n1, n2):  real (m0, n1, 2nc) -> work0 (m0, n1, nc)
     if (f->m0 > 0) PMB_CHECK(exec_r2c(f, f->slab_r2c, real, f->work0));
     if (f->p2p) {
@@ -658,6 +841,7 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
         PMB_CHECK(exec_c2r(f, f->full_c2r, real, real));
         return PMB_OK;
     }
+    if (f->P1 > 1) return f->elsize == 8 ? pencil_c2r<double2>(f, cplx, real) : pencil_c2r<float2>(f, cplx, real);
     // 1. inverse lines along axis 0: cplx (m1*nc, n0) -> work0 (input preserved)
     if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx, f->work0, CUFFT_INVERSE));
     if (f->p2p) {
@@ -702,7 +886,7 @@ static int c2r_from_work(pmb_fft *f, void *real)
 // a pure streaming multiply: one complex load, one complex store, no sin/div-mod per cell.
 struct TfArgs {
     int kind, ndim, P;
-    int64_t n[3], nc, s1, m1;
+    int64_t n[3], nc, s1, m1, s2, mc;
     const double *ktab[3];   // wavenumber per global index of each (left-padded) axis
     const double *mtab;      // per-index multiplier along the direction axis (or window factors, 3 axes)
     int dd;                  // direction axis (left-padded index)
@@ -787,9 +971,9 @@ pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int
         if (a.P == 1) {           // (n0, n1, nc): rows = (i0, i1), inner = i2
             i1 = row % a.n[1];
             i0 = row / a.n[1];
-        } else {                  // (m1, nc, n0): rows = (j, i2), inner = i0
-            i2 = row % a.nc;
-            i1 = a.s1 + row / a.nc;
+        } else {                  // (m1, mc, n0): rows = (j, i2), inner = i0
+            i2 = a.s2 + row % a.mc;
+            i1 = a.s1 + row / a.mc;
             i0 = 0;
         }
         const double kA = a.P == 1 ? a.ktab[0][i0] : a.ktab[2][i2];
@@ -805,6 +989,73 @@ pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int
             }
         }
     }
+}
+
+// ---- collective reductions over the independent modes ------------------------------------------------
+// sum over the stored half-complex modes of conj(b) * a * w, w = 2 for 0 < k_last < N/2 (the mode stands
+// for itself and its Hermitian conjugate), 1 for k_last = 0 and N/2 (BaseComplexField._expand_hermitian,
+// pm.py:911-918; cdot pm.py:945-974, cnorm pm.py:920-943 with the default norm).  One warp per row of the
+// contiguous axis as in pmb_k_transfer; float64 accumulation; per-block partial sums, added on the host.
+template <typename C>
+__global__ void __launch_bounds__(256)
+pmb_k_cdot(const C *__restrict__ a, const C *__restrict__ b, int64_t nrows, int64_t rowlen, int P, int64_t mc, int64_t s2,
+           int64_t nlast, double2 *partial)
+{
+    __shared__ double sh[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double re = 0, im = 0;
+    const int64_t nyq = nlast / 2;
+    for (int64_t row = (int64_t) blockIdx.x * 8 + warp; row < nrows; row += (int64_t) gridDim.x * 8) {
+        const int64_t i2row = P == 1 ? 0 : s2 + row % mc;
+        for (int64_t c = lane; c < rowlen; c += 32) {
+            const int64_t i2 = P == 1 ? c : i2row;
+            const double w = (i2 != 0 && i2 != nyq) ? 2.0 : 1.0;
+            const C x = a[row * rowlen + c], y = b[row * rowlen + c];
+            // conj(y) * x
+            re += w * ((double) y.x * (double) x.x + (double) y.y * (double) x.y);
+            im += w * ((double) y.x * (double) x.y - (double) y.y * (double) x.x);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (lane == 0) { sh[0][warp] = re; sh[1][warp] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0, i = 0;
+        for (int k = 0; k < 8; k++) { r += sh[0][k]; i += sh[1][k]; }
+        partial[blockIdx.x] = make_double2(r, i);
+    }
+}
+
+extern "C" int pmb_cdot(pmb_fft *f, const void *a, const void *b, double *result_h)
+{
+    PMB_REQUIRE(f && a && b && result_h, "null argument");
+    pmb_ctx *ctx = f->ctx;
+    result_h[0] = result_h[1] = 0;
+    int64_t nrows, rowlen;
+    if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
+    else { nrows = f->m1 * f->mc; rowlen = f->n[0]; }
+    if (nrows == 0 || rowlen == 0) return PMB_OK;
+    int64_t grid = (nrows + 7) / 8;
+    const int64_t cap = (int64_t) ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    void *partial;
+    PMB_CHECK(pmb_scratch(ctx, sizeof(double2) * grid, &partial));
+    if (f->elsize == 8)
+        pmb_k_cdot<double2><<<(int) grid, 256, 0, ctx->stream>>>((const double2 *) a, (const double2 *) b, nrows, rowlen, f->P, f->mc, f->s2, f->n[2], (double2 *) partial);
+    else
+        pmb_k_cdot<float2><<<(int) grid, 256, 0, ctx->stream>>>((const float2 *) a, (const float2 *) b, nrows, rowlen, f->P, f->mc, f->s2, f->n[2], (double2 *) partial);
+    PMB_LAUNCH_CHECK(ctx);
+    double2 *h = (double2 *) malloc(sizeof(double2) * grid);
+    if (!h) return PMB_ENOMEM;
+    cudaError_t e = cudaMemcpyAsync(h, partial, sizeof(double2) * grid, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(h); return pmb_cuda_fail(e, "cdot copy", __FILE__, __LINE__); }
+    for (int64_t i = 0; i < grid; i++) { result_h[0] += h[i].x; result_h[1] += h[i].y; }
+    free(h);
+    return PMB_OK;
 }
 
 extern "C" int pmb_transfer(pmb_fft *f, int kind, int dir, const double *params_h, const double *boxsize_h,
@@ -875,12 +1126,12 @@ extern "C" int pmb_transfer_scaled(pmb_fft *f, int kind, int dir, const double *
     a.kind = kind; a.ndim = f->ndim; a.P = f->P; a.dd = dd;
     for (int d = 0; d < 3; d++) { a.n[d] = f->n[d]; a.ktab[d] = (const double *) dev + off[d]; }
     a.mtab = (const double *) dev + ntab;
-    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1;
+    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1; a.s2 = f->s2; a.mc = f->mc;
     a.p0 = params_h ? params_h[0] : 0.0;
     a.pre = prefactor;
     int64_t nrows, rowlen;
     if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
-    else { nrows = f->m1 * f->nc; rowlen = f->n[0]; }
+    else { nrows = f->m1 * f->mc; rowlen = f->n[0]; }
     if (nrows == 0 || rowlen == 0) return PMB_OK;
     int64_t grid = (nrows + 7) / 8;
     const int64_t cap = (int64_t) ctx->sm_count * 8;

@@ -25,6 +25,11 @@ struct pmb_ctx {
     int sm_count;
     cudaStream_t stream;
     cudaEvent_t t0[PMB_NTIMERS], t1[PMB_NTIMERS];
+    // copy streams (1: host -> device, 2: device -> host) and the events that order them against the
+    // compute stream (0); created on first use (pmb_memcpy_*_async, pmb_stream_*)
+    cudaStream_t copy_stream[2];
+    cudaEvent_t sev[PMB_NTIMERS];
+    int streams_ready;
     int64_t launches;
     // growable scratch (deterministic paint, routing, pack buffers)
     void *scratch;

@@ -171,6 +171,13 @@ class Layout(object):
                                          recv.ptr, rc.ctypes.data, ro.ctypes.data, int(itemsize)))
         return recv
 
+    def _remote_offsets(self, offsets, selfcount):
+        """offsets of the per-rank segments in a buffer that leaves the segment of this rank out"""
+        off = numpy.array(offsets, dtype='i8')
+        off[self.comm.rank + 1:] -= int(selfcount)
+        off[self.comm.rank] = 0
+        return off
+
     def _exchange(self, data):
         ddata, dtype, trailing, was_host = self._to_device_records(
             data, self.sendlength, 'the length of data does not match that used to build the layout')
@@ -190,16 +197,18 @@ class Layout(object):
             # records that stay on this rank are gathered straight into their place in the receive
             # buffer; only what really leaves is packed into `send` and goes through NCCL
             recv = DeviceArray.empty((int(self.recvlength), itemsize), 'u1')
-            send = DeviceArray.empty((nsend, itemsize), 'u1')
             s0, sn = int(self.sendoffsets[me]), int(self.sendcounts[me])
+            # the send buffer holds only what leaves: [records for ranks < me | records for ranks > me]
+            send = DeviceArray.empty((max(nsend - sn, 1), itemsize), 'u1')
+            soff = self._remote_offsets(self.sendoffsets, sn)
             ip = self._indices_ptr()
             for a, b, dst in ((0, s0, send.ptr), (s0, s0 + sn, recv.ptr + int(self.recvoffsets[me]) * itemsize),
-                              (s0 + sn, nsend, send.ptr + (s0 + sn) * itemsize)):
+                              (s0 + sn, nsend, send.ptr + s0 * itemsize)):
                 if b > a:
                     src_idx = None if ip is None else ip + 4 * a
                     src = ddata.ptr + (a * itemsize if ip is None else 0)
                     _lib.check(ctx.lib.pmb_take(ctx.handle, src, itemsize, src_idx, b - a, dst))
-            self._alltoallv(ctx, send, self.sendcounts, self.sendoffsets, recv,
+            self._alltoallv(ctx, send, self.sendcounts, soff, recv,
                             self.recvcounts, self.recvoffsets, itemsize, skip_self=True)
         out = DeviceArray((int(self.recvlength),) + tuple(trailing), dtype, ptr=recv.ptr, base=recv, ctx=ctx)
         if was_host:
@@ -242,9 +251,12 @@ class Layout(object):
         if P == 1:
             back = ddata
         else:
-            back = DeviceArray.empty((nback, max(itemsize, 1)), 'u1')
+            # only the ghosts other ranks hold come back; the block of this rank is read where it lies
+            sn = int(self.sendcounts[me])
+            back = DeviceArray.empty((max(nback - sn, 1), max(itemsize, 1)), 'u1')
+            boff = self._remote_offsets(self.sendoffsets, sn)
             back = self._alltoallv(ctx, ddata, self.recvcounts, self.recvoffsets, back,
-                            self.sendcounts, self.sendoffsets, itemsize, skip_self=True)
+                            self.sendcounts, boff, itemsize, skip_self=True)
         full_dtype = numpy.dtype((dtype, tuple(trailing)))
 
         if self.sendlength == 0:
@@ -267,10 +279,12 @@ class Layout(object):
             offs = numpy.zeros(self.comm.size + 1, dtype='i8')
             offs[1:] = numpy.cumsum(self.sendcounts)
             segs = (ctypes.c_void_p * P)()
-            for q in range(P):
-                segs[q] = back.ptr + int(offs[q]) * itemsize
             if P > 1:
+                for q in range(P):
+                    segs[q] = back.ptr + int(boff[q]) * itemsize
                 segs[me] = ddata.ptr + int(self.recvoffsets[me]) * itemsize
+            else:
+                segs[0] = back.ptr
             _lib.check(ctx.lib.pmb_gather_sum_segments(ctx.handle, segs, dtype.itemsize, ncomp, self._indices_ptr(),
                                                        offs.ctypes.data, P, int(self.sendlength),
                                                        dout.ptr, dout.dtype.itemsize))
@@ -281,10 +295,18 @@ class Layout(object):
             out[...] = dout.to_host()
             return out
 
-        # the remaining modes are host-side bookkeeping on the returned ghosts (never on the force path)
-        if P > 1 and self.sendcounts[me] > 0:
-            ctx.d2d(back.ptr + int(self.sendoffsets[me]) * itemsize, ddata.ptr + int(self.recvoffsets[me]) * itemsize,
-                    int(self.sendcounts[me]) * itemsize)
+        # the remaining modes are host-side bookkeeping on the returned ghosts (never on the force path):
+        # assemble the full returned buffer (rank order), the block of this rank from where it lies
+        if P > 1:
+            full = DeviceArray.empty((nback, max(itemsize, 1)), 'u1')
+            s0 = int(self.sendoffsets[me])
+            if s0 > 0:
+                ctx.d2d(full.ptr, back.ptr, s0 * itemsize)
+            if sn > 0:
+                ctx.d2d(full.ptr + s0 * itemsize, ddata.ptr + int(self.recvoffsets[me]) * itemsize, sn * itemsize)
+            if nback - s0 - sn > 0:
+                ctx.d2d(full.ptr + (s0 + sn) * itemsize, back.ptr + s0 * itemsize, (nback - s0 - sn) * itemsize)
+            back = full
         recvbuffer = DeviceArray((nback,) + tuple(trailing), dtype, ptr=back.ptr, base=back, ctx=ctx).to_host()
         indices = self.indices
         if mode == 'all':

@@ -542,6 +542,14 @@ class RealField(Field):
         """ Collective sum of the entire mesh (reference pm.py:725-739). """
         if dtype is None:
             dtype = self.dtype
+        if numpy.dtype(dtype) == self.dtype and self.ndim <= 3:
+            # device reduction (float64 accumulation), then the scalar allreduce
+            a = self._device(absorb=True)
+            out = ctypes.c_double(0.0)
+            sz = (ctypes.c_int64 * 3)(*a.shape)
+            st = (ctypes.c_int64 * 3)(*a.strides)
+            _lib.check(self.pm.ctx.lib.pmb_field_sum(self.pm.ctx.handle, a.ptr, a.dtype.itemsize, len(a.shape), sz, st, ctypes.byref(out)))
+            return self.pm.comm.allreduce(self.dtype.type(out.value * self._pending))
         v = self.readonly_value()
         arg = numpy.argsort(self._layout_strides)
         sum1 = v.transpose(arg[::-1])
@@ -630,6 +638,15 @@ class RealField(Field):
 
     def cdot(self, other):
         self._check_compatible(other)
+        if isinstance(other, RealField) and other.pm is self.pm and self.ndim <= 3:
+            # sum(self * other) on the device (pmb_field_dot), then the scalar allreduce (pm.py:897-902)
+            a, b = self._device(), other._device()
+            if a.strides == b.strides and a.shape == b.shape:
+                out = ctypes.c_double(0.0)
+                sz = (ctypes.c_int64 * 3)(*a.shape)
+                st = (ctypes.c_int64 * 3)(*a.strides)
+                _lib.check(self.pm.ctx.lib.pmb_field_dot(self.pm.ctx.handle, a.ptr, b.ptr, a.dtype.itemsize, len(a.shape), sz, st, ctypes.byref(out)))
+                return self.pm.comm.allreduce(self.dtype.type(out.value * self._pending * other._pending))
         return self.pm.comm.allreduce(numpy.sum(self[...] * other[...]))
 
     def cnorm(self):
@@ -660,8 +677,23 @@ class BaseComplexField(Field):
         y += mask * y
         return y
 
-    def cnorm(self, metric=None, norm=lambda x: x.real ** 2 + x.imag ** 2):
+    def _device_cdot(self, other):
+        """ rank-local sum over the stored modes of conj(other) * self, conjugate modes counted (pmb_cdot) """
+        a, b = self._device(), other._device()
+        res = (ctypes.c_double * 2)(0.0, 0.0)
+        _lib.check(self.pm.ctx.lib.pmb_cdot(self.pm._plan, a.ptr, b.ptr, res))
+        f = self._pending * other._pending
+        return self.dtype.type(complex(res[0] * f, res[1] * f))
+
+    _default_norm = None
+
+    def cnorm(self, metric=None, norm=None):
         """ compute the norm collectively; the conjugates are added too (reference pm.py:920-943) """
+        if norm is None:
+            if metric is None and self.compressed:
+                # |y|^2 summed on the device (float64 accumulation)
+                return self.pm.comm.allreduce(self._device_cdot(self).real)
+            norm = lambda x: x.real ** 2 + x.imag ** 2
         def filter2(k, y):
             y = norm(y)
             if metric is not None:
@@ -677,6 +709,8 @@ class BaseComplexField(Field):
         if isinstance(other, Field):
             if not isinstance(other, _gettype(self)):
                 raise TypeError("type of two operands of cdot must be the same type")
+        if metric is None and isinstance(other, BaseComplexField) and other.pm is self.pm and self.compressed:
+            return self.pm.comm.allreduce(self._device_cdot(other))
         r = self.pm.create(type=_gettype(self), value=other)
         r.value[...] = numpy.conj(r.value[...])
         r.value[...] *= self.value
@@ -875,13 +909,24 @@ class ParticleMesh(object):
         if len(Nmesh) == 1 and self.comm.size != 1:
             raise ValueError("Running 1d transforms on multiple ranks is not supported")
         if np is None:
+            # the reference defaults to pfft.split_size_2d for 3-D meshes (pm.py:1319-1327); on one NVSwitch
+            # node (<= 8 GPUs) slabs need one global transpose per transform instead of two, so they are the
+            # default here.  np=[P0, P1] selects pencils.
             np = [] if len(Nmesh) == 1 else [self.comm.size]
-        np = [int(p) for p in np if int(p) != 1] or ([] if len(Nmesh) == 1 else [1])
-        if len(np) > 1:
-            raise NotImplementedError("pencil (2-D) process meshes are not implemented; use np=[P] slabs")
-        if len(np) == 1 and np[0] != self.comm.size:
+        np = [int(p) for p in np]
+        if len(np) > len(Nmesh) - 1 and len(Nmesh) > 1:
+            raise ValueError("process mesh of %d dimensions for a %d-dimensional mesh" % (len(np), len(Nmesh)))
+        if len(np) > 2:
+            raise NotImplementedError("process meshes of more than 2 dimensions are not implemented")
+        if int(numpy.prod(np, dtype='i8')) != self.comm.size and not (len(np) == 0 and self.comm.size == 1):
             raise ValueError("np must multiply to the communicator size")
+        # a trailing (or leading) 1 makes it a slab decomposition
+        if len(np) == 2 and np[1] == 1:
+            np = [np[0]]
         self.np = np
+        self._procmesh = (np[0], np[1]) if len(np) == 2 else (self.comm.size, 1)
+        if self._procmesh[1] > 1 and len(Nmesh) != 3:
+            raise NotImplementedError("pencil decompositions are implemented for 3-D meshes")
         self._use_padded = True
 
         dtype = numpy.dtype(dtype)
@@ -900,7 +945,8 @@ class ParticleMesh(object):
         self.comm.ensure_device_comm(self.ctx)
         nm = (ctypes.c_int64 * 3)(*[int(n) for n in self.Nmesh])
         plan = ctypes.c_void_p()
-        _lib.check(self.ctx.lib.pmb_fft_create(self.ctx.handle, self.ndim, nm, dtype.itemsize, ctypes.byref(plan)))
+        npm = (ctypes.c_int * 2)(*self._procmesh)
+        _lib.check(self.ctx.lib.pmb_fft_create_np(self.ctx.handle, self.ndim, nm, dtype.itemsize, npm, ctypes.byref(plan)))
         self._plan = plan
         arrs = [(ctypes.c_int64 * 3)() for _ in range(6)]
         ra, ca = ctypes.c_int64(), ctypes.c_int64()
@@ -913,9 +959,10 @@ class ParticleMesh(object):
         edges = []
         for d in range(self.ndim):
             n = int(self.Nmesh[d])
-            if d == 0 and self.comm.size > 1:
-                blk = (n + self.comm.size - 1) // self.comm.size
-                edges.append(numpy.array([min(r * blk, n) for r in range(self.comm.size + 1)], dtype='intp'))
+            parts = self._procmesh[d] if d < 2 else 1
+            if parts > 1:
+                blk = (n + parts - 1) // parts          # FFTW / PFFT default block: ceil(n / P)
+                edges.append(numpy.array([min(r * blk, n) for r in range(parts + 1)], dtype='intp'))
             else:
                 edges.append(numpy.array([0, n], dtype='intp'))
         self._i_edges = edges

@@ -132,6 +132,75 @@ def main():
         comm.Barrier()
         if r == 0:
             print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
+    # 7. pencil (2-D) process meshes, the reference's default for 3-D fields (pm.py:1319-1327): real space
+    #    split along axes (0, 1), complex space along (1, 2); everything against the serial oracle
+    meshes = {2: [[1, 2]], 4: [[2, 2], [1, 4]], 8: [[2, 4], [4, 2]]}.get(P, [])
+    for np_ in meshes:
+        for n3, res, dtype in (((16, 20, 24), "cic", "f8"), ((12, 12, 12), "tsc", "f4")):
+            L = 100.0
+            tol = 1e-6 if dtype == "f8" else 2e-4
+            pm = ParticleMesh(BoxSize=L, Nmesh=list(n3), dtype=dtype, resampler=res, comm=comm, np=np_)
+            start, shape = pm._layout["i_start"], pm._layout["i_shape"]
+            c0, c1 = r // np_[1], r % np_[1]
+            for d, (parts, c) in enumerate(((np_[0], c0), (np_[1], c1))):
+                blk = -(-n3[d] // parts)
+                assert start[d] == min(c * blk, n3[d]) and shape[d] == min((c + 1) * blk, n3[d]) - start[d]
+            sl = tuple(slice(int(a), int(a + b)) for a, b in zip(start, shape))
+            full = numpy.random.default_rng(31).uniform(-1, 1, n3).astype(dtype)
+            ck_full = oracle.r2c(full.astype("f8"))
+            rho = pm.create("real", value=full[sl])
+            rhok = rho.r2c()
+            osl = tuple(slice(int(a), int(a + b)) for a, b in zip(rhok.start, rhok.shape))
+            assert rhok.shape[0] == n3[0] and rhok.start[0] == 0
+            assert rel(rhok.value, ck_full[osl]) < tol, ("pencil r2c", np_, rel(rhok.value, ck_full[osl]))
+            assert rel(rhok.c2r().value, full[sl]) < tol
+            assert rel(rhok.value, ck_full[osl]) < tol                     # input preserved
+            cip = pm.create("real", value=full[sl]).r2c(out=Ellipsis)
+            assert rel(cip.value, ck_full[osl]) < tol
+            assert rel(cip.c2r(out=Ellipsis).value, full[sl]) < tol
+            # cnorm / cdot over the independent modes: device reduction + allreduce == numpy on the whole field
+            w = numpy.full(n3[2] // 2 + 1, 2.0)
+            w[0] = 1.0
+            if n3[2] % 2 == 0:
+                w[-1] = 1.0
+            want_norm = float((abs(ck_full) ** 2 * w).sum())
+            assert abs(rhok.cnorm() - want_norm) < 1e-5 * want_norm
+            # transfer + c2r on the pencil layout
+            Lb = [L] * 3
+            for d in range(3):
+                fr_full = oracle.c2r(oracle.transfer(ck_full, list(n3), Lb, "gravity_fd4", d), list(n3))
+                f = rhok.apply(T.GravityFD4(d)).c2r()
+                assert rel(f.value, fr_full[sl]) < tol, ("pencil transfer", np_, d)
+            # white noise is independent of the partition
+            cdt = "complex128" if dtype == "f8" else "complex64"
+            wn_full = oracle.whitenoise(numpy.zeros((n3[0], n3[1], n3[2] // 2 + 1), dtype=cdt), 0, n3, 4242, False)
+            wn = pm.generate_whitenoise(4242)
+            wsl = tuple(slice(int(a), int(a + b)) for a, b in zip(wn.start, wn.shape))
+            if wn.size:
+                assert abs(wn.value - wn_full[wsl]).max() < (1e-13 if dtype == "f8" else 5e-7)
+            # routing on the 2-D domain grid, decomposed paint, readout with the ghost sum
+            allpos = [numpy.random.default_rng(500 + q).uniform(-0.2 * L, 1.2 * L, (2000 + 50 * q, 3)) for q in range(P)]
+            scale = numpy.array(n3) / L
+            lays = [oracle.decompose(allpos[q], pm.domain.edges, P, smoothing=0.5 * pm.resampler.support,
+                                     assign=pm.domain.DomainAssign, scale=scale) for q in range(P)]
+            layout = pm.decompose(allpos[r])
+            assert numpy.array_equal(layout.sendcounts, lays[r][0]) and numpy.array_equal(layout.indices, lays[r][1])
+            want_pos = oracle.exchange_all(allpos, lays)[r]
+            rho = pm.paint(allpos[r], layout=layout, mode="deterministic")
+            blockv = numpy.zeros(tuple(shape), dtype)
+            oracle.paint(blockv, want_pos, res, scale=scale, translate=-start, period=list(n3))
+            assert numpy.array_equal(rho.value, blockv), "decomposed paint on pencils differs"
+            serial = numpy.zeros(n3, dtype)
+            oracle.paint(serial, numpy.concatenate(allpos), res, scale=scale, period=list(n3))
+            assert rel(blockv, serial[sl]) < (1e-12 if dtype == "f8" else 1e-5)
+            got = rho.readout(allpos[r], layout=layout)
+            want = oracle.readout(serial, allpos[r], res, scale=scale, period=list(n3))
+            assert rel(got, want) < tol
+            comm.Barrier()
+            if r == 0:
+                print("pencil ok: np=%s n=%s %s %s" % (np_, n3, res, dtype))
+            del pm, rho, rhok, cip, f, wn, layout
+
     # a second mesh of a configuration used before takes the pooled peer-memory landing buffers again
     del pm
     for rep in range(2):
