@@ -17,13 +17,74 @@ def _density_ratio(src_pm, dst_pm):
 
 
 # ---------------------------------------------------------------------------------------------- C order
+# The reference moves values between the field layout and the global C order with mpsort (a distributed
+# sort: pm.py:418-420, 444-446, 513).  The keys here are global C indices, so no sort is needed: the owner of
+# every index is known from the chunk sizes, and the values travel in one exchange.  These are host-side
+# I/O-order operations (they work on the numpy mirror of a field, like the reference); the exchange goes
+# through the communicator's object collectives.
 def c_order_is_local(field):
     """True when the global C-order ravel of the field, cut into pieces of the local sizes, is every
-    rank's own values in local C order: one rank, or a field distributed along axis 0 only (the
-    real-space slabs of this engine).  The reference sorts with mpsort in general (pm.py:418-420);
-    here the one layout that would need the exchange is the transposed complex field on P > 1 ranks."""
-    from .pm import RealField
-    return field.pm.comm.size == 1 or isinstance(field, RealField)
+    rank's own values in local C order: one rank, or a field distributed along axis 0 only (real-space
+    slabs)."""
+    if field.pm.comm.size == 1:
+        return True
+    return all(int(field.shape[d]) == int(field.cshape[d]) for d in range(1, field.ndim))
+
+
+def _alltoall(comm, pieces):
+    """pieces[q] goes to rank q; returns what every rank sent to this one, in rank order"""
+    if comm.size == 1:
+        return [pieces[0]]
+    everything = comm.allgather(pieces)
+    return [everything[src][comm.rank] for src in range(comm.size)]
+
+
+def _global_c_index(field):
+    """global C-order index of every local element (local logical C order), int64"""
+    idx = numpy.zeros(tuple(int(n) for n in field.shape), dtype='i8')
+    stride = 1
+    for d in reversed(range(field.ndim)):
+        r = numpy.arange(int(field.start[d]), int(field.start[d]) + int(field.shape[d]), dtype='i8') * stride
+        shp = [1] * field.ndim
+        shp[d] = -1
+        idx = idx + r.reshape(shp)
+        stride *= int(field.cshape[d])
+    return idx.ravel()
+
+
+def _chunk_offsets(comm, n):
+    sizes = numpy.array(comm.allgather(int(n)), dtype='i8')
+    return numpy.concatenate([[0], numpy.cumsum(sizes)])
+
+
+def dist_put(comm, values, gindex, outlen):
+    """out[g - first] = v for every (g, v) of every rank, where the global C order is cut into chunks of
+    `outlen` elements per rank (mpsort.sort by a key that is the global index)"""
+    offs = _chunk_offsets(comm, outlen)
+    dest = numpy.searchsorted(offs[1:], gindex, side='right')
+    pieces = []
+    for q in range(comm.size):
+        m = dest == q
+        pieces.append((gindex[m] - offs[q], values[m]))
+    out = numpy.empty(int(outlen), dtype=values.dtype)
+    for li, vv in _alltoall(comm, pieces):
+        out[li] = vv
+    return out
+
+
+def dist_take(comm, chunk, gindex):
+    """chunks[...][gindex] for a 1-D array distributed in rank order as `chunk` (mpsort.take / permute)"""
+    chunk = numpy.asarray(chunk)
+    offs = _chunk_offsets(comm, len(chunk))
+    gindex = numpy.asarray(gindex, dtype='i8')
+    owner = numpy.searchsorted(offs[1:], gindex, side='right')
+    where = [numpy.flatnonzero(owner == q) for q in range(comm.size)]
+    asked = _alltoall(comm, [gindex[w] - offs[q] for q, w in enumerate(where)])
+    answers = _alltoall(comm, [chunk[a] for a in asked])
+    out = numpy.empty(len(gindex), dtype=chunk.dtype)
+    for w, v in zip(where, answers):
+        out[w] = v
+    return out
 
 
 def _flat_target(field, out):
@@ -42,10 +103,10 @@ def _flat_target(field, out):
 def ravel(field, out=None):
     """reference pm.py:389-424; out: a flatiter / array (its .flat is used) or Ellipsis for in place"""
     out = _flat_target(field, out)
-    if not c_order_is_local(field):
-        raise NotImplementedError("ravel of a transposed complex field on more than one rank needs the "
-                                  "distributed sort (mpsort); not built")
-    out[...] = numpy.array(field.value.flat)
+    if c_order_is_local(field):
+        out[...] = numpy.array(field.value.flat)
+    else:
+        out[...] = dist_put(field.pm.comm, numpy.array(field.value.flat), _global_c_index(field), int(field.size))
     return out
 
 
@@ -55,10 +116,12 @@ def unravel(field, flatiter):
         flatiter = flatiter.flat
     assert isinstance(flatiter, numpy.flatiter)
     assert field.pm.comm.allreduce(len(flatiter)) == field.csize
-    if not c_order_is_local(field):
-        raise NotImplementedError("unravel of a transposed complex field on more than one rank needs the "
-                                  "distributed sort (mpsort); not built")
-    field.value.flat[...] = numpy.array(flatiter)
+    if field.pm.comm.size == 1:
+        field.value.flat[...] = numpy.array(flatiter)
+    else:
+        v = field.value
+        v.flat[...] = dist_take(field.pm.comm, numpy.array(flatiter), _global_c_index(field))
+        field.value = v
 
 
 # ------------------------------------------------------------------------------------- Fourier resample
@@ -80,12 +143,11 @@ def fourier_resample(field, out):
     if all(out.Nmesh == field.Nmesh):
         # same mesh: only the representation changes
         field.cast(type=_gettype(out), out=out)
-    if field.pm.comm.size > 1:
-        raise NotImplementedError("Fourier-space resample on more than one rank needs the distributed take "
-                                  "(mpsort); not built")
     ndim = field.ndim
     src = field.cast(type=TransposedComplexField)
     dest = out.pm.create(type=TransposedComplexField, base=out._base, value=0)
+    if field.pm.comm.size > 1:
+        return _fourier_resample_distributed(src, dest, out)
     sv = src.value
     dv = numpy.zeros(dest.shape, dtype=dest.dtype)
     carried = numpy.ones(dest.shape, dtype='?')
@@ -105,6 +167,40 @@ def fourier_resample(field, out):
     for mesh in (dest.Nmesh, src.Nmesh):
         nyq = functools.reduce(numpy.bitwise_or, [ii == n // 2 for ii, n in zip(i, mesh)])
         dv[numpy.broadcast_to(nyq, dest.shape)] = 0
+    dest.value = dv
+    if isinstance(out, RealField):
+        dest.c2r(out)
+    elif out is not dest:
+        out.value = dest.value
+    return out
+
+
+def _fourier_resample_distributed(src, dest, out):
+    """the same on P > 1 ranks: the source modes are fetched from their owners with a distributed take on
+    the C-order ravel of the source (reference pm.py:493-516)"""
+    from .pm import RealField
+    comm = src.pm.comm
+    ndim = src.ndim
+    flat = numpy.empty(int(src.size), dtype=src.dtype)
+    ravel(src, out=flat)
+    carried = numpy.ones(tuple(int(n) for n in dest.shape), dtype='?')
+    gidx = numpy.zeros(carried.shape, dtype='i8')
+    stride = 1
+    for d in reversed(range(ndim)):
+        t = mode_table(src.Nmesh[d], dest.Nmesh[d])[numpy.r_[dest.slices[d]]]
+        ok = (t >= 0) & (t < src.cshape[d])
+        shp = [-1 if dd == d else 1 for dd in range(ndim)]
+        carried &= ok.reshape(shp)
+        gidx = gidx + (numpy.where(ok, t, 0).astype('i8') * stride).reshape(shp)
+        stride *= int(src.cshape[d])
+    dv = numpy.zeros(carried.shape, dtype=dest.dtype)
+    dv[carried] = dist_take(comm, flat, gidx[carried])
+    i = dest.i
+    selfconj = functools.reduce(numpy.bitwise_and, [(n - ii) % n == ii for ii, n in zip(i, dest.Nmesh)])
+    dv.imag[numpy.broadcast_to(selfconj, dv.shape)] = 0
+    for mesh in (dest.Nmesh, src.Nmesh):
+        nyq = functools.reduce(numpy.bitwise_or, [ii == n // 2 for ii, n in zip(i, mesh)])
+        dv[numpy.broadcast_to(nyq, dv.shape)] = 0
     dest.value = dv
     if isinstance(out, RealField):
         dest.c2r(out)

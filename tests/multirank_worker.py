@@ -129,6 +129,37 @@ def main():
             got = numpy.stack([f.to_host() for f in Fmine], axis=1)
             assert rel(got, Fall[off:off + len(allpos[r])]) < 1e-6
 
+        # 6b. I/O order: ravel / unravel of the transposed complex field and the Fourier resample go through the
+        #     distributed index exchange (the reference's mpsort, pm.py:389-448, 479-547)
+        if dtype == "f8":
+            import functools
+            from pmesh_b200.resample import mode_table
+            chunk = numpy.empty(int(rhok.size), dtype=rhok.dtype)
+            rhok.ravel(out=chunk)
+            whole = numpy.concatenate(comm.allgather(chunk))
+            assert numpy.array_equal(whole, ck_full.astype(rhok.dtype).ravel()) or rel(whole, ck_full.ravel()) < 1e-12
+            other = pm.create("complex")
+            other.unravel(chunk)
+            assert numpy.array_equal(other.value, rhok.value)
+            n2 = n // 2
+            pm2 = ParticleMesh(BoxSize=L, Nmesh=[n2, n2, n2], dtype=dtype, resampler=res, comm=comm)
+            small = pm2.create("complex")
+            rhok.resample(small)
+            tabs = [mode_table(n, n2) for _ in range(3)]
+            tabs[2] = tabs[2][:n2 // 2 + 1]
+            ok = [(t >= 0) & (t < m) for t, m in zip(tabs, ck_full.shape)]
+            want_s = ck_full[numpy.ix_(*[numpy.where(o, t, 0) for o, t in zip(ok, tabs)])]
+            want_s = numpy.where(ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :], want_s, 0)
+            ii = numpy.meshgrid(*[numpy.arange(m) for m in want_s.shape], indexing="ij", sparse=True)
+            selfconj = functools.reduce(numpy.bitwise_and, [(n2 - i_) % n2 == i_ for i_ in ii])
+            want_s.imag[numpy.broadcast_to(selfconj, want_s.shape)] = 0
+            for mm in (n2, n):
+                nyq = functools.reduce(numpy.bitwise_or, [i_ == mm // 2 for i_ in ii])
+                want_s[numpy.broadcast_to(nyq, want_s.shape)] = 0
+            sl2 = tuple(slice(int(a), int(a + b)) for a, b in zip(small.start, small.shape))
+            assert rel(small.value, want_s[sl2]) < 1e-12, "distributed Fourier resample"
+            del pm2, small, other
+
         comm.Barrier()
         if r == 0:
             print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
@@ -196,6 +227,15 @@ def main():
             got = rho.readout(allpos[r], layout=layout)
             want = oracle.readout(serial, allpos[r], res, scale=scale, period=list(n3))
             assert rel(got, want) < tol
+            # I/O order on pencils: neither the real nor the complex field is C-order local
+            for fld, whole_want in ((pm.create("real", value=full[sl]), full), (rhok, ck_full.astype(rhok.dtype))):
+                chunk = numpy.empty(int(fld.size), dtype=fld.dtype)
+                fld.ravel(out=chunk)
+                whole = numpy.concatenate(comm.allgather(chunk))
+                assert rel(whole, whole_want.ravel()) < tol
+                back_f = pm.create(type(fld))
+                back_f.unravel(chunk)
+                assert numpy.array_equal(back_f.value, fld.value)
             comm.Barrier()
             if r == 0:
                 print("pencil ok: np=%s n=%s %s %s" % (np_, n3, res, dtype))

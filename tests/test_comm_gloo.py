@@ -64,6 +64,19 @@ WORKER = textwrap.dedent("""
     oracle.paint(serial, numpy.concatenate([allpos[0], allpos[1]]), "cic", period=[n, n, n])
     assert abs(full - serial).max() < 1e-13, abs(full - serial).max()
     assert abs(full.sum() - 800) < 1e-9
+    # I/O-order exchange behind ravel / unravel / Fourier resample on P > 1 (resample.dist_put / dist_take,
+    # the reference's mpsort.sort / permute / take): a global array of 37 items cut into chunks of 20 + 17
+    from pmesh_b200 import resample as R
+    whole = numpy.random.default_rng(9).uniform(size=37)
+    lens = [20, 17]
+    first = sum(lens[:r])
+    mine_g = numpy.arange(37)[r::2]                      # this rank holds the items with g mod 2 == r, any order
+    mine_g = mine_g[numpy.random.default_rng(r).permutation(len(mine_g))]
+    chunk = R.dist_put(comm, whole[mine_g], mine_g, lens[r])
+    assert numpy.array_equal(chunk, whole[first:first + lens[r]])
+    want = numpy.random.default_rng(20 + r).integers(0, 37, size=25)
+    assert numpy.array_equal(R.dist_take(comm, chunk, want), whole[want])
+    assert len(R.dist_take(comm, chunk, numpy.zeros(0, dtype="i8"))) == 0
     sys.stdout.write("rank%%d-ok\\n" %% r); sys.stdout.flush()
 """)
 
