@@ -134,6 +134,16 @@ int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a);
  * positions).  a->mesh / a->out / a->out_stride are ignored; results are those of nfields pmb_readout calls. */
 int pmb_readout_multi(pmb_ctx *ctx, const pmb_resample_args *a, int nfields, const void *const *meshes_h,
                       void *const *outs_h, const int64_t *out_strides_h);
+/* pmb_readout_multi fused with the ghost sum of Layout.gather('sum') (domain.py:208-318): of the npart local
+ * particles, [own_begin, own_begin + own_count) are the block this rank sent to itself; the value of own
+ * particle k goes straight to row own_index[k] of the float64 column own_outs_h[q] (the original particle
+ * order; the columns must be zero-filled: rows without an own copy stay 0), the values of the ghosts held
+ * for other ranks go to the compact float64 column ghost_outs_h[q] (npart - own_count rows, own block cut
+ * out) from which the reverse alltoallv takes them; pmb_gather_add_segments then adds what comes back.
+ * PMB_EUNSUPPORTED when the window / geometry has no fused kernel (callers use pmb_readout + pmb_gather_sum). */
+int pmb_readout_multi_gather(pmb_ctx *ctx, const pmb_resample_args *a, int nfields, const void *const *meshes_h,
+                             void *const *ghost_outs_h, void *const *own_outs_h, const int32_t *own_index,
+                             int64_t own_begin, int64_t own_count);
 /* fused value + ndim gradients in one neighbour sweep (paint_vjp / readout_vjp helper).
  * out_value may be NULL; out_grad is (npart, ndim) with byte strides gs0, gs1, element size out_elsize. */
 int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1);
@@ -231,6 +241,11 @@ int pmb_gather_sum(pmb_ctx *ctx, const void *data, int data_elsize, int ncomp, c
 int pmb_gather_sum_segments(pmb_ctx *ctx, const void *const *segments_h, int data_elsize, int ncomp,
                             const int32_t *indices, const int64_t *offsets_h, int nranks, int64_t nout,
                             void *out, int out_elsize);
+
+/* out[indices[j]] += data[j] over the segments of every rank but skip_rank, in rank order (float64 out) */
+int pmb_gather_add_segments(pmb_ctx *ctx, const void *const *segments_h, int data_elsize, int ncomp,
+                            const int32_t *indices, const int64_t *offsets_h, int nranks, int skip_rank,
+                            int64_t nout, void *out);
 
 /* ---- communicator (NCCL over NVLink), one rank per process ------------------------ */
 int pmb_comm_unique_id(char *id128_h);                      /* 128 bytes */

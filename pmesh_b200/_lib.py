@@ -62,10 +62,10 @@ SYMBOLS = [
     "pmb_malloc", "pmb_free", "pmb_malloc_host", "pmb_free_host", "pmb_memcpy_h2d", "pmb_memcpy_d2h",
     "pmb_memcpy_d2d", "pmb_memset", "pmb_memcpy_h2d_async", "pmb_memcpy_d2h_async", "pmb_stream_record", "pmb_stream_wait", "pmb_stream_sync", "pmb_mem_info", "pmb_timer_start", "pmb_timer_stop", "pmb_launch_count",
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
-    "pmb_paint", "pmb_readout", "pmb_readout_multi", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum", "pmb_field_dot",
+    "pmb_paint", "pmb_readout", "pmb_readout_multi", "pmb_readout_multi_gather", "pmb_readout_grad", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum", "pmb_field_dot",
     "pmb_axpy", "pmb_lincomb", "pmb_column_mod", "pmb_kick_drift", "pmb_dot",
     "pmb_particles_uniform", "pmb_particles_lattice", "pmb_particles_replicate",
-    "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments",
+    "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments", "pmb_gather_add_segments",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
     "pmb_fft_create", "pmb_fft_create_np", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_library_ms",
@@ -91,6 +91,7 @@ _ARGTYPES = {
     "pmb_window_query": [_I, _I, _P, _P], "pmb_window_fwindow": [_I, _I, _P, _P, _L],
     "pmb_paint": [_P, _P], "pmb_readout": [_P, _P], "pmb_readout_grad": [_P, _P, _P, _L, _L],
     "pmb_readout_multi": [_P, _P, _I, _P, _P, _P],
+    "pmb_readout_multi_gather": [_P, _P, _I, _P, _P, _P, _P, _L, _L],
     "pmb_field_fill": [_P, _P, _I, _I, _P, _P, _D], "pmb_field_scale": [_P, _P, _I, _I, _I, _P, _P, _D],
     "pmb_field_sum": [_P, _P, _I, _I, _P, _P, _P],
     "pmb_field_dot": [_P, _P, _P, _I, _I, _P, _P, _P],
@@ -107,6 +108,7 @@ _ARGTYPES = {
     "pmb_take": [_P, _P, _L, _P, _L, _P],
     "pmb_gather_sum": [_P, _P, _I, _I, _P, _P, _I, _L, _P, _I],
     "pmb_gather_sum_segments": [_P, _P, _I, _I, _P, _P, _I, _L, _P, _I],
+    "pmb_gather_add_segments": [_P, _P, _I, _I, _P, _P, _I, _I, _L, _P],
     "pmb_comm_unique_id": [_P], "pmb_comm_init_rank": [_P, _P, _I, _I], "pmb_comm_destroy": [_P],
     "pmb_comm_rank": [_P, _P, _P],
     "pmb_alltoallv": [_P, _P, _P, _P, _P, _P, _P, _L],

@@ -531,3 +531,27 @@ extern "C" int pmb_gather_sum_segments(pmb_ctx *ctx, const void *const *segments
     }
     return PMB_OK;
 }
+
+// out[indices[j]] += data[j] for the segments of every rank but `skip_rank`, in rank order: the ghosts that
+// came back through the reverse alltoallv are added to columns that already hold the rank's own results
+// (pmb_readout_multi_gather).  out is float64, (nout, ncomp) rows.
+extern "C" int pmb_gather_add_segments(pmb_ctx *ctx, const void *const *segments_h, int data_elsize, int ncomp,
+                                       const int32_t *indices, const int64_t *offsets_h, int nranks, int skip_rank,
+                                       int64_t nout, void *out)
+{
+    PMB_REQUIRE(ctx && offsets_h && segments_h && ncomp >= 1 && nout >= 0, "bad gather arguments");
+    PMB_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXRANKS, "gather supports 1..%d ranks", ROUTE_MAXRANKS);
+    PMB_REQUIRE(data_elsize == 4 || data_elsize == 8, "float32/float64 only");
+    if (nout == 0) return PMB_OK;
+    PMB_REQUIRE(out && indices, "null out / indices");
+    for (int r = 0; r < nranks; r++) {
+        if (r == skip_rank) continue;
+        const int64_t b = offsets_h[r], e = offsets_h[r + 1];
+        if (e <= b) continue;
+        PMB_REQUIRE(segments_h[r], "null data segment %d", r);
+        pmb_k_gather_pass<false><<<pmb_grid(ctx, (e - b) * ncomp, 256, 8), 256, 0, ctx->stream>>>(
+            segments_h[r], data_elsize, ncomp, indices, b, e, (double *) out);
+        PMB_LAUNCH_CHECK(ctx);
+    }
+    return PMB_OK;
+}

@@ -219,7 +219,7 @@ pmb_k_readout_cic32_perm(PmbGeom32 g, PmbParticles p, PmbFields f, int64_t npart
                         value += pmb_mesh_load<MeshT, false>((const char *) f.mesh[q], (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), policy)
                                  * ((Vx[a] * Vy[b]) * Vz[c]);
                     }
-            pmb_st_real_stream(f.out[q], i * f.out_stride[q], f.out_elsize, value);
+            pmb_store_result(f, q, i, value);
         }
     }
 }

@@ -866,9 +866,15 @@ extern "C" int pmb_readout(pmb_ctx *ctx, const pmb_resample_args *a)
 }
 
 // readout of up to 3 canvases of identical geometry at the same positions
+struct PmbGatherFuse {      // see PmbFields: results of the rank's own particles go straight to the gathered columns
+    void *const *own_outs;
+    const int32_t *own_index;
+    int64_t own_begin, own_count;
+};
+
 template <typename MeshT>
 static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, const void *const *meshes,
-                              void *const *outs, const int64_t *out_strides, bool *done)
+                              void *const *outs, const int64_t *out_strides, bool *done, const PmbGatherFuse *gf = NULL)
 {
     *done = false;
     PmbGeom g;
@@ -885,6 +891,12 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
     memset(&f, 0, sizeof(f));
     for (int q = 0; q < nf; q++) { f.mesh[q] = meshes[q]; f.out[q] = outs[q]; f.out_stride[q] = out_strides[q]; }
     f.out_elsize = a->out_elsize;
+    if (gf) {
+        for (int q = 0; q < nf; q++) f.out2[q] = (double *) gf->own_outs[q];
+        f.oidx = gf->own_index;
+        f.sel0 = gf->own_begin;
+        f.sel1 = gf->own_begin + gf->own_count;
+    }
     const uint32_t *perm;
     PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
     if (perm) {
@@ -927,6 +939,31 @@ extern "C" int pmb_readout_multi(pmb_ctx *ctx, const pmb_resample_args *a, int n
         PMB_CHECK(pmb_readout(ctx, &b));
     }
     return PMB_OK;
+}
+
+extern "C" int pmb_readout_multi_gather(pmb_ctx *ctx, const pmb_resample_args *a, int nfields, const void *const *meshes_h,
+                                        void *const *ghost_outs_h, void *const *own_outs_h, const int32_t *own_index,
+                                        int64_t own_begin, int64_t own_count)
+{
+    PMB_REQUIRE(ctx && a && meshes_h && ghost_outs_h && own_outs_h, "null argument");
+    PMB_REQUIRE(nfields >= 1 && nfields <= 3, "1..3 fields");
+    PMB_REQUIRE(own_begin >= 0 && own_count >= 0 && own_begin + own_count <= a->npart, "bad range of own particles");
+    PMB_REQUIRE(own_count == 0 || own_index, "null index of own particles");
+    PMB_REQUIRE(a->out_elsize == 8, "the fused ghost sum produces float64 columns");
+    pmb_resample_args b = *a;
+    b.mesh = (void *) meshes_h[0];
+    b.out = ghost_outs_h[0];
+    b.out_stride = 8;
+    PMB_CHECK(check_args(ctx, &b, 1));
+    if (a->npart == 0) return PMB_OK;
+    int64_t strides[3] = {8, 8, 8};
+    PmbGatherFuse gf = {own_outs_h, own_index, own_begin, own_count};
+    bool done = false;
+    if (a->mesh_elsize == 8) PMB_CHECK(readout_multi_impl<double>(ctx, a, nfields, meshes_h, ghost_outs_h, strides, &done, &gf));
+    else PMB_CHECK(readout_multi_impl<float>(ctx, a, nfields, meshes_h, ghost_outs_h, strides, &done, &gf));
+    if (done) return PMB_OK;
+    pmb_set_error("fused readout + ghost sum is available for the CIC window on 3-D meshes with >= 2^18 contiguous float64 positions");
+    return PMB_EUNSUPPORTED;
 }
 
 extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1)

@@ -48,7 +48,28 @@ struct PmbFields {
     void *out[3];
     int64_t out_stride[3];
     int out_elsize;
+    // fused ghost-sum routing of the results (Layout.gather('sum') without its pass over the particles):
+    // particles j in [sel0, sel1) are this rank's own (the block it sent to itself); their value goes
+    // straight to row oidx[j - sel0] of the float64 column out2[q] (the original particle order); every other
+    // particle is a ghost held for another rank: its value goes to the compact column out[q] at
+    // j (j < sel0) or j - (sel1 - sel0).  sel1 <= sel0: plain readout, out[q][j].
+    double *out2[3];
+    const int32_t *oidx;
+    int64_t sel0, sel1;
 };
+
+// where the result of particle j for field q goes (see PmbFields)
+__device__ __forceinline__ void pmb_store_result(const PmbFields &f, int q, int64_t j, double value)
+{
+    if (f.sel1 > f.sel0) {
+        if (j >= f.sel0 && j < f.sel1) {
+            f.out2[q][f.oidx[j - f.sel0]] = 0.0 + value;      // bincount starts from 0.0: -0.0 becomes +0.0
+            return;
+        }
+        if (j >= f.sel1) j -= f.sel1 - f.sel0;
+    }
+    pmb_st_real_stream(f.out[q], j * f.out_stride[q], f.out_elsize, value);
+}
 
 // ---- readout of NF fields in one sweep ---------------------------------------------------------------
 // indices and weights are computed once per particle and used for NF gathers (the three force components
@@ -141,7 +162,7 @@ pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields 
                         const bool ok = !CHECK || (ex[a] >= 0 && ey[b] >= 0 && ez[cc] >= 0);
                         if (ok) value += mv[q][a][b][cc] * w[a][b][cc];
                     }
-            pmb_st_real_stream(f.out[q], i * f.out_stride[q], f.out_elsize, value);
+            pmb_store_result(f, q, i, value);
         }
     }
 }

@@ -215,6 +215,38 @@ class Layout(object):
             return out.to_host()
         return out
 
+    # ------------------------------------------------------------------ fused readout + gather
+    def fused_gather_plan(self):
+        """(own_begin, own_count, pointer to the indices of the own block) for kernels that write the results of
+        this rank's own particles straight into the gathered columns; None when there is nothing to fuse"""
+        if self.identity or self.comm.size == 1:
+            return None
+        me = self.comm.rank
+        return (int(self.recvoffsets[me]), int(self.recvcounts[me]),
+                self.indices_device.ptr + 4 * int(self.sendoffsets[me]))
+
+    def gather_add_ghosts(self, ghost_cols, own_cols):
+        """second half of the fused ghost sum: ``ghost_cols`` (compact float64 columns of the ghosts this rank
+        holds for others, the own block cut out) travel back through the reverse alltoallv and are added,
+        in rank order, to ``own_cols`` (sendlength rows), which already hold the own results"""
+        me, P = self.comm.rank, self.comm.size
+        rn, sn = int(self.recvcounts[me]), int(self.sendcounts[me])
+        nback = int(self.sendcounts.sum())
+        roff = self._remote_offsets(self.recvoffsets, rn)
+        boff = self._remote_offsets(self.sendoffsets, sn)
+        offs = numpy.zeros(P + 1, dtype='i8')
+        offs[1:] = numpy.cumsum(self.sendcounts)
+        for g, o in zip(ghost_cols, own_cols):
+            ctx = g.ctx
+            back = DeviceArray.empty((max(nback - sn, 1), 8), 'u1')
+            self._alltoallv(ctx, g, self.recvcounts, roff, back, self.sendcounts, boff, 8, skip_self=True)
+            segs = (ctypes.c_void_p * P)()
+            for q in range(P):
+                segs[q] = back.ptr + int(boff[q]) * 8
+            _lib.check(ctx.lib.pmb_gather_add_segments(ctx.handle, segs, 8, 1, self.indices_device.ptr,
+                                                       offs.ctypes.data, P, me, int(self.sendlength), o.ptr))
+        return own_cols
+
     # ------------------------------------------------------------------ gather
     def gather(self, data, mode='sum', out=None):
         """

@@ -79,7 +79,7 @@ def force(pm, Q, S=None, factor=1.0):
     # (pm.readout_fields): positions, cell indices and weights are shared by the components
     from .pm import readout_fields
     f = [rhok.apply(force_transfer(d), out=pm.create('complex')).c2r(out=Ellipsis) for d in range(pm.ndim)]
-    return [layout.gather(col) for col in readout_fields(f, lpos)]
+    return readout_fields(f, lpos, gather=layout)
 
 
 def lpt1(pm, dlinear, Q):

@@ -788,13 +788,19 @@ class TransposedComplexField(BaseComplexField):
 ComplexField = TransposedComplexField
 
 
-def readout_fields(fields, pos, resampler=None, transform=None, layout=None):
+def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None):
     """
     Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles
     (engine extension; the force step's three components, examples/nbody.py:211-216, share the pass
     over the positions).  Equals ``[f.readout(pos, layout=layout) for f in fields]`` value for value.
 
     pos : DeviceArray (N, ndim);  returns a list of DeviceArray (N,)
+    layout : exchange ``pos`` first and reduce the results back (like RealField.readout)
+    gather : ``pos`` is ALREADY the result of ``gather.exchange(...)``; the results are reduced back to the
+             original particles, ``[gather.gather(c) for c in columns]``, without the gather's own pass over
+             the particles: the kernel writes the results of the rank's own particles straight into the
+             gathered columns and only the ghosts travel (sums agree with Layout.gather to rounding: the
+             own value is added first instead of in rank order)
     """
     pm = fields[0].pm
     if not transform:
@@ -802,11 +808,22 @@ def readout_fields(fields, pos, resampler=None, transform=None, layout=None):
     resampler = FindResampler(pm.resampler if resampler is None else resampler)
     if layout is not None:
         pos = layout.exchange(pos)
+        gather = layout
+    plan = gather.fused_gather_plan() if (gather is not None and is_device(pos)) else None
+    if plan is not None and len(fields) <= 3:
+        own_begin, own_count, own_index = plan
+        nghost = int(pos.shape[0]) - own_count
+        own = [DeviceArray.zeros((int(gather.sendlength),), 'f8') for _ in fields]
+        ghosts = [DeviceArray.empty((max(nghost, 1),), 'f8') for _ in fields]
+        if resampler.readout_multi_gather([f._device() for f in fields], pos, ghosts, own, own_index, own_begin, own_count,
+                                          transform=transform):
+            return gather.gather_add_ghosts(ghosts, own)
+        del own, ghosts
     out = []
     for i in range(0, len(fields), 3):
         out += resampler.readout_multi([f._device() for f in fields[i:i + 3]], pos, transform=transform)
-    if layout is not None:
-        out = [layout.gather(o) for o in out]
+    if gather is not None:
+        out = [gather.gather(o) for o in out]
     return out
 
 

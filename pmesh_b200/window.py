@@ -294,6 +294,31 @@ class ResampleWindow(object):
         del keep
         return list(outs)
 
+    def readout_multi_gather(self, reals, pos, ghost_outs, own_outs, own_index_ptr, own_begin, own_count, transform=None):
+        """readout_multi fused with the routing of Layout.gather('sum') (pmb_readout_multi_gather): results of
+        the rank's own particles [own_begin, own_begin + own_count) go to row own_index[k] of ``own_outs``,
+        those of the ghosts to the compact columns ``ghost_outs``.  Returns False when no fused kernel exists
+        for this window / geometry (nothing is written then)."""
+        meshes = [self._device_mesh(r)[0] for r in reals]
+        m0 = meshes[0]
+        nf = len(meshes)
+        for m in meshes[1:]:
+            assert m.shape == m0.shape and m.strides == m0.strides and m.dtype == m0.dtype, "canvases must share one geometry"
+        a, keep, n = self._args(m0, pos, None, None, transform)
+        a.out_elsize = 8
+        mp = (ctypes.c_void_p * nf)(*[m.ptr for m in meshes])
+        gp = (ctypes.c_void_p * nf)(*[o.ptr for o in ghost_outs])
+        op = (ctypes.c_void_p * nf)(*[o.ptr for o in own_outs])
+        ctx = m0.ctx
+        ctx.ensure_tables()
+        rc = ctx.lib.pmb_readout_multi_gather(ctx.handle, ctypes.byref(a), nf, mp, gp, op, ctypes.c_void_p(own_index_ptr),
+                                              int(own_begin), int(own_count))
+        del keep
+        if rc == -5:          # PMB_EUNSUPPORTED
+            return False
+        _lib.check(rc)
+        return True
+
     def readout_grad(self, real, pos, hsml=None, transform=None, want_value=True):
         """value and all ndim gradients in one neighbour sweep (device arrays): (value | None, grad (N, ndim)).
         Each column equals readout(diffdir=d) bit for bit; this is the paint_vjp / readout_vjp helper."""

@@ -200,7 +200,14 @@ def test_gather_sum_matches_bincount(D, oracle):
     lay.recvcounts = counts
     lay.recvoffsets = lay.sendoffsets
     lay.recvlength = counts.sum()
-    lay._alltoallv = lambda ctx, send, *a, **k: send            # pretend the reverse alltoallv happened
+    # pretend the reverse alltoallv happened: what comes back is everything but the block of this rank
+    # (rank 0: the first segment), packed -- the layout Layout.gather expects of its `back` buffer
+
+    def fake_alltoallv(ctx, send, sc, so, recv, rc, ro, itemsize, skip_self=False):
+        own = int(counts[0]) * int(itemsize)
+        nbytes = int(counts.sum()) * int(itemsize) - own
+        return DeviceArray((max(nbytes, 1),), "u1", ptr=send.ptr + own, base=send, ctx=ctx)
+    lay._alltoallv = fake_alltoallv
     for dt in ("f8", "f4"):
         for trailing in ((), (3,)):
             vals = rng.uniform(-1, 1, (len(indices),) + trailing).astype(dt)
