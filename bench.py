@@ -200,10 +200,11 @@ class ForceStep(object):
         self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
         self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
         self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
-        from pmesh_b200.pm import readout_fields
+        from pmesh_b200.pm import apply_gradients, readout_fields
+        # the three gravity transfers read the density modes once (pm.apply_gradients) ...
+        self._t("transfer", lambda: apply_gradients(self.rhok, self.tf, outs=self.tmp))
         real = []
         for d in range(3):
-            self._t("transfer", lambda: self.rhok.apply(self.tf[d], out=self.tmp[d]))
             real.append(self._t("c2r", lambda: self.tmp[d].c2r(out=Ellipsis)))
         # the three force fields are read in ONE sweep over the particles (shared positions / weights)
         # ... and the ghost sum is fused into it: F[d] = layout.gather(real[d].readout(lpos)), nbody.py:214-216
@@ -493,7 +494,7 @@ def run_ours(args):
                "d2h_bytes_per_step": int(3 * fb), "steps": ke, "serial_ms": round(serial_ms, 3),
                "overlap": "upload of step k+1 || download of step k (independent evaluations); compute between them"}
         F = Fk
-        del Xh, Fh
+        del Xh, Fh, Xd, Fk
 
     # ---- parity at full size against the oracle (periodic replicas of a small problem) ----
     del X, F

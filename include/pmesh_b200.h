@@ -301,6 +301,12 @@ int pmb_transfer(pmb_fft *plan, int kind, int dir, const double *params_h, const
 int pmb_transfer_scaled(pmb_fft *plan, int kind, int dir, const double *params_h, const double *boxsize_h,
                         double prefactor, const void *in, void *out);
 
+/* The three gradient transfers of the force step in ONE pass over the density modes:
+ * outs_h[d] = prefactor * i m_d(k_d) / k^2 * in, d = 0, 1, 2, with m_d = kfinite_d (PMB_TF_GRAVITY_FD4,
+ * examples/nbody.py:162-170) or k_d (PMB_TF_GRADIENT_K, :154-160).  Values equal three pmb_transfer_scaled calls. */
+int pmb_transfer_grad3(pmb_fft *plan, int kind, const double *boxsize_h, double prefactor, const void *in,
+                       void *const *outs_h);
+
 /* result_h[0..1] = (re, im) of sum over the LOCAL stored half-complex modes of conj(b) * a * w, w = 2 for
  * modes that stand for themselves and their Hermitian conjugate (0 < k_last < N/2), else 1 -- the rank-local
  * term of ComplexField.cdot / cnorm (pm.py:911-974, default metric and norm); float64 accumulation. */

@@ -18,7 +18,7 @@
 // WARP w owns the contiguous particles [w*per_unit, (w+1)*per_unit): no block-level synchronisation
 // anywhere.  Lane r (and r + 32) of a warp keeps the count / cursor of rank r in a register.
 // MaskT: the narrowest unsigned type that holds one bit per rank (1 byte per particle up to 8 ranks).
-#define ROUTE_UNROLL 4
+#define ROUTE_UNROLL 8
 template <int NDIM, typename MaskT>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t npart,
@@ -42,11 +42,23 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
     const int64_t end = min(begin + per_unit, npart);
     int c0 = 0, c1 = 0;
     for (int64_t base = begin; base < end; base += 32 * ROUTE_UNROLL) {
+        // all coordinates of the ROUTE_UNROLL particles of this lane are requested before the first one is
+        // used: the routing arithmetic is branchy (fmod fall-backs, edge searches) and the compiler does not
+        // hoist loads across it -- one load in flight per lane left the kernel at 25 % of the HBM bandwidth
+        // (ncu launch list profiles/r2_route_launches.csv: 2.0 ms for 134 M particles)
+        double xs[ROUTE_UNROLL][NDIM];
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const int64_t i = base + u * 32 + lane;
+#pragma unroll
+            for (int d = 0; d < NDIM; d++)
+                xs[u][d] = (i < end && pmb_route_axis_used(g, d)) ? pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize) : 0.0;
+        }
         uint64_t mask[ROUTE_UNROLL];
 #pragma unroll
         for (int u = 0; u < ROUTE_UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
-            mask[u] = i < end ? pmb_route_mask<NDIM>(g, edges, pos, elsize, ps0, ps1, i) : 0;
+            mask[u] = i < end ? pmb_route_mask_x<NDIM>(g, edges, xs[u]) : 0;
         }
 #pragma unroll
         for (int u = 0; u < ROUTE_UNROLL; u++) {

@@ -991,6 +991,95 @@ pmb_k_transfer(const C *__restrict__ in, C *__restrict__ out, int64_t nrows, int
     }
 }
 
+// The three gradient transfers of the force step in one pass: out_d = i m_d(k_d) / k^2 * in for d = 0, 1, 2
+// (m_d = kfinite_d for PMB_TF_GRAVITY_FD4, k_d for PMB_TF_GRADIENT_K).  The density modes are read once and
+// 1 / k^2 is formed once: 16 + 48 bytes per cell instead of 3 x 32.
+template <typename C>
+__global__ void __launch_bounds__(256)
+pmb_k_transfer_grad3(const C *__restrict__ in, C *__restrict__ o0, C *__restrict__ o1, C *__restrict__ o2,
+                     int64_t nrows, int64_t rowlen, TfArgs a)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *m0 = a.mtab, *m1 = a.mtab + a.n[0], *m2 = a.mtab + a.n[0] + a.n[1];
+    for (int64_t row = (int64_t) blockIdx.x * 8 + warp; row < nrows; row += (int64_t) gridDim.x * 8) {
+        int64_t i0 = 0, i1, i2 = 0;
+        if (a.P == 1) { i1 = row % a.n[1]; i0 = row / a.n[1]; }
+        else { i2 = a.s2 + row % a.mc; i1 = a.s1 + row / a.mc; }
+        const double kB = a.ktab[1][i1];
+        for (int64_t c = lane; c < rowlen; c += 32) {
+            const int64_t t = row * rowlen + c;
+            const int64_t j0 = a.P == 1 ? i0 : c, j2 = a.P == 1 ? c : i2;
+            const double k0 = a.ktab[0][j0], k2v = a.ktab[2][j2];
+            // the same order of additions as pmb_tf_apply: ((k0^2) + k1^2) + k2^2
+            double k2 = 0;
+            k2 = k2 + k0 * k0;
+            k2 = k2 + kB * kB;
+            k2 = k2 + k2v * k2v;
+            if (k2 == 0) k2 = 1.0;
+            const C v = in[t];
+            const double im[3] = {(m0[j0] / k2) * a.pre, (m1[i1] / k2) * a.pre, (m2[j2] / k2) * a.pre};
+            C r;
+            r.x = (decltype(r.x)) (0.0 - (double) v.y * im[0]); r.y = (decltype(r.y)) ((double) v.x * im[0]); o0[t] = r;
+            r.x = (decltype(r.x)) (0.0 - (double) v.y * im[1]); r.y = (decltype(r.y)) ((double) v.x * im[1]); o1[t] = r;
+            r.x = (decltype(r.x)) (0.0 - (double) v.y * im[2]); r.y = (decltype(r.y)) ((double) v.x * im[2]); o2[t] = r;
+        }
+    }
+}
+
+extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
+                                  void *const *outs_h)
+{
+    PMB_REQUIRE(f && boxsize_h && in && outs_h && outs_h[0] && outs_h[1] && outs_h[2], "null argument");
+    PMB_REQUIRE(kind == PMB_TF_GRAVITY_FD4 || kind == PMB_TF_GRADIENT_K, "grad3 serves the two gradient transfers");
+    PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
+    pmb_ctx *ctx = f->ctx;
+    const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
+    double *h = (double *) malloc(sizeof(double) * 2 * ntab);
+    if (!h) return PMB_ENOMEM;
+    int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
+    double *m = h + ntab;
+    for (int d = 0; d < 3; d++)
+        for (int64_t i = 0; i < f->n[d]; i++) {
+            const double k = host_wavenumber(i, f->n[d], boxsize_h[d]);
+            h[off[d] + i] = k;
+            if (kind == PMB_TF_GRAVITY_FD4) {
+                const double Cc = boxsize_h[d] / (double) f->n[d];
+                const double w = k * Cc;
+                m[off[d] + i] = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
+            } else {
+                m[off[d] + i] = k;
+            }
+        }
+    void *dev;
+    int rc = pmb_scratch(ctx, sizeof(double) * 2 * ntab, &dev);
+    if (rc != PMB_OK) { free(h); return rc; }
+    cudaError_t e = cudaMemcpyAsync(dev, h, sizeof(double) * 2 * ntab, cudaMemcpyHostToDevice, ctx->stream);
+    free(h);
+    if (e != cudaSuccess) return pmb_cuda_fail(e, "transfer tables", __FILE__, __LINE__);
+    TfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kind = kind; a.ndim = 3; a.P = f->P;
+    for (int d = 0; d < 3; d++) { a.n[d] = f->n[d]; a.ktab[d] = (const double *) dev + off[d]; }
+    a.mtab = (const double *) dev + ntab;
+    a.nc = f->nc; a.s1 = f->s1; a.m1 = f->m1; a.s2 = f->s2; a.mc = f->mc;
+    a.pre = prefactor;
+    int64_t nrows, rowlen;
+    if (f->P == 1) { nrows = f->n[0] * f->n[1]; rowlen = f->nc; }
+    else { nrows = f->m1 * f->mc; rowlen = f->n[0]; }
+    if (nrows == 0 || rowlen == 0) return PMB_OK;
+    int64_t grid = (nrows + 7) / 8;
+    const int64_t cap = (int64_t) ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (f->elsize == 8)
+        pmb_k_transfer_grad3<double2><<<(int) grid, 256, 0, ctx->stream>>>((const double2 *) in, (double2 *) outs_h[0], (double2 *) outs_h[1],
+                                                                            (double2 *) outs_h[2], nrows, rowlen, a);
+    else
+        pmb_k_transfer_grad3<float2><<<(int) grid, 256, 0, ctx->stream>>>((const float2 *) in, (float2 *) outs_h[0], (float2 *) outs_h[1],
+                                                                          (float2 *) outs_h[2], nrows, rowlen, a);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
 // ---- collective reductions over the independent modes ------------------------------------------------
 // sum over the stored half-complex modes of conj(b) * a * w, w = 2 for 0 < k_last < N/2 (the mode stands
 // for itself and its Hermitian conjugate), 1 for k_last = 0 and N/2 (BaseComplexField._expand_hermitian,

@@ -94,20 +94,26 @@ PMB_HD double pmb_pymod_fast(double a, double b)
 // per-particle rank mask; ref: pmesh/domain.py:609-630 (sil/sir) + pmesh/_domain.pyx:62-100 (patch walk)
 // NDIM is a compile-time constant so that sil / sir / the patch odometer live in registers; `edges`
 // point into shared memory (the binary searches of digitize never leave the SM).
+// does the routing look at coordinate d at all?  (one periodic domain on an axis: no)
+PMB_HD bool pmb_route_axis_used(const RouteGeom &g, int d)
+{
+    return !(g.periodic && g.shape[d] == 1);
+}
+
+// xin[d]: the raw coordinates of the particle (only the axes pmb_route_axis_used says are read)
 template <int NDIM>
-PMB_HD uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, const void *pos,
-                                                   int elsize, int64_t ps0, int64_t ps1, int64_t i)
+PMB_HD uint64_t pmb_route_mask_x(const RouteGeom &g, const double *const *edges, const double *xin)
 {
     int sil[NDIM], sir[NDIM];
 #pragma unroll
     for (int d = 0; d < NDIM; d++) {
-        if (g.periodic && g.shape[d] == 1) {
+        if (!pmb_route_axis_used(g, d)) {
             // one periodic domain on this axis: sil = p - 1, sir = p, and the single patch cell wraps
             // to domain 0 whatever the coordinate is (also for NaN: digitize gives len(edges))
             sil[d] = 0; sir[d] = 1;
             continue;
         }
-        const double x = g.scale[d] * pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize);
+        const double x = g.scale[d] * xin[d];
         const double sm = g.smoothing[d];
         const double *e = edges[d];
         const int ne = g.nedges[d];
@@ -170,3 +176,14 @@ PMB_HD uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, c
     return mask;
 }
 
+// the same from the particle array (host harness, and callers that do not prefetch)
+template <int NDIM>
+PMB_HD uint64_t pmb_route_mask(const RouteGeom &g, const double *const *edges, const void *pos,
+                                                   int elsize, int64_t ps0, int64_t ps1, int64_t i)
+{
+    double x[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++)
+        x[d] = pmb_route_axis_used(g, d) ? pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize) : 0.0;
+    return pmb_route_mask_x<NDIM>(g, edges, x);
+}

@@ -788,6 +788,32 @@ class TransposedComplexField(BaseComplexField):
 ComplexField = TransposedComplexField
 
 
+def apply_gradients(field, transfers, outs=None):
+    """
+    ``[field.apply(t, out=o) for t, o in zip(transfers, outs)]`` for the three gradient transfers of a force
+    or displacement evaluation (``GravityFD4(0..2)`` or ``GradientK(0..2)``, examples/nbody.py:154-170) in ONE
+    pass over the modes of ``field`` (engine extension: the modes are read once, 1 / k^2 is formed once).
+    Any other combination is applied one transfer at a time.
+    """
+    pm = field.pm
+    if outs is None:
+        outs = [pm.create(type=_gettype(field)) for _ in transfers]
+    tfs = [find_transfer(t) for t in transfers]
+    same = (len(tfs) == 3 and pm.ndim == 3 and all(t is not None for t in tfs)
+            and tfs[0].kind in (_lib.TF_GRAVITY_FD4, _lib.TF_GRADIENT_K) and all(t.kind == tfs[0].kind for t in tfs)
+            and [int(t.direction) for t in tfs] == [0, 1, 2] and isinstance(field, BaseComplexField)
+            and all(isinstance(o, BaseComplexField) and o is not field for o in outs))
+    if not same:
+        return [field.apply(t, out=o) for t, o in zip(transfers, outs)]
+    src = field._device(absorb=True)
+    box = (ctypes.c_double * 3)(*[float(b) for b in field.BoxSize])
+    ptrs = (ctypes.c_void_p * 3)(*[o._dev.ptr for o in outs])
+    _lib.check(pm.ctx.lib.pmb_transfer_grad3(pm._plan, tfs[0].kind, box, float(field._pending), src.ptr, ptrs))
+    for o in outs:
+        o._mark_device_written()
+    return list(outs)
+
+
 def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None):
     """
     Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles

@@ -260,3 +260,43 @@ def test_conservation_properties_at_scale():
         assert rms > 0
         for f in F:
             assert abs(f.sum()) < 1e-9 * n * rms
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_apply_gradients_and_device_reductions(P, oracle, dtype):
+    """pm.apply_gradients (three gradient transfers in one pass over the modes) == three apply calls;
+    csum / cdot / cnorm reduce on the device (pmb_field_sum / pmb_field_dot / pmb_cdot) == numpy"""
+    from pmesh_b200 import transfer as T
+    n = (12, 10, 16)
+    pm = P.ParticleMesh(BoxSize=[7.0, 9.0, 11.0], Nmesh=n, dtype=dtype)
+    tol = 1e-6 if dtype == "f8" else 1e-4
+    rng = numpy.random.default_rng(3)
+    x = rng.normal(size=n).astype(dtype)
+    y = rng.normal(size=n).astype(dtype)
+    rx, ry = pm.create(type="real", value=x), pm.create(type="real", value=y)
+    cx, cy = rx.r2c(), ry.r2c()
+    for make in (T.GravityFD4, T.GradientK):
+        tfs = [make(d) for d in range(3)]
+        fused = P.apply_gradients(cx, tfs)
+        for d in range(3):
+            rel_close(fused[d].value, cx.apply(tfs[d]).value, 1e-14 if dtype == "f8" else 1e-6)
+    # a pending scalar of the input rides along
+    rs = pm.create(type="real", value=x)
+    rs.scale(3.5)
+    cs = rs.r2c()
+    fused = P.apply_gradients(cs, [T.GravityFD4(d) for d in range(3)])
+    rel_close(fused[1].value, 3.5 * cx.apply(T.GravityFD4(1)).value, tol)
+    # reductions
+    rel_close(rx.csum(), x.astype("f8").sum(), tol)
+    rel_close(rx.cdot(ry), (x.astype("f8") * y.astype("f8")).sum(), tol)
+    rel_close(rx.cnorm(), (x.astype("f8") ** 2).sum(), tol)
+    w = numpy.full(n[2] // 2 + 1, 2.0)
+    w[0] = 1.0
+    w[-1] = 1.0
+    kx, ky = oracle.r2c(x.astype("f8")), oracle.r2c(y.astype("f8"))
+    rel_close(cx.cnorm(), (abs(kx) ** 2 * w).sum(), tol)
+    got = cx.cdot(cy)
+    want = (kx * numpy.conj(ky) * w).sum()
+    assert abs(got - want) <= tol * abs(want).max() + tol * (abs(kx) ** 2 * w).sum() ** 0.5 * (abs(ky) ** 2 * w).sum() ** 0.5
+    # Parseval through the engine: cnorm of the modes == mean square of the field
+    rel_close(cx.cnorm(), (x.astype("f8") ** 2).sum() / x.size, tol)
