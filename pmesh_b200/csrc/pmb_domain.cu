@@ -18,8 +18,8 @@
 // WARP w owns the contiguous particles [w*per_unit, (w+1)*per_unit): no block-level synchronisation
 // anywhere.  Lane r (and r + 32) of a warp keeps the count / cursor of rank r in a register.
 // MaskT: the narrowest unsigned type that holds one bit per rank (1 byte per particle up to 8 ranks).
-#define ROUTE_UNROLL 8
-template <int NDIM, typename MaskT>
+#define ROUTE_UNROLL 8          // granularity of a unit: 32 * ROUTE_UNROLL particles
+template <int NDIM, typename MaskT, int UNROLL>
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t ps1, int64_t npart,
                   int64_t per_unit, MaskT *masks, int32_t *unithist)
@@ -41,27 +41,27 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
     const int64_t begin = unit * per_unit;
     const int64_t end = min(begin + per_unit, npart);
     int c0 = 0, c1 = 0;
-    for (int64_t base = begin; base < end; base += 32 * ROUTE_UNROLL) {
-        // all coordinates of the ROUTE_UNROLL particles of this lane are requested before the first one is
+    for (int64_t base = begin; base < end; base += 32 * UNROLL) {
+        // all coordinates of the UNROLL particles of this lane are requested before the first one is
         // used: the routing arithmetic is branchy (fmod fall-backs, edge searches) and the compiler does not
         // hoist loads across it -- one load in flight per lane left the kernel at 25 % of the HBM bandwidth
         // (ncu launch list profiles/r2_route_launches.csv: 2.0 ms for 134 M particles)
-        double xs[ROUTE_UNROLL][NDIM];
+        double xs[UNROLL][NDIM];
 #pragma unroll
-        for (int u = 0; u < ROUTE_UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
 #pragma unroll
             for (int d = 0; d < NDIM; d++)
                 xs[u][d] = (i < end && pmb_route_axis_used(g, d)) ? pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize) : 0.0;
         }
-        uint64_t mask[ROUTE_UNROLL];
+        uint64_t mask[UNROLL];
 #pragma unroll
-        for (int u = 0; u < ROUTE_UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
             mask[u] = i < end ? pmb_route_mask_x<NDIM>(g, edges, xs[u]) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < ROUTE_UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
             if (i < end) __stcs(masks + i, (MaskT) mask[u]);
             // ranks that any lane of the warp targets (usually one or two)
@@ -293,9 +293,21 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
     for (int d = 0; d < a->ndim; d++) tot_edges += a->nedges[d];
     const size_t smem = sizeof(double) * tot_edges;
     ctx->route_maskbytes = a->nranks <= 8 ? 1 : (a->nranks <= 16 ? 2 : 8);
+    // coordinates requested ahead per lane (PMB_ROUTE_UNROLL = 2, 4, 8; measured in profiles/r2_route_unroll.json)
+    static int route_unroll = -1;
+    if (route_unroll < 0) { const char *e = getenv("PMB_ROUTE_UNROLL"); route_unroll = e ? atoi(e) : 4; }
 #define ROUTE_COUNT(ND, MT)                                                                          \
-    pmb_k_route_count<ND, MT><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(                     \
-        g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_unit, (MT *) ctx->route_masks, hist)
+    do {                                                                                             \
+        if (route_unroll >= 8)                                                                       \
+            pmb_k_route_count<ND, MT, 8><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(          \
+                g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_unit, (MT *) ctx->route_masks, hist); \
+        else if (route_unroll >= 4)                                                                  \
+            pmb_k_route_count<ND, MT, 4><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(          \
+                g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_unit, (MT *) ctx->route_masks, hist); \
+        else                                                                                         \
+            pmb_k_route_count<ND, MT, 2><<<(int) nblocks, ROUTE_BLOCK, smem, ctx->stream>>>(          \
+                g, a->pos, a->pos_elsize, a->pos_stride0, a->pos_stride1, a->npart, per_unit, (MT *) ctx->route_masks, hist); \
+    } while (0)
 #define ROUTE_COUNT_ND(MT)                                                                           \
     do {                                                                                             \
         if (a->ndim == 1) ROUTE_COUNT(1, MT); else if (a->ndim == 2) ROUTE_COUNT(2, MT); else ROUTE_COUNT(3, MT); \

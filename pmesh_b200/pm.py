@@ -245,7 +245,20 @@ class Field(NDArrayLike):
             st = (ctypes.c_int64 * 3)(es)
             _lib.check(ctx.lib.pmb_field_scale(ctx.handle, self._dev.ptr, es, 0, 1, n, st, float(factor)))
 
+    def _host_is_stale(self):
+        """this view handed its host array out (it is host-authoritative), but ANOTHER view of the same memory
+        (an in-place r2c / c2r partner, a field created with base=) has written the device since: the memory
+        is newer than the mirror.  The device wins -- in the reference `.value` IS the one shared buffer, so
+        the later writer wins there too; what is lost is a write made through a retained `.value` array after
+        the other view's device operation, which the reference would have kept."""
+        if not self._dev_valid and self._host_version != self._base.version:
+            self._dev_valid = True
+            self._host_valid = False
+            return True
+        return False
+
     def _sync_host(self):
+        self._host_is_stale()
         # the device copy is authoritative unless this view handed its host array out (_dev_valid False)
         if self._dev_valid and (not self._host_valid or self._host_version != self._base.version):
             self._materialize()
@@ -266,6 +279,7 @@ class Field(NDArrayLike):
         self._host[...] = v
         self._host_valid = True
         self._dev_valid = False
+        self._host_version = self._base.version       # the mirror is newer than anything written so far
 
     def readonly_value(self):
         """host copy of the values without invalidating the device copy"""
@@ -278,6 +292,7 @@ class Field(NDArrayLike):
         """DeviceArray view of the field, uploading the host mirror if it is authoritative.
         absorb=True: the caller folds ``self._pending`` into its own arithmetic; otherwise the pending
         factor is multiplied in first."""
+        self._host_is_stale()
         if not self._dev_valid:
             h = self._host
             if self.size:

@@ -242,7 +242,7 @@ def main():
             del pm, rho, rhok, cip, f, wn, layout
 
     # a second mesh of a configuration used before takes the pooled peer-memory landing buffers again
-    del pm
+    pm = None
     for rep in range(2):
         pm = ParticleMesh(BoxSize=100.0, Nmesh=[16, 16, 16], dtype="f8", resampler="cic", comm=comm)
         shape = pm._layout["i_shape"]
