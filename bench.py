@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--inputs", default="zeldovich,uniform,lattice",
                     help="inputs for which paint / readout are timed alone (comma separated)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-size parity check against the oracle")
+    ap.add_argument("--np", default="", help="process mesh, e.g. 2,4 for pencils (default: slabs, np = [gpus])")
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -360,7 +361,8 @@ def run_ours(args):
     if comm.size != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE is %d (launch with torch.distributed.run)" % (args.gpus, comm.size))
     M = args.nmesh
-    pm = ParticleMesh(BoxSize=float(M), Nmesh=[M, M, M], dtype=args.dtype, resampler=args.window, comm=comm)
+    npm = [int(v) for v in args.np.split(",")] if args.np else None
+    pm = ParticleMesh(BoxSize=float(M), Nmesh=[M, M, M], dtype=args.dtype, resampler=args.window, comm=comm, np=npm)
     ctx = pm.ctx
     X, ntot = make_particles(pm, args, comm)
     n = X.shape[0]
@@ -519,7 +521,7 @@ def run_ours(args):
                                       "" if comm.size > 1 else ", single GPU"),
                        "nmesh": M, "nparticles": ntot, "window": args.window, "paint_mode": args.paint_mode,
                        "particles": INPUT_LABEL[args.particles],
-                       "decomposition": "slab np=[%d]" % comm.size,
+                       "decomposition": ("pencil np=%s" % pm.np) if len(pm.np) == 2 else "slab np=[%d]" % comm.size,
                        "l2": "inputs (%.1f GB positions + %.1f GB mesh per rank) are larger than L2"
                              % (n * 24 / 1e9, int(numpy.prod(pm._layout['i_shape'])) * es / 1e9)},
             "paint_readout_gparticles_per_s": main["paint_readout_gparticles_per_s"],

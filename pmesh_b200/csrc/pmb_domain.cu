@@ -42,10 +42,9 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
     const int64_t end = min(begin + per_unit, npart);
     int c0 = 0, c1 = 0;
     for (int64_t base = begin; base < end; base += 32 * UNROLL) {
-        // all coordinates of the UNROLL particles of this lane are requested before the first one is
-        // used: the routing arithmetic is branchy (fmod fall-backs, edge searches) and the compiler does not
-        // hoist loads across it -- one load in flight per lane left the kernel at 25 % of the HBM bandwidth
-        // (ncu launch list profiles/r2_route_launches.csv: 2.0 ms for 134 M particles)
+        // all coordinates of the UNROLL particles of this lane are requested before the first one is used:
+        // the routing arithmetic is branchy (fmod fall-backs, edge searches) and the compiler does not hoist
+        // loads across it
         double xs[UNROLL][NDIM];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
@@ -295,7 +294,9 @@ extern "C" int pmb_decompose_count(pmb_ctx *ctx, const pmb_decompose_args *a, in
     ctx->route_maskbytes = a->nranks <= 8 ? 1 : (a->nranks <= 16 ? 2 : 8);
     // coordinates requested ahead per lane (PMB_ROUTE_UNROLL = 2, 4, 8; measured in profiles/r2_route_unroll.json)
     static int route_unroll = -1;
-    if (route_unroll < 0) { const char *e = getenv("PMB_ROUTE_UNROLL"); route_unroll = e ? atoi(e) : 4; }
+    // 268 M particles, 2 slabs (B200, ms): 2 -> 4.12, 4 -> 5.01, 8 -> 8.56: registers (48 / 64 / 93), i.e. resident
+    // warps, matter more than loads in flight per lane
+    if (route_unroll < 0) { const char *e = getenv("PMB_ROUTE_UNROLL"); route_unroll = e ? atoi(e) : 2; }
 #define ROUTE_COUNT(ND, MT)                                                                          \
     do {                                                                                             \
         if (route_unroll >= 8)                                                                       \

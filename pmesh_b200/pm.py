@@ -169,6 +169,7 @@ class Field(NDArrayLike):
             r._host[...] = self._host
             r._dev_valid = False
             r._host_valid = True
+            r._host_version = r._base.version
         return r
 
     def __init__(self, pm, base=None):
@@ -272,6 +273,7 @@ class Field(NDArrayLike):
         device operation uploads it (the caller may have written through the returned array)."""
         self._sync_host()
         self._dev_valid = False
+        self._host_version = self._base.version
         return self._host
 
     @value.setter
