@@ -53,7 +53,43 @@ struct pmb_fft {
     cudaEvent_t ev[FFT_NEV][2];
     int nev;
     float lib_ms;
+    // device copies of the per-axis tables of the transfer functions (wavenumbers | multipliers), kept per
+    // (kind, direction, box, parameters): the force step applies the same few transfers every step
+    struct TfCache { int kind, dir; double box[3], p[2]; void *dev; } tfc[8];
+    int ntfc;
 };
+
+// cached tables or NULL
+static void *tf_cache_find(pmb_fft *f, int kind, int dir, const double *box, double p0, double p1)
+{
+    for (int i = 0; i < f->ntfc; i++) {
+        const pmb_fft::TfCache &c = f->tfc[i];
+        if (c.kind == kind && c.dir == dir && c.box[0] == box[0] && c.box[1] == box[1] && c.box[2] == box[2] &&
+            c.p[0] == p0 && c.p[1] == p1) return c.dev;
+    }
+    return NULL;
+}
+
+// upload freshly built host tables (nbytes) and remember them; *dev is valid for kernels on the context's stream
+static int tf_cache_store(pmb_fft *f, int kind, int dir, const double *box, double p0, double p1,
+                          const void *host, size_t nbytes, void **dev)
+{
+    pmb_ctx *ctx = f->ctx;
+    if (f->ntfc == 8) {
+        // full: drop the oldest entry (kernels that read it are ordered before the free by the synchronisation)
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PMB_CUDA(cudaFree(f->tfc[0].dev));
+        for (int i = 1; i < 8; i++) f->tfc[i - 1] = f->tfc[i];
+        f->ntfc = 7;
+    }
+    PMB_CUDA(cudaMalloc(dev, nbytes));
+    cudaError_t e = cudaMemcpyAsync(*dev, host, nbytes, cudaMemcpyHostToDevice, ctx->stream);   // pageable source: staged before return
+    if (e != cudaSuccess) { cudaFree(*dev); return pmb_cuda_fail(e, "transfer tables", __FILE__, __LINE__); }
+    pmb_fft::TfCache &c = f->tfc[f->ntfc++];
+    c.kind = kind; c.dir = dir; c.p[0] = p0; c.p[1] = p1; c.dev = *dev;
+    for (int d = 0; d < 3; d++) c.box[d] = box[d];
+    return PMB_OK;
+}
 
 static int cufft_fail(cufftResult r, const char *what, int line)
 {
@@ -360,6 +396,7 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
         if (f->m1 * f->mc > 0) cufftDestroy(f->pen_l0);
     }
     p2p_teardown(f);
+    for (int i = 0; i < f->ntfc; i++) cudaFree(f->tfc[i].dev);
     if (f->work0) cudaFree(f->work0);
     if (f->work1) cudaFree(f->work1);
     for (int i = 0; i < FFT_NEV; i++) { cudaEventDestroy(f->ev[i][0]); cudaEventDestroy(f->ev[i][1]); }
@@ -1034,28 +1071,28 @@ extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h,
     PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
     pmb_ctx *ctx = f->ctx;
     const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
-    double *h = (double *) malloc(sizeof(double) * 2 * ntab);
-    if (!h) return PMB_ENOMEM;
     int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
-    double *m = h + ntab;
-    for (int d = 0; d < 3; d++)
-        for (int64_t i = 0; i < f->n[d]; i++) {
-            const double k = host_wavenumber(i, f->n[d], boxsize_h[d]);
-            h[off[d] + i] = k;
-            if (kind == PMB_TF_GRAVITY_FD4) {
-                const double Cc = boxsize_h[d] / (double) f->n[d];
-                const double w = k * Cc;
-                m[off[d] + i] = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
-            } else {
-                m[off[d] + i] = k;
+    void *dev = tf_cache_find(f, kind, -3, boxsize_h, 0.0, 0.0);
+    if (!dev) {
+        double *h = (double *) malloc(sizeof(double) * 2 * ntab);
+        if (!h) return PMB_ENOMEM;
+        double *m = h + ntab;
+        for (int d = 0; d < 3; d++)
+            for (int64_t i = 0; i < f->n[d]; i++) {
+                const double k = host_wavenumber(i, f->n[d], boxsize_h[d]);
+                h[off[d] + i] = k;
+                if (kind == PMB_TF_GRAVITY_FD4) {
+                    const double Cc = boxsize_h[d] / (double) f->n[d];
+                    const double w = k * Cc;
+                    m[off[d] + i] = 1.0 / Cc * 1 / 6.0 * (8 * sin(w) - sin(2 * w));
+                } else {
+                    m[off[d] + i] = k;
+                }
             }
-        }
-    void *dev;
-    int rc = pmb_scratch(ctx, sizeof(double) * 2 * ntab, &dev);
-    if (rc != PMB_OK) { free(h); return rc; }
-    cudaError_t e = cudaMemcpyAsync(dev, h, sizeof(double) * 2 * ntab, cudaMemcpyHostToDevice, ctx->stream);
-    free(h);
-    if (e != cudaSuccess) return pmb_cuda_fail(e, "transfer tables", __FILE__, __LINE__);
+        const int rc = tf_cache_store(f, kind, -3, boxsize_h, 0.0, 0.0, h, sizeof(double) * 2 * ntab, &dev);
+        free(h);
+        if (rc != PMB_OK) return rc;
+    }
     TfArgs a;
     memset(&a, 0, sizeof(a));
     a.kind = kind; a.ndim = 3; a.P = f->P;
@@ -1164,15 +1201,21 @@ extern "C" int pmb_transfer_scaled(pmb_fft *f, int kind, int dir, const double *
     double box[3] = {1.0, 1.0, 1.0};
     for (int d = 0; d < f->ndim; d++) box[pad + d] = boxsize_h[d];
     const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
+    int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
+    const int dd = dir + pad;
+    int rc = PMB_OK;
+    // tables that depend on parameters: the compensation (window kind, support); others only on kind / dir / box
+    const double cp0 = (kind == PMB_TF_COMPENSATE && params_h) ? params_h[0] : 0.0;
+    const double cp1 = (kind == PMB_TF_COMPENSATE && params_h) ? params_h[1] : 0.0;
+    void *dev = tf_cache_find(f, kind, dir, box, cp0, cp1);
+    if (!dev) {
     // host tables: [k0 | k1 | k2 | mult]
     double *h = (double *) malloc(sizeof(double) * 2 * ntab);
     if (!h) return PMB_ENOMEM;
-    int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
     for (int d = 0; d < 3; d++)
         for (int64_t i = 0; i < f->n[d]; i++) h[off[d] + i] = d < pad ? 0.0 : host_wavenumber(i, f->n[d], box[d]);
     double *m = h + ntab;
-    const int dd = dir + pad;
-    int rc = PMB_OK;
+    for (int64_t i = 0; i < ntab; i++) m[i] = 0.0;
     if (kind == PMB_TF_GRAVITY_FD4) {
         // kfinite = 1/C * 1/6 * (8 sin w - sin 2w), w = k C   (examples/nbody.py:166-168)
         const double Cc = box[dd] / (double) f->n[dd];
@@ -1203,12 +1246,10 @@ extern "C" int pmb_transfer_scaled(pmb_fft *f, int kind, int dir, const double *
                 m[off[d] + i] = s;
             }
     }
-    void *dev;
-    rc = pmb_scratch(ctx, sizeof(double) * 2 * ntab, &dev);
-    if (rc != PMB_OK) { free(h); return rc; }
-    cudaError_t e = cudaMemcpyAsync(dev, h, sizeof(double) * 2 * ntab, cudaMemcpyHostToDevice, ctx->stream);
-    free(h);     // pageable source: the copy was staged before cudaMemcpyAsync returned
-    if (e != cudaSuccess) return pmb_cuda_fail(e, "transfer tables", __FILE__, __LINE__);
+    rc = tf_cache_store(f, kind, dir, box, cp0, cp1, h, sizeof(double) * 2 * ntab, &dev);
+    free(h);
+    if (rc != PMB_OK) return rc;
+    }
 
     TfArgs a;
     memset(&a, 0, sizeof(a));
