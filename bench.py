@@ -230,7 +230,7 @@ def kernel_names(args, nl):
     """names of the paint / readout kernels the dispatch of pmb_resample.cu picks (for the roofline block)"""
     big = nl >= (1 << 18)
     if args.window == "cic" and big:
-        return {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32"}
+        return {"paint": "pmb_k_paint_cic_carry32", "readout": "pmb_k_readout_cic32_ring"}
     if args.window in ("nnb", "cic", "tsc", "pcs"):
         return {"paint": ("pmb_k_paint_carry32" if args.window in ("tsc", "pcs") else "pmb_k_paint_sched") if big else "pmb_k_paint_tuned",
                 "readout": "pmb_k_readout_sched" if big else "pmb_k_readout_tuned"}
