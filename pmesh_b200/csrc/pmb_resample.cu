@@ -218,6 +218,67 @@ pmb_k_readout_grad_tuned(PmbGeom g, PmbParticles p, const char *mesh, int64_t np
     }
 }
 
+// the same for every window with a run-time support (lanczos, acg, wavelets, hsml-scaled windows): the mesh
+// neighbourhood (216 loads for lanczos3) is swept ONCE for the value and the NDIM gradients instead of
+// 1 + NDIM times; per-axis value weights and derivative weights are evaluated once per particle.  Every
+// accumulator sees the addends of the separate readout(gradient = d) in the same order, with the same
+// product ((v0 * v1) * v2) * mesh: the results are bit-identical to pmb_k_readout_dyn's.
+template <typename MeshT, int NDIM>
+__global__ void __launch_bounds__(128)
+pmb_k_readout_grad_dyn(PmbGeom g, PmbWindow w, PmbParticles p, const char *mesh, int64_t npart, int pcsfix,
+                       void *out, int out_elsize, int64_t out_stride, void *grad, int64_t gs0, int64_t gs1)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int zero[3] = {0, 0, 0};
+    for (; i < npart; i += stride) {
+        double x[NDIM];
+        pmb_load_pos<NDIM>(p, i, x);
+        const double h = pmb_load_hsml(p, i);
+        PmbWinInfo info;
+        pmb_window_info(w.nativesupport, w.support * h, &info);
+        PmbAxes<NDIM, PMB_MAX_SUPPORT> A;
+        pmb_axes_dyn<NDIM>(g, w, info, zero, x, pcsfix, A);
+        const int S = A.S;
+        // derivative weights of every axis: the weights pmb_axes_dyn gives that axis for order[d] = 1
+        double D[NDIM][PMB_MAX_SUPPORT];
+        {
+            PmbAxes<NDIM, PMB_MAX_SUPPORT> B;
+            int one[3] = {1, 1, 1};
+            pmb_axes_dyn<NDIM>(g, w, info, one, x, pcsfix, B);
+            for (int d = 0; d < NDIM; d++)
+                for (int s = 0; s < S; s++) D[d][s] = B.V[d][s];
+        }
+        double value = 0, gr[3] = {0, 0, 0};
+#pragma unroll 1
+        for (int a = 0; a < S; a++) {
+            const int64_t o0 = A.off[0][a];
+#pragma unroll 1
+            for (int b = 0; b < (NDIM > 1 ? S : 1); b++) {
+                const int64_t o1 = NDIM > 1 ? A.off[NDIM > 1 ? 1 : 0][b] : 0;
+#pragma unroll 1
+                for (int c = 0; c < (NDIM > 2 ? S : 1); c++) {
+                    const int64_t o2 = NDIM > 2 ? A.off[NDIM > 2 ? 2 : 0][c] : 0;
+                    if (o0 == PMB_OFF_INVALID || o1 == PMB_OFF_INVALID || o2 == PMB_OFF_INVALID) continue;
+                    const double mval = pmb_mesh_ld<MeshT>(mesh, o0 + o1 + o2);
+                    const double v0 = A.V[0][a], d0 = D[0][a];
+                    const double v1 = NDIM > 1 ? A.V[NDIM > 1 ? 1 : 0][b] : 1.0;
+                    const double d1 = NDIM > 1 ? D[NDIM > 1 ? 1 : 0][b] : 1.0;
+                    const double v2 = NDIM > 2 ? A.V[NDIM > 2 ? 2 : 0][c] : 1.0;
+                    const double d2 = NDIM > 2 ? D[NDIM > 2 ? 2 : 0][c] : 1.0;
+                    value += ((v0 * v1) * v2) * mval;
+                    gr[0] += ((d0 * v1) * v2) * mval;
+                    if (NDIM > 1) gr[1] += ((v0 * d1) * v2) * mval;
+                    if (NDIM > 2) gr[2] += ((v0 * v1) * d2) * mval;
+                }
+            }
+        }
+        if (out) pmb_st_real_stream(out, i * out_stride, out_elsize, value);
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) pmb_st_real_stream(grad, i * gs0 + d * gs1, out_elsize, gr[d]);
+    }
+}
+
 // ------------------------------------------------------------------ deterministic paint
 // per-axis dense indices variant of the stencil walk for the deterministic path: we need the
 // C-order cell number (sort key), not the byte offset.  To share all arithmetic with the atomic
@@ -984,7 +1045,27 @@ extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *
     PMB_CHECK(pmb_resolve_window(ctx, a->kind, a->support, a->ndim, a->order, &w, 1));
     const int fam = fixed_family(w, a);
     if (!fam) {
-        // generic windows: value pass + one pass per axis through the ordinary readout kernel
+        // generic windows whose stencil fits the per-thread arrays: one fused sweep (pmb_k_readout_grad_dyn)
+        bool fits = !a->hsml;
+        if (fits) {
+            PmbWinInfo info;
+            pmb_window_info(w.nativesupport, w.support * a->hsml_scalar, &info);
+            fits = info.support <= PMB_MAX_SUPPORT;
+        }
+        if (fits && pmb_env_flag("PMB_GRAD_FUSED", 1)) {
+            const char *mesh = (const char *) a->mesh;
+            const int grid = pmb_grid(ctx, a->npart, 128, 8);
+            if (a->mesh_elsize == 8) {
+                PMB_DISPATCH_NDIM(a->ndim, (pmb_k_readout_grad_dyn<double, NDIM><<<grid, 128, 0, ctx->stream>>>(
+                    g, w, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1)));
+            } else {
+                PMB_DISPATCH_NDIM(a->ndim, (pmb_k_readout_grad_dyn<float, NDIM><<<grid, 128, 0, ctx->stream>>>(
+                    g, w, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1)));
+            }
+            PMB_LAUNCH_CHECK(ctx);
+            return PMB_OK;
+        }
+        // per-particle hsml or very wide stencils: value pass + one pass per axis through the ordinary readout kernel
         pmb_resample_args b = *a;
         if (a->out) PMB_CHECK(pmb_readout(ctx, &b));
         for (int d = 0; d < a->ndim; d++) {

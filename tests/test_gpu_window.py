@@ -390,3 +390,30 @@ def test_readout_multi_equals_single_readouts(W, oracle, order):
     outs = W.windows["tsc"].readout_multi([DeviceArray.from_host(f) for f in fields], dpos, transform=tr)
     for f, o in zip(fields, outs):
         assert_array_equal(o.to_host(), oracle.readout(f, pos, "tsc", period=[N] * 3))
+
+
+@pytest.mark.parametrize("name", ["lanczos3", "acg3", "db6", "cubic", "linear"])
+def test_fused_gradient_sweep_of_generic_windows(W, oracle, name):
+    """value + all gradients of a run-time-support window in ONE neighbourhood sweep (pmb_k_readout_grad_dyn)
+    == the separate readout(diffdir = d) calls == the oracle, bit for bit; 3-D periodic, 2-D non-periodic
+    and a translated slab canvas, f8 and f4 meshes"""
+    from pmesh_b200.device import DeviceArray
+    rng = numpy.random.default_rng(29)
+    for shape, translate, period in (((20, 18, 22), [0.0, 0.0, 0.0], [20, 18, 22]),
+                                     ((9, 18, 22), [-5.0, 0.0, 0.0], [20, 18, 22]),
+                                     ((24, 30), [1.5, -2.0], [0, 0])):
+        nd = len(shape)
+        pos = rng.uniform(-3, 25, (3000, nd))
+        dpos = DeviceArray.from_host(pos)
+        tr = W.Affine(nd, scale=1.0, translate=translate, period=period)
+        for dtype in ("f8", "f4"):
+            field = rng.uniform(-1, 1, shape).astype(dtype)
+            dfield = DeviceArray.from_host(field)
+            val, grad = W.windows[name].readout_grad(dfield, dpos, transform=tr)
+            assert_array_equal(val.to_host(), oracle.readout(field, pos, name, translate=translate, period=period))
+            gh = grad.to_host()
+            for d in range(nd):
+                want = oracle.readout(field, pos, name, diffdir=d, translate=translate, period=period)
+                assert_array_equal(gh[:, d], want)
+                sep = W.windows[name].readout(dfield, dpos, diffdir=d, transform=tr)
+                assert_array_equal(sep.to_host(), want)
