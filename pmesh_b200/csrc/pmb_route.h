@@ -105,6 +105,7 @@ template <int NDIM>
 PMB_HD uint64_t pmb_route_mask_x(const RouteGeom &g, const double *const *edges, const double *xin)
 {
     int sil[NDIM], sir[NDIM];
+    bool single = true;          // every axis so far has a patch of exactly one domain
 #pragma unroll
     for (int d = 0; d < NDIM; d++) {
         if (!pmb_route_axis_used(g, d)) {
@@ -127,22 +128,35 @@ PMB_HD uint64_t pmb_route_mask_x(const RouteGeom &g, const double *const *edges,
             // and between the same two edges, so l = r = p without two more searches
             const double cl = c - sm, cr = c + sm;
             if (sm >= 0.0 && p >= 1 && p < ne && cl >= 0.0 && cr < box && e[p - 1] <= cl && cr < e[p]) {
-                l = p; r = p;
+                // l = r = p: sil = p - (0 % shape) - 1, sir = p + (0 % shape), without the two integer divisions
+                l = p - 1; r = p;
             } else {
                 l = pmb_digitize_near(pmb_pymod_fast(cl, box), e, ne, inv_w);
                 r = pmb_digitize_near(pmb_pymod_fast(cr, box), e, ne, inv_w);
+                l = p - pmb_imod(p - l, g.shape[d]) - 1;
+                r = p + pmb_imod(r - p, g.shape[d]);
+                single = false;
             }
-            l = p - pmb_imod(p - l, g.shape[d]) - 1;
-            r = p + pmb_imod(r - p, g.shape[d]);
         } else {
             l = pmb_digitize_near(x - sm, e, ne, inv_w);
             r = pmb_digitize_near(x + sm, e, ne, inv_w);
             l = l - 1;
             l = l < 0 ? 0 : (l > g.shape[d] ? g.shape[d] : l);
             r = r < 0 ? 0 : (r > g.shape[d] ? g.shape[d] : r);
+            single = false;
         }
         sil[d] = (int) (int16_t) l;     // the reference stores sil/sir as int16 (domain.py:603-604)
         sir[d] = (int) (int16_t) r;
+    }
+    if (single) {
+        // the common case, particles well inside their domain on every axis: ONE patch cell, sil[d] = p - 1 in
+        // [0, shape) (1 <= p < nedges), no periodic wrap to apply -- the walk below reduces to one lookup
+        int target = 0;
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) target += sil[d] * g.dstride[d];
+        const int rank = g.assign[target];
+        const int deg = (rank >= 0 && rank < g.ndomains) ? g.degenerate[rank] : 0;
+        return (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) ? (uint64_t) 1 << rank : 0;
     }
     long long patch = 1;
     int p[NDIM];
