@@ -853,7 +853,8 @@ def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gat
         pos = layout.exchange(pos)
         gather = layout
     plan = gather.fused_gather_plan() if (gather is not None and is_device(pos)) else None
-    if plan is not None and len(fields) <= 3:
+    # the fused kernel exists for the CIC window on 3-D meshes with at least 2^18 particles (pmb_readout_multi_gather)
+    if plan is not None and len(fields) <= 3 and resampler.kind == 'tunedcic' and pm.ndim == 3 and pos.shape[0] >= (1 << 18):
         own_begin, own_count, own_index = plan
         nghost = int(pos.shape[0]) - own_count
         own = [DeviceArray.zeros((int(gather.sendlength),), 'f8') for _ in fields]
