@@ -163,6 +163,32 @@ def main():
         comm.Barrier()
         if r == 0:
             print("multirank ok: n=%d %s %s on %d ranks" % (n, res, dtype, P))
+    # 6c. the gather fused with the ghost sum (pm.readout_fields(..., gather=layout): the kernel writes the own
+    #     results straight into the gathered columns, only ghosts travel) == Layout.gather of separate readouts;
+    #     needs >= 2^18 local particles to take the fused kernel
+    from pmesh_b200.pm import apply_gradients, readout_fields
+    n, L = 48, 100.0
+    pm = ParticleMesh(BoxSize=L, Nmesh=[n, n, n], dtype="f8", resampler="cic", comm=comm)
+    mine = numpy.random.default_rng(900 + r).uniform(0, L, (300000 + 1000 * r, 3))
+    dmine = DeviceArray.from_host(mine)
+    layout = pm.decompose(dmine, smoothing=1.0 * pm.resampler.support)
+    lpos = layout.exchange(dmine)
+    assert lpos.shape[0] >= (1 << 18)
+    rhok = pm.paint(lpos).r2c()
+    fields = [t.c2r(out=Ellipsis) for t in apply_gradients(rhok, [T.GravityFD4(d) for d in range(3)])]
+    fused = readout_fields(fields, lpos, gather=layout)
+    for d in range(3):
+        sep = layout.gather(fields[d].readout(lpos))
+        assert rel(fused[d].to_host(), sep.to_host()) < 1e-14, "fused ghost sum differs"
+        one = rhok.apply(T.GravityFD4(d)).c2r()
+        assert numpy.array_equal(one.value, fields[d].value)          # three transfers in one pass == one at a time
+    two = readout_fields(fields[:2], lpos, gather=layout)
+    assert numpy.array_equal(two[1].to_host(), fused[1].to_host())
+    comm.Barrier()
+    if r == 0:
+        print("fused gather ok on %d ranks" % P)
+    del pm, layout, lpos, rhok, fields, fused, two
+
     # 7. pencil (2-D) process meshes, the reference's default for 3-D fields (pm.py:1319-1327): real space
     #    split along axes (0, 1), complex space along (1, 2); everything against the serial oracle
     meshes = {2: [[1, 2]], 4: [[2, 2], [1, 4]], 8: [[2, 4], [4, 2]]}.get(P, [])
