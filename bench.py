@@ -378,6 +378,7 @@ def run_ours(args):
     clocks = ClockSampler(ctx.device)
     ctx.launch_count(reset=True)
     pm.fft_library_ms(reset=True)
+    pm.fft_transpose_stats(reset=True)
     ctx.timer_start(0)
     for _ in range(args.steps):
         step(X, ntot, F)
@@ -386,6 +387,7 @@ def run_ours(args):
     stage_ms = dict((k, round(v / args.steps, 3)) for k, v in step.stage.items())
     launches = ctx.launch_count()
     fft_ms = pm.fft_library_ms()
+    xp_ms, xp_bytes = pm.fft_transpose_stats()
     clk = clocks.stop()
     ms_step = comm.allreduce(ms / args.steps, op=C.MAX)
     fft_step = comm.allreduce(fft_ms / args.steps, op=C.MAX)
@@ -527,6 +529,10 @@ def run_ours(args):
             "paint_readout_gparticles_per_s": main["paint_readout_gparticles_per_s"],
             "particles_per_s_force_step": round(ntot / (ms_step * 1e-3), 1),
             "cufft_library_ms_per_step": round(fft_step, 3),
+            "fft_transpose": None if comm.size == 1 else {
+                "ms_per_step": round(xp_ms / args.steps, 3), "nvlink_gb_per_step": round(xp_bytes / args.steps / 1e9, 3),
+                "nvlink_gbs_achieved": round(xp_bytes / max(xp_ms, 1e-9) / 1e6, 1), "nvlink_gbs_peak_measured": 770.0,
+                "note": "rank 0: bytes the fused transpose kernels stored into peer memory / their CUDA-event time"},
             "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "inputs": inputs, "e2e": e2e, "cpu_baseline": cpu,
             "verify": verify,

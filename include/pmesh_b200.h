@@ -281,6 +281,9 @@ int pmb_fft_layout(pmb_fft *plan, int64_t *i_start, int64_t *i_shape, int64_t *i
  * complex is preserved unless in place. */
 int pmb_fft_r2c(pmb_fft *plan, const void *real, void *cplx, double scale);
 int pmb_fft_c2r(pmb_fft *plan, const void *cplx, void *real);
+/* milliseconds spent inside the transpose kernels of the distributed transforms (events on the stream) and
+ * the bytes they stored into other ranks' landing buffers over NVLink since the last reset */
+int pmb_fft_transpose_stats(pmb_fft *plan, float *ms, double *remote_bytes, int reset);
 /* seconds spent inside cuFFT exec calls since the last reset, measured with events (library time) */
 int pmb_fft_library_ms(pmb_fft *plan, float *ms, int reset);
 

@@ -51,8 +51,11 @@ struct pmb_fft {
     void *peer_x[64][2];          // the same buffers of every rank, mapped into this process
     void *pool;                   // the pool entry that owns them
     cudaEvent_t ev[FFT_NEV][2];
+    int ev_kind[FFT_NEV];         // 0: a cuFFT exec (library time), 1: a transpose kernel of this library
     int nev;
     float lib_ms;
+    float xpose_ms;               // time inside the transpose (+ NVLink store) kernels
+    double xpose_remote_bytes;    // bytes they stored into OTHER ranks' landing buffers
     // device copies of the per-axis tables of the transfer functions (wavenumbers | multipliers), kept per
     // (kind, direction, box, parameters): the force step applies the same few transfers every step
     struct TfCache { int kind, dir; double box[3], p[2]; void *dev; } tfc[8];
@@ -443,14 +446,15 @@ static int lib_flush(pmb_fft *f)
     for (int i = 0; i < f->nev; i++) {
         float ms = 0;
         PMB_CUDA(cudaEventElapsedTime(&ms, f->ev[i][0], f->ev[i][1]));
-        f->lib_ms += ms;
+        if (f->ev_kind[i] == 0) f->lib_ms += ms; else f->xpose_ms += ms;
     }
     f->nev = 0;
     return PMB_OK;
 }
-static int lib_begin(pmb_fft *f)
+static int lib_begin(pmb_fft *f, int kind = 0)
 {
     if (f->nev == FFT_NEV) PMB_CHECK(lib_flush(f));
+    f->ev_kind[f->nev] = kind;
     PMB_CUDA(cudaEventRecord(f->ev[f->nev][0], f->ctx->stream));
     return PMB_OK;
 }
@@ -460,6 +464,18 @@ static int lib_end(pmb_fft *f)
     f->nev++;
     return PMB_OK;
 }
+// time spent in the transpose kernels and the bytes they stored over NVLink since the last reset:
+// achieved link bandwidth of this rank = remote_bytes / ms
+extern "C" int pmb_fft_transpose_stats(pmb_fft *f, float *ms, double *remote_bytes, int reset)
+{
+    PMB_REQUIRE(f && ms && remote_bytes, "null argument");
+    PMB_CHECK(lib_flush(f));
+    *ms = f->xpose_ms;
+    *remote_bytes = f->xpose_remote_bytes;
+    if (reset) { f->xpose_ms = 0; f->xpose_remote_bytes = 0; }
+    return PMB_OK;
+}
+
 extern "C" int pmb_fft_library_ms(pmb_fft *f, float *ms, int reset)
 {
     PMB_REQUIRE(f && ms, "null argument");
@@ -633,8 +649,12 @@ static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, i
     int64_t grid = tr * tc * ndest * nbatch;
     const int64_t cap = (int64_t) f->ctx->sm_count * 8;
     if (grid > cap) grid = cap;
+    PMB_CHECK(lib_begin(f, 1));
     pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
     PMB_LAUNCH_CHECK(f->ctx);
+    PMB_CHECK(lib_end(f));
+    for (int q = 0; q < ndest; q++)
+        if (q != me) f->xpose_remote_bytes += (double) R * (double) d.ncols[q] * (double) nbatch * (double) sizeof(C);
     return PMB_OK;
 }
 template <typename C>

@@ -1072,6 +1072,14 @@ class ParticleMesh(object):
         _lib.check(self.ctx.lib.pmb_fft_library_ms(self._plan, ctypes.byref(ms), int(reset)))
         return ms.value
 
+    def fft_transpose_stats(self, reset=False):
+        """ (ms, bytes): time inside the transpose kernels of the distributed transforms and the bytes they
+            stored into other ranks' memory over NVLink, since the last reset """
+        ms = ctypes.c_float()
+        nb = ctypes.c_double()
+        _lib.check(self.ctx.lib.pmb_fft_transpose_stats(self._plan, ctypes.byref(ms), ctypes.byref(nb), int(reset)))
+        return ms.value, nb.value
+
     def create_coords(self, field_type, return_indices=False):
         """ coordinate arrays (or integer indices) broadcastable to the field (reference pm.py:1505-1531) """
         field_type = _typestr_to_type(field_type)
