@@ -201,12 +201,11 @@ class ForceStep(object):
         self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
         self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
         self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
-        from pmesh_b200.pm import apply_gradients, readout_fields
+        from pmesh_b200.pm import apply_gradients, c2r_fields, readout_fields
         # the three gravity transfers read the density modes once (pm.apply_gradients) ...
         self._t("transfer", lambda: apply_gradients(self.rhok, self.tf, outs=self.tmp))
-        real = []
-        for d in range(3):
-            real.append(self._t("c2r", lambda: self.tmp[d].c2r(out=Ellipsis)))
+        # ... the three backward transforms overlap their NVLink transposes with each other's local FFTs
+        real = self._t("c2r", lambda: c2r_fields(self.tmp, outs=[Ellipsis] * 3))
         # the three force fields are read in ONE sweep over the particles (shared positions / weights)
         # ... and the ghost sum is fused into it: F[d] = layout.gather(real[d].readout(lpos)), nbody.py:214-216
         Fn = self._t("readout+gather", lambda: readout_fields(real, lpos, gather=layout))

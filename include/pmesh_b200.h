@@ -281,6 +281,10 @@ int pmb_fft_layout(pmb_fft *plan, int64_t *i_start, int64_t *i_shape, int64_t *i
  * complex is preserved unless in place. */
 int pmb_fft_r2c(pmb_fft *plan, const void *real, void *cplx, double scale);
 int pmb_fft_c2r(pmb_fft *plan, const void *cplx, void *real);
+/* n (<= 4) backward transforms, results equal to n pmb_fft_c2r calls.  On slab decompositions with peer-memory
+ * transposes the NVLink stores of every transform run on a second stream, under the cuFFT kernels of the others
+ * (the three c2r of a force evaluation, examples/nbody.py:211-213); PMB_FFT_OVERLAP=0 runs them one by one. */
+int pmb_fft_c2r_multi(pmb_fft *plan, int n, const void *const *cplx_h, void *const *real_h);
 /* milliseconds spent inside the transpose kernels of the distributed transforms (events on the stream) and
  * the bytes they stored into other ranks' landing buffers over NVLink since the last reset */
 int pmb_fft_transpose_stats(pmb_fft *plan, float *ms, double *remote_bytes, int reset);

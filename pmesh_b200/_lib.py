@@ -68,7 +68,7 @@ SYMBOLS = [
     "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments", "pmb_gather_add_segments",
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
-    "pmb_fft_create", "pmb_fft_create_np", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_library_ms", "pmb_fft_transpose_stats",
+    "pmb_fft_create", "pmb_fft_create_np", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_c2r_multi", "pmb_fft_library_ms", "pmb_fft_transpose_stats",
     "pmb_transfer", "pmb_transfer_scaled", "pmb_transfer_grad3", "pmb_cdot", "pmb_whitenoise",
 ]
 
@@ -115,7 +115,7 @@ _ARGTYPES = {
     "pmb_allreduce_f64": [_P, _P, _L, _I], "pmb_allgather_bytes": [_P, _P, _P, _L], "pmb_barrier": [_P],
     "pmb_fft_create": [_P, _I, _P, _I, _P], "pmb_fft_create_np": [_P, _I, _P, _I, _P, _P], "pmb_fft_destroy": [_P],
     "pmb_fft_layout": [_P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "pmb_fft_r2c": [_P, _P, _P, _D], "pmb_fft_c2r": [_P, _P, _P], "pmb_fft_library_ms": [_P, _P, _I], "pmb_fft_transpose_stats": [_P, _P, _P, _I],
+    "pmb_fft_r2c": [_P, _P, _P, _D], "pmb_fft_c2r": [_P, _P, _P], "pmb_fft_c2r_multi": [_P, _I, _P, _P], "pmb_fft_library_ms": [_P, _P, _I], "pmb_fft_transpose_stats": [_P, _P, _P, _I],
     "pmb_transfer": [_P, _I, _I, _P, _P, _P, _P],
     "pmb_transfer_scaled": [_P, _I, _I, _P, _P, _D, _P, _P],
     "pmb_cdot": [_P, _P, _P, _P],

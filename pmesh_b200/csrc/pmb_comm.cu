@@ -202,6 +202,22 @@ int pmb_stream_barrier(pmb_ctx *ctx)
     return PMB_OK;
 }
 
+// the same barrier on an explicit stream (the FFT's transpose stream); its own token so that it never shares
+// a buffer with a barrier of the compute stream
+int pmb_stream_barrier_on(pmb_ctx *ctx, cudaStream_t stream)
+{
+    if (ctx->nranks <= 1) return PMB_OK;
+    PMB_REQUIRE(ctx->comm, "communicator not initialised");
+    if (!ctx->barrier_token) {
+        PMB_CUDA(cudaMalloc(&ctx->barrier_token, 256));
+        PMB_CUDA(cudaMemsetAsync(ctx->barrier_token, 0, 256, ctx->stream));
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    char *tok = (char *) ctx->barrier_token + 128;
+    PMB_NCCL(g_nccl.AllReduce(tok, tok, 1, ncclInt, ncclMax, (ncclComm_t) ctx->comm, stream));
+    return PMB_OK;
+}
+
 // allgather of small host records (setup paths only): staged through device scratch, synchronous
 int pmb_allgather_host(pmb_ctx *ctx, const void *send_h, void *recv_h, size_t nbytes)
 {

@@ -54,6 +54,10 @@ struct pmb_fft {
     int ev_kind[FFT_NEV];         // 0: a cuFFT exec (library time), 1: a transpose kernel of this library
     int nev;
     float lib_ms;
+    // second stream for the transposes of pmb_fft_c2r_multi (NVLink stores overlap the cuFFT of the other transforms)
+    cudaStream_t xstream;
+    cudaEvent_t xev[16];
+    bool have_xstream;
     float xpose_ms;               // time inside the transpose (+ NVLink store) kernels
     double xpose_remote_bytes;    // bytes they stored into OTHER ranks' landing buffers
     // device copies of the per-axis tables of the transfer functions (wavenumbers | multipliers), kept per
@@ -400,6 +404,11 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
     }
     p2p_teardown(f);
     for (int i = 0; i < f->ntfc; i++) cudaFree(f->tfc[i].dev);
+    if (f->have_xstream) {
+        cudaStreamSynchronize(f->xstream);
+        cudaStreamDestroy(f->xstream);
+        for (int i = 0; i < 16; i++) cudaEventDestroy(f->xev[i]);
+    }
     if (f->work0) cudaFree(f->work0);
     if (f->work1) cudaFree(f->work1);
     for (int i = 0; i < FFT_NEV; i++) { cudaEventDestroy(f->ev[i][0]); cudaEventDestroy(f->ev[i][1]); }
@@ -639,8 +648,10 @@ pmb_k_xpose_scatter(const C *__restrict__ in, int64_t in_ld, int64_t R, int64_t 
 
 template <typename C>
 static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, int64_t out_ld, const XDest &d, double s,
-                         int ndest = -1, int me = -1, int64_t nbatch = 1, int64_t in_bs = 0)
+                         int ndest = -1, int me = -1, int64_t nbatch = 1, int64_t in_bs = 0, cudaStream_t stream = 0)
 {
+    const bool own_stream = stream != 0;        // a caller that runs the transposes on its own stream (c2r_multi)
+    if (!own_stream) stream = f->ctx->stream;
     if (ndest < 0) { ndest = f->P; me = f->rank; }
     int64_t cmax = 0;
     for (int q = 0; q < ndest; q++) if (d.ncols[q] > cmax) cmax = d.ncols[q];
@@ -649,12 +660,14 @@ static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, i
     int64_t grid = tr * tc * ndest * nbatch;
     const int64_t cap = (int64_t) f->ctx->sm_count * 8;
     if (grid > cap) grid = cap;
-    PMB_CHECK(lib_begin(f, 1));
-    pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, f->ctx->stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
+    if (!own_stream) PMB_CHECK(lib_begin(f, 1));       // event brackets are taken on the compute stream only
+    pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
     PMB_LAUNCH_CHECK(f->ctx);
-    PMB_CHECK(lib_end(f));
-    for (int q = 0; q < ndest; q++)
-        if (q != me) f->xpose_remote_bytes += (double) R * (double) d.ncols[q] * (double) nbatch * (double) sizeof(C);
+    if (!own_stream) {
+        PMB_CHECK(lib_end(f));
+        for (int q = 0; q < ndest; q++)
+            if (q != me) f->xpose_remote_bytes += (double) R * (double) d.ncols[q] * (double) nbatch * (double) sizeof(C);
+    }
     return PMB_OK;
 }
 template <typename C>
@@ -915,6 +928,88 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
         return PMB_OK;
     }
     return c2r_from_work(f, real);
+}
+
+// ---- several backward transforms with their transposes overlapped ------------------------------------
+// The three c2r of a force evaluation are independent; run one after the other each is
+//   L (lines along 0, cuFFT, HBM-bound) -> S (transpose + NVLink stores) -> barrier -> P (planes, cuFFT).
+// Here L and P of all transforms stay on the compute stream and every S (+ its barrier) goes to a second
+// stream: the NVLink stores of transform d run under the cuFFT kernels of transforms d - 1 and d + 1.
+// Buffers: work0 / work1 alternate as the source of S_d; the two landing buffers alternate as its target.
+// Ordering (events E; every barrier is issued on the transpose stream, so the NCCL calls of this communicator
+// never run concurrently):
+//   transpose stream: wait(entry) barrier | wait(L_d) [d >= 2: wait(P_{d-2}) barrier] S_d barrier rec(S_d) | ...
+//                     | wait(P_last) barrier rec(exit)
+//   compute stream:   rec(entry) L_0 rec L_1 rec | wait(S_d) P_d rec(P_d) ; L_{d+2} rec ... | wait(exit)
+// - the entry barrier: every rank has finished all earlier work (reads of both landing buffers included)
+//   before anybody stores into a peer;
+// - S_d (d >= 2) reuses the landing buffer of transform d - 2: it waits for P_{d-2} here AND, through the
+//   extra barrier, on every other rank;  L_{d+2} reuses the work buffer of S_d: it follows wait(S_d);
+// - the exit barrier: every rank has finished its last P before a later transform may store into it.
+extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, void *const *real_h)
+{
+    PMB_REQUIRE(f && cplx_h && real_h && n >= 1 && n <= 4, "bad arguments");
+    for (int d = 0; d < n; d++) PMB_REQUIRE(cplx_h[d] && real_h[d], "null field %d", d);
+    static int overlap = -1;
+    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    if (!(f->P > 1 && f->P1 == 1 && f->p2p && n >= 2 && overlap && f->work1)) {
+        for (int d = 0; d < n; d++) PMB_CHECK(pmb_fft_c2r(f, cplx_h[d], real_h[d]));
+        return PMB_OK;
+    }
+    pmb_ctx *ctx = f->ctx;
+    if (!f->have_xstream) {
+        PMB_CUDA(cudaStreamCreateWithFlags(&f->xstream, cudaStreamNonBlocking));
+        for (int i = 0; i < 16; i++) PMB_CUDA(cudaEventCreateWithFlags(&f->xev[i], cudaEventDisableTiming));
+        f->have_xstream = true;
+    }
+    cudaStream_t ms = ctx->stream, xs = f->xstream;
+    cudaEvent_t *evL = f->xev, *evS = f->xev + 4, *evP = f->xev + 8, evEntry = f->xev[12], evExit = f->xev[13];
+    void *wk[2] = {f->work0, f->work1};
+    int xb[4];
+    for (int d = 0; d < n; d++) { xb[d] = f->xcur; f->xcur ^= 1; }
+    // entry
+    PMB_CUDA(cudaEventRecord(evEntry, ms));
+    PMB_CUDA(cudaStreamWaitEvent(xs, evEntry, 0));
+    PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
+    auto line = [&](int d) -> int {          // L_d on the compute stream
+        if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx_h[d], wk[d & 1], CUFFT_INVERSE));
+        PMB_CUDA(cudaEventRecord(evL[d], ms));
+        return PMB_OK;
+    };
+    auto scatter = [&](int d) -> int {       // S_d + barrier on the transpose stream
+        PMB_CUDA(cudaStreamWaitEvent(xs, evL[d], 0));
+        if (d >= 2) {
+            PMB_CUDA(cudaStreamWaitEvent(xs, evP[d - 2], 0));
+            PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
+        }
+        XDest dst;
+        xdest_bwd(f, xb[d], &dst);
+        if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, wk[d & 1], f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
+        else PMB_CHECK(xpose_scatter<float2>(f, wk[d & 1], f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
+        PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
+        PMB_CUDA(cudaEventRecord(evS[d], xs));
+        return PMB_OK;
+    };
+    auto planes = [&](int d) -> int {        // P_d on the compute stream
+        PMB_CUDA(cudaStreamWaitEvent(ms, evS[d], 0));
+        if (f->m0 > 0) PMB_CHECK(exec_c2r(f, f->slab_c2r, f->xbuf[xb[d]], real_h[d]));
+        PMB_CUDA(cudaEventRecord(evP[d], ms));
+        return PMB_OK;
+    };
+    PMB_CHECK(line(0));
+    PMB_CHECK(scatter(0));
+    if (n > 1) PMB_CHECK(line(1));
+    for (int d = 0; d < n; d++) {
+        if (d + 1 < n) PMB_CHECK(scatter(d + 1));     // S_{d+1} is queued before P_d: it runs under it
+        PMB_CHECK(planes(d));
+        if (d + 2 < n) PMB_CHECK(line(d + 2));        // reuses the work buffer of S_d, which P_d has waited for
+    }
+    // exit
+    PMB_CUDA(cudaStreamWaitEvent(xs, evP[n - 1], 0));
+    PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
+    PMB_CUDA(cudaEventRecord(evExit, xs));
+    PMB_CUDA(cudaStreamWaitEvent(ms, evExit, 0));
+    return PMB_OK;
 }
 
 // steps 2-5 of the backward transform; work0 holds the axis-0 inverse-transformed lines (m1*nc, n0)

@@ -71,6 +71,7 @@ void pmb_set_error(const char *fmt, ...);
 int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out);
 int pmb_stream_barrier(pmb_ctx *ctx);
+int pmb_stream_barrier_on(pmb_ctx *ctx, cudaStream_t stream);
 int pmb_allgather_host(pmb_ctx *ctx, const void *send_h, void *recv_h, size_t nbytes);
 int pmb_resolve_window(pmb_ctx *ctx, int kind, int support_req, int ndim, const int *order,
                        PmbWindow *w, int for_device);

@@ -805,6 +805,40 @@ class TransposedComplexField(BaseComplexField):
 ComplexField = TransposedComplexField
 
 
+def c2r_fields(fields, outs=None):
+    """
+    ``[f.c2r(out=o) for f, o in zip(fields, outs)]`` (``outs`` None: new RealFields; Ellipsis entries: in place)
+    with the global transposes of the transforms overlapped with each other's local FFTs on P > 1 ranks
+    (engine extension, pmb_fft_c2r_multi; values equal the separate calls).
+    """
+    pm = fields[0].pm
+    if outs is None:
+        outs = [None] * len(fields)
+    res, cptr, rptr, pend = [], [], [], []
+    for f, o in zip(fields, outs):
+        assert isinstance(f, BaseComplexField) and f.pm is pm
+        if o is None:
+            o = RealField(pm)
+        if is_inplace(o) or o is f:
+            o = RealField(pm, f._base)
+        assert isinstance(o, RealField)
+        src = f._device(absorb=True)
+        cptr.append(src.ptr)
+        rptr.append(o._dev.ptr)
+        pend.append(f._pending)
+        res.append(o)
+    for i in range(0, len(fields), 4):
+        n = len(cptr[i:i + 4])
+        ca = (ctypes.c_void_p * n)(*cptr[i:i + 4])
+        ra = (ctypes.c_void_p * n)(*rptr[i:i + 4])
+        _lib.check(pm.ctx.lib.pmb_fft_c2r_multi(pm._plan, n, ca, ra))
+    for f, o, p in zip(fields, res, pend):
+        o._mark_device_written(pending=p)
+        if o._base is f._base:
+            f._host_valid = False
+    return res
+
+
 def apply_gradients(field, transfers, outs=None):
     """
     ``[field.apply(t, out=o) for t, o in zip(transfers, outs)]`` for the three gradient transfers of a force
