@@ -147,6 +147,13 @@ int pmb_readout_multi_gather(pmb_ctx *ctx, const pmb_resample_args *a, int nfiel
 /* fused value + ndim gradients in one neighbour sweep (paint_vjp / readout_vjp helper).
  * out_value may be NULL; out_grad is (npart, ndim) with byte strides gs0, gs1, element size out_elsize. */
 int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, int64_t gs0, int64_t gs1);
+/* Particle arrays WITHOUT spatial order (the reference makes no ordering assumption, _window.pyx:157-165): paint
+ * and readout of >= 2^18 particles on 3-D meshes work on a tile-sorted COPY of the position records kept in the
+ * context (a one-pass counting sort; reused only while a content hash of the caller's array is unchanged).
+ * pmb_bin_stats: reorders done so far and bytes held; pmb_bin_release frees the copy.  PMB_BIN=0 switches the
+ * reorder off (the kernels then walk the array through a permutation), PMB_BIN=2 reorders every large array. */
+int pmb_bin_stats(pmb_ctx *ctx, int64_t *builds, int64_t *bytes_held);
+int pmb_bin_release(pmb_ctx *ctx);
 
 /* elementwise helpers on (strided, up to 3-D) fields */
 int pmb_field_fill(pmb_ctx *ctx, void *mesh, int elsize, int ndim, const int64_t *size,
@@ -283,7 +290,7 @@ int pmb_fft_r2c(pmb_fft *plan, const void *real, void *cplx, double scale);
 int pmb_fft_c2r(pmb_fft *plan, const void *cplx, void *real);
 /* n (<= 4) backward transforms, results equal to n pmb_fft_c2r calls.  On slab decompositions with peer-memory
  * transposes the NVLink stores of every transform run on a second stream, under the cuFFT kernels of the others
- * (the three c2r of a force evaluation, examples/nbody.py:211-213); PMB_FFT_OVERLAP=0 runs them one by one. */
+ * (the three c2r of a force evaluation, examples/nbody.py:211-213); with PMB_FFT_OVERLAP=1 (default 0: one by one; measured at 2 GPUs, profiles/README.md). */
 int pmb_fft_c2r_multi(pmb_fft *plan, int n, const void *const *cplx_h, void *const *real_h);
 /* milliseconds spent inside the transpose kernels of the distributed transforms (events on the stream) and
  * the bytes they stored into other ranks' landing buffers over NVLink since the last reset */

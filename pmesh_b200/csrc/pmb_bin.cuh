@@ -1,0 +1,418 @@
+// pmb_bin.cuh -- physical reorder of the particle records by mesh tile, for particle arrays WITHOUT
+// spatial order in memory.
+//
+// Walking unordered particles through a permutation (pmb_perm.cuh) fixes the mesh traffic but leaves one
+// random 24-byte fetch and one random 8-byte store per particle: 1024^3 uniform random particles on a B200
+// paint in 150 ms and gather in 154 ms, the price of 1.6 G random DRAM sectors (profiles/README.md).
+// Here the RECORDS are moved, once, by a one-pass counting sort:
+//
+//   count    tile of every particle (T0 x T1 x 128 cells, <= 32768 tiles) into a shared-memory histogram
+//            per CTA, flushed with one red per non-empty (CTA, tile); the same pass folds the position
+//            bits and particle numbers into a 128-bit content hash
+//   scan     exclusive prefix of the tile counts = first slot of every tile (one CTA)
+//   scatter  slot d = atomicAdd(cursor[tile], 1); sorted[d] = (x, y, z, i) as ONE 32-byte store; dest[i] = d
+//
+// The scatter's stores go to <= 32768 write fronts that advance 24 bytes at a time: the fronts live in L2
+// (4 MB of lines), every DRAM line of the sorted copy is written once, whole.  dest[] is written in the
+// original order, coalesced.  The sorted copy is then painted / read by the ordinary kernels (contiguous
+// float64 rows: bulk-copy ring and all), and results return to the original order by the mirror image of
+// the scatter, out[i] = tmp[dest[i]]: reads from the same fronts in the same traversal order.
+//
+// Slots inside a tile are handed out in arrival order, so the sorted order is not reproducible from run to
+// run: the atomic paint does not care (its order of additions never was), every gather result is computed
+// per particle and is bit-identical whatever the order.
+//
+// The sorted copy is cached in the context.  It is VALID only for the exact content it was made from:
+// reuse requires the same array (address, count, strides, geometry) AND an equal content hash, recomputed
+// by a read-only pass (~1/5 of the cost of the reorder).  A force step therefore sorts once: the paint
+// builds the copy, the gather of the three force fields re-validates and reuses it.
+#pragma once
+#include "pmb_perm.cuh"
+
+#define PMB_BIN_MAXTILES 32768            // tiles a shared-memory histogram holds (128 KB)
+#define PMB_BIN_HARDTILES (1 << 20)       // tiles the counter arrays hold (PMB_BIN_TILES > 32768: histogram by global reds)
+#define PMB_BIN_COUNT_THREADS 1024
+
+struct PmbBinTiling {
+    int s0, s1, s2;        // log2 of the tile extent along axes 0, 1, 2 (cells)
+    int n1, n2;            // tiles along axes 1, 2
+    int ntiles;
+};
+
+// tiles of 8 x 8 x 2^PMB_BIN_TZ cells (default 64 along the contiguous axis), doubled along axes 0 / 1 until
+// at most PMB_BIN_TILES (default 262144) cover the canvas.  Measured at 1024^3 uniform random (B200, ms; tiles
+// 16x16x128 / 8x8x64 / 8x8x32): scatter 24.1 / 24.2 / 25.0, ring gather 23.9 / 21.0 / 19.9, return pass 22.4 each with
+// 12.9 / 14.4 / 31.1 GB of DRAM reads (the read fronts of 2^20 tiles no longer fit in L2)
+static void pmb_bin_tiling(const PmbGeom &g, PmbBinTiling *t)
+{
+    int64_t maxtiles = pmb_env_flag("PMB_BIN_TILES", 262144);
+    if (maxtiles < 64) maxtiles = 64;
+    if (maxtiles > PMB_BIN_HARDTILES) maxtiles = PMB_BIN_HARDTILES;
+    t->s0 = t->s1 = 3;
+    t->s2 = pmb_env_flag("PMB_BIN_TZ", 6);
+    if (t->s2 < 3) t->s2 = 3;
+    if (t->s2 > 10) t->s2 = 10;
+    for (;;) {
+        const int64_t n0 = (g.size[0] + (1 << t->s0) - 1) >> t->s0;
+        const int64_t n1 = (g.size[1] + (1 << t->s1) - 1) >> t->s1;
+        const int64_t n2 = (g.size[2] + (1 << t->s2) - 1) >> t->s2;
+        if (n0 * n1 * n2 <= maxtiles) {
+            t->n1 = (int) n1; t->n2 = (int) n2; t->ntiles = (int) (n0 * n1 * n2);
+            return;
+        }
+        if (t->s0 <= t->s1) t->s0++; else t->s1++;
+    }
+}
+
+__device__ __forceinline__ uint32_t pmb_bin_tile(const PmbGeom &g, const PmbBinTiling &t, const double *x)
+{
+    const int c0 = pmb_cell_of(x[0], g.scale[0], g.translate[0], g.period[0], g.size[0]) >> t.s0;
+    const int c1 = pmb_cell_of(x[1], g.scale[1], g.translate[1], g.period[1], g.size[1]) >> t.s1;
+    const int c2 = pmb_cell_of(x[2], g.scale[2], g.translate[2], g.period[2], g.size[2]) >> t.s2;
+    return (uint32_t) ((c0 * t.n1 + c1) * t.n2 + c2);
+}
+
+__device__ __forceinline__ uint64_t pmb_mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// content hash of one record: a chain over (particle number, x0, x1, x2); the array's hash is the pair of
+// wrapping sums of u and mix(u + c) over all records (independent of the order of summation)
+__device__ __forceinline__ void pmb_bin_hash(int64_t i, const double *x, uint64_t &h1, uint64_t &h2)
+{
+    uint64_t u = pmb_mix64((uint64_t) i * 0x9E3779B97F4A7C15ull + 0xD6E8FEB86659FD93ull);
+    u = pmb_mix64(u ^ (uint64_t) __double_as_longlong(x[0]));
+    u = pmb_mix64(u ^ (uint64_t) __double_as_longlong(x[1]));
+    u = pmb_mix64(u ^ (uint64_t) __double_as_longlong(x[2]));
+    h1 += u;
+    h2 += pmb_mix64(u + 0xA0761D6478BD642Full);
+}
+
+// COUNT 1: tile histogram in dynamic shared memory (ntiles words) + hash; 2: histogram by global reds + hash
+// (more tiles than shared memory holds); 0: hash only
+template <int COUNT>
+__global__ void __launch_bounds__(PMB_BIN_COUNT_THREADS, 1)
+pmb_k_bin_count(PmbGeom g, PmbParticles p, int64_t npart, PmbBinTiling t, uint32_t *counts, unsigned long long *hash)
+{
+    extern __shared__ uint32_t s_hist[];
+    if (COUNT == 1) {
+        for (int k = threadIdx.x; k < t.ntiles; k += blockDim.x) s_hist[k] = 0;
+        __syncthreads();
+    }
+    uint64_t h1 = 0, h2 = 0;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (int64_t i0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i0 < npart; i0 += U * stride) {
+        double x[U][3];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < npart) pmb_load_pos<3>(p, i, x[u], 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i >= npart) break;
+            pmb_bin_hash(i, x[u], h1, h2);
+            if (COUNT == 1) atomicAdd(&s_hist[pmb_bin_tile(g, t, x[u])], 1u);
+            if (COUNT == 2) atomicAdd(&counts[pmb_bin_tile(g, t, x[u])], 1u);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        h1 += __shfl_xor_sync(0xffffffffu, (unsigned long long) h1, o);
+        h2 += __shfl_xor_sync(0xffffffffu, (unsigned long long) h2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(hash, (unsigned long long) h1);
+        atomicAdd(hash + 1, (unsigned long long) h2);
+    }
+    if (COUNT == 1) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < t.ntiles; k += blockDim.x) {
+            const uint32_t c = s_hist[k];
+            if (c) atomicAdd(&counts[k], c);
+        }
+    }
+}
+
+// exclusive prefix sum of the tile counts (one CTA of 1024 threads, ntiles / 1024 tiles per thread)
+__global__ void __launch_bounds__(1024)
+pmb_k_bin_scan(const uint32_t *__restrict__ counts, uint32_t *__restrict__ cursors, int ntiles, int cstride)
+{
+    __shared__ uint32_t s[1024];
+    const int per = (ntiles + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; k++) if (b0 + k < ntiles) sum += counts[b0 + k];
+    s[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s[threadIdx.x] - sum;
+    for (int k = 0; k < per; k++)
+        if (b0 + k < ntiles) { cursors[(size_t) (b0 + k) * cstride] = run; run += counts[b0 + k]; }
+}
+
+// Work is handed out in chunks of 256 * U particles through a ticket counter: the chunks in flight are one
+// compact window of the array however unevenly the CTAs progress, so slots are handed out in nearly the
+// caller's order and the return pass (same traversal) finds its rows near the fronts it reads.
+// `variant` (PMB_BIN_VARIANT, measurements only -- anything but 0 does NOT sort): 1 slot = i (no atomics),
+// 2 atomics but slot = i, 3 pseudo-random slot (no atomics).  `cstride`: words between two cursors.
+__global__ void __launch_bounds__(256)
+pmb_k_bin_scatter(PmbGeom g, PmbParticles p, int64_t npart, PmbBinTiling t, uint32_t *cursors, int cstride,
+                  double *__restrict__ spos, uint32_t *__restrict__ dest, unsigned long long *ticket, int variant)
+{
+    constexpr int U = 4;
+    __shared__ unsigned long long s_tk[2];
+    const int64_t nchunks = (npart + 256 * U - 1) / (256 * U);
+    if (threadIdx.x == 0) s_tk[0] = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int64_t c = (int64_t) s_tk[it & 1];
+        if (c >= nchunks) break;
+        if (threadIdx.x == 0) s_tk[(it + 1) & 1] = atomicAdd(ticket, 1ull);    // the next ticket travels under this chunk's work
+        const int64_t i0 = c * (256 * U) + threadIdx.x;
+        double x[U][3];
+        uint32_t d[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * 256;
+            if (i < npart) pmb_load_pos<3>(p, i, x[u], 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * 256;
+            if (i < npart) {
+                if (variant == 1) d[u] = (uint32_t) i;
+                else if (variant == 3) d[u] = (uint32_t) (pmb_mix64((uint64_t) i) % (uint64_t) npart);
+                else {
+                    d[u] = atomicAdd(&cursors[(size_t) pmb_bin_tile(g, t, x[u]) * cstride], 1u);
+                    if (variant == 2) d[u] = (uint32_t) i;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * 256;
+            if (i >= npart) break;
+            // one full, aligned 32-byte sector per record: (x, y, z, particle number).  Three 8-byte stores cost three
+            // partial-sector transactions in L2 and made this kernel 4 x slower (profiles/README.md)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(spos + 4 * (int64_t) d[u]), "d"(x[u][0]), "d"(x[u][1]),
+                         "d"(x[u][2]), "d"(__longlong_as_double((long long) i)) : "memory");
+            __stcs(dest + i, d[u]);
+        }
+        __syncthreads();
+    }
+}
+
+// a per-particle column into the sorted order (mass): sorted[dest[i]] = column[i]
+__global__ void __launch_bounds__(256)
+pmb_k_bin_column(const void *col, int elsize, int64_t stride_bytes, int64_t npart, const uint32_t *__restrict__ dest,
+                 double *__restrict__ sorted)
+{
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < npart; i += stride)
+        sorted[__ldcs(dest + i)] = pmb_ld_real_stream(col, i * stride_bytes, elsize);
+}
+
+// results back to the original order: particle i's values are row dest[i] of the (npart, NF) staging array
+template <int NF>
+__global__ void __launch_bounds__(256)
+pmb_k_bin_unsort(PmbFields f, const double *__restrict__ tmp, const uint32_t *__restrict__ dest, int64_t npart,
+                 unsigned long long *ticket)
+{
+    constexpr int U = 4;
+    __shared__ unsigned long long s_tk[2];
+    const int64_t nchunks = (npart + 256 * U - 1) / (256 * U);
+    if (threadIdx.x == 0) s_tk[0] = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int64_t c = (int64_t) s_tk[it & 1];
+        if (c >= nchunks) break;
+        if (threadIdx.x == 0) s_tk[(it + 1) & 1] = atomicAdd(ticket, 1ull);
+        const int64_t i0 = c * (256 * U) + threadIdx.x;
+        double v[U][NF];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * 256;
+            if (i < npart) {
+                const double *r = tmp + (int64_t) NF * __ldcs(dest + i);
+#pragma unroll
+                for (int q = 0; q < NF; q++) v[u][q] = r[q];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * 256;
+            if (i >= npart) break;
+#pragma unroll
+            for (int q = 0; q < NF; q++) pmb_store_result(f, q, i, v[u][q]);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static inline uint64_t pmb_hostmix(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct PmbBinned {
+    const double *pos;       // sorted (npart, 4) float64 records (x, y, z, particle number); NULL: the array is used as it is
+    const uint32_t *dest;    // slot of original particle i
+    int verdict;             // 0: chunks are compact; 1: scattered, sorted copy in pos / dest; 2: not decided here
+                             //    (reorder switched off or out of memory): pmb_perm_prepare serves the array
+};
+
+static void *pmb_bin_try_scratch(pmb_ctx *ctx, size_t nbytes)
+{
+    void *o = NULL;
+    if (pmb_scratch(ctx, nbytes, &o) != PMB_OK) { cudaGetLastError(); return NULL; }
+    return o;
+}
+
+static int pmb_bin_grow(pmb_ctx *ctx, void **buf, size_t *have, size_t need)
+{
+    if (need <= *have) return PMB_OK;
+    if (*buf) { PMB_CUDA(cudaStreamSynchronize(ctx->stream)); PMB_CUDA(cudaFree(*buf)); *buf = NULL; *have = 0; }
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e != cudaSuccess) { cudaGetLastError(); *buf = NULL; return PMB_ENOMEM; }
+    *have = need;
+    return PMB_OK;
+}
+
+static void pmb_bin_free(pmb_ctx *ctx)
+{
+    if (ctx->bin_pos) cudaFree(ctx->bin_pos);
+    if (ctx->bin_dest) cudaFree(ctx->bin_dest);
+    if (ctx->bin_col) cudaFree(ctx->bin_col);
+    if (ctx->bin_small) cudaFree(ctx->bin_small);
+    ctx->bin_pos = ctx->bin_dest = ctx->bin_col = ctx->bin_small = NULL;
+    ctx->bin_pos_bytes = ctx->bin_dest_bytes = ctx->bin_col_bytes = 0;
+    ctx->bin_sig = 0; ctx->bin_state = 0; ctx->bin_npart = -1;
+}
+
+// b->pos = the tile-sorted copy of the positions when the particle array is scattered in memory, NULL when its
+// chunks are compact, when the reorder is switched off (PMB_BIN=0) or when its buffers do not fit in memory
+// (the callers then fall back to the permutation walk).  PMB_BIN=2 reorders whatever the probe says.
+static int pmb_bin_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart, PmbBinned *b)
+{
+    b->pos = NULL; b->dest = NULL; b->verdict = 2;
+    const int mode = pmb_env_flag("PMB_BIN", 1);
+    if (!mode || ctx->bin_bypass || g.ndim != 3 || npart < ((int64_t) 1 << 18) || npart >= ((int64_t) 1 << 31)) return PMB_OK;
+    uint64_t sig = (uint64_t) (uintptr_t) p.pos * 0x9E3779B97F4A7C15ull ^ (uint64_t) npart * 0xD6E8FEB86659FD93ull
+                   ^ (uint64_t) p.ps0 * 31 ^ (uint64_t) p.ps1 * 131 ^ (uint64_t) p.pos_elsize
+                   ^ ((uint64_t) g.size[0] << 40) ^ ((uint64_t) g.size[1] << 20) ^ (uint64_t) g.size[2];
+    for (int d = 0; d < 3; d++) {
+        uint64_t w;
+        memcpy(&w, &g.translate[d], sizeof(w)); sig ^= pmb_hostmix(w + d);
+        memcpy(&w, &g.scale[d], sizeof(w)); sig ^= pmb_hostmix(w + 8 + d);
+        sig ^= pmb_hostmix((uint64_t) g.period[d] + 16 + d);
+    }
+    if (!sig) sig = 1;
+    if (!ctx->bin_small) {
+        PMB_CUDA(cudaMalloc(&ctx->bin_small, 256 + 2 * sizeof(uint32_t) * PMB_BIN_HARDTILES));
+        static bool attr_done = false;
+        if (!attr_done) {
+            PMB_CUDA(cudaFuncSetAttribute(pmb_k_bin_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int) (sizeof(uint32_t) * PMB_BIN_MAXTILES)));
+            attr_done = true;
+        }
+    }
+    unsigned long long *d_hash = (unsigned long long *) ctx->bin_small;          // [0..1] hash, [2] probe counter
+    uint32_t *d_counts = (uint32_t *) ((char *) ctx->bin_small + 256), *d_cursors = d_counts + PMB_BIN_HARDTILES;
+    PmbBinTiling t;
+    pmb_bin_tiling(g, &t);
+    const bool same = ctx->bin_sig == sig && ctx->bin_npart == npart;
+    if (same && ctx->bin_state == 0 && ctx->bin_uses < 8) { ctx->bin_uses++; b->verdict = 0; return PMB_OK; }
+    unsigned long long hash[4] = {0, 0, 0, 0};
+    if (same && ctx->bin_state == 1) {
+        // the cached copy is good for exactly the content it was made from
+        PMB_CUDA(cudaMemsetAsync(d_hash, 0, 32, ctx->stream));
+        pmb_k_bin_count<0><<<ctx->sm_count, PMB_BIN_COUNT_THREADS, 0, ctx->stream>>>(g, p, npart, t, d_counts, d_hash);
+        PMB_LAUNCH_CHECK(ctx);
+        PMB_CUDA(cudaMemcpyAsync(hash, d_hash, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hash[0] == ctx->bin_hash[0] && hash[1] == ctx->bin_hash[1]) {
+            b->pos = (const double *) ctx->bin_pos; b->dest = (const uint32_t *) ctx->bin_dest; b->verdict = 1;
+            return PMB_OK;
+        }
+    }
+    // ---- probe (pmb_perm.cuh): are 256-particle chunks compact in space? ----
+    ctx->bin_sig = sig; ctx->bin_npart = npart; ctx->bin_uses = 1; ctx->bin_state = 0;
+    if (mode < 2) {
+        const int64_t nchunks = (npart + PMB_CHUNK - 1) / PMB_CHUNK;
+        const int nsamples = 512;
+        unsigned int *d_scat = (unsigned int *) (d_hash + 2);
+        PMB_CUDA(cudaMemsetAsync(d_scat, 0, sizeof(unsigned int), ctx->stream));
+        pmb_k_probe_chunks<<<(nsamples + 127) / 128, 128, 0, ctx->stream>>>(g, p, npart, nchunks, nsamples, d_scat);
+        PMB_LAUNCH_CHECK(ctx);
+        unsigned int scattered = 0;
+        PMB_CUDA(cudaMemcpyAsync(&scattered, d_scat, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (scattered * 4 <= (unsigned) nsamples) { b->verdict = 0; return PMB_OK; }
+    }
+    // ---- reorder ----
+    if (pmb_bin_grow(ctx, &ctx->bin_pos, &ctx->bin_pos_bytes, sizeof(double) * 4 * (size_t) npart) != PMB_OK ||
+        pmb_bin_grow(ctx, &ctx->bin_dest, &ctx->bin_dest_bytes, sizeof(uint32_t) * (size_t) npart) != PMB_OK) {
+        ctx->bin_sig = 0;       // no room: the permutation walk serves this array
+        return PMB_OK;
+    }
+    PMB_CUDA(cudaMemsetAsync(ctx->bin_small, 0, 256 + sizeof(uint32_t) * t.ntiles, ctx->stream));
+    if (t.ntiles <= PMB_BIN_MAXTILES)
+        pmb_k_bin_count<1><<<ctx->sm_count, PMB_BIN_COUNT_THREADS, sizeof(uint32_t) * t.ntiles, ctx->stream>>>(g, p, npart, t, d_counts, d_hash);
+    else
+        pmb_k_bin_count<2><<<ctx->sm_count, PMB_BIN_COUNT_THREADS, 0, ctx->stream>>>(g, p, npart, t, d_counts, d_hash);
+    PMB_LAUNCH_CHECK(ctx);
+    const int cstride = 1;     // measured: cursors one per 128-byte line change nothing
+    pmb_k_bin_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, d_cursors, t.ntiles, cstride);
+    PMB_LAUNCH_CHECK(ctx);
+    pmb_k_bin_scatter<<<pmb_grid(ctx, npart, 256 * 4, pmb_env_flag("PMB_BIN_SCATTER_CTAS", 4)), 256, 0, ctx->stream>>>(
+        g, p, npart, t, d_cursors, cstride, (double *) ctx->bin_pos, (uint32_t *) ctx->bin_dest,
+        (unsigned long long *) ((char *) ctx->bin_small + 64), pmb_env_flag("PMB_BIN_VARIANT", 0));
+    PMB_LAUNCH_CHECK(ctx);
+    PMB_CUDA(cudaMemcpyAsync(hash, d_hash, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bin_hash[0] = hash[0]; ctx->bin_hash[1] = hash[1];
+    ctx->bin_state = 1;
+    ctx->bin_builds++;
+    b->pos = (const double *) ctx->bin_pos; b->dest = (const uint32_t *) ctx->bin_dest; b->verdict = 1;
+    return PMB_OK;
+}
+
+// a per-particle column of the caller in sorted order (never cached: it is re-made from the caller's column)
+static int pmb_bin_column(pmb_ctx *ctx, const PmbBinned &b, const void *col, int elsize, int64_t stride_bytes, int64_t npart,
+                          const double **sorted)
+{
+    *sorted = NULL;
+    if (pmb_bin_grow(ctx, &ctx->bin_col, &ctx->bin_col_bytes, sizeof(double) * (size_t) npart) != PMB_OK) {
+        pmb_set_error("out of device memory for the sorted mass column (%lld particles)", (long long) npart);
+        return PMB_ENOMEM;
+    }
+    pmb_k_bin_column<<<pmb_grid(ctx, npart, 256, 8), 256, 0, ctx->stream>>>(col, elsize, stride_bytes, npart, b.dest, (double *) ctx->bin_col);
+    PMB_LAUNCH_CHECK(ctx);
+    *sorted = (const double *) ctx->bin_col;
+    return PMB_OK;
+}
+
+static int pmb_bin_unsort(pmb_ctx *ctx, const PmbBinned &b, const PmbFields &f, int nf, const double *tmp, int64_t npart)
+{
+    const int grid = pmb_grid(ctx, npart, 256 * 4, pmb_env_flag("PMB_BIN_UNSORT_CTAS", 6));
+    unsigned long long *ticket = (unsigned long long *) ((char *) ctx->bin_small + 64);
+    PMB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx->stream));
+    if (nf == 1) pmb_k_bin_unsort<1><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
+    else if (nf == 2) pmb_k_bin_unsort<2><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
+    else pmb_k_bin_unsort<3><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
+    PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}

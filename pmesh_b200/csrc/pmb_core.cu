@@ -81,6 +81,10 @@ extern "C" int pmb_ctx_destroy(pmb_ctx *ctx)
     if (ctx->route_blockhist) cudaFree(ctx->route_blockhist);
     if (ctx->sched_buf) cudaFree(ctx->sched_buf);
     if (ctx->perm_ids) cudaFree(ctx->perm_ids);
+    if (ctx->bin_pos) cudaFree(ctx->bin_pos);
+    if (ctx->bin_dest) cudaFree(ctx->bin_dest);
+    if (ctx->bin_col) cudaFree(ctx->bin_col);
+    if (ctx->bin_small) cudaFree(ctx->bin_small);
     if (ctx->streams_ready) {
         for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->copy_stream[i]); cudaStreamDestroy(ctx->copy_stream[i]); }
         for (int i = 0; i < PMB_NTIMERS; i++) cudaEventDestroy(ctx->sev[i]);

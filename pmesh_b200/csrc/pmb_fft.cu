@@ -658,7 +658,11 @@ static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, i
     if (R == 0 || cmax == 0 || nbatch == 0) return PMB_OK;
     const int64_t tr = (R + 31) / 32, tc = (cmax + 31) / 32;
     int64_t grid = tr * tc * ndest * nbatch;
-    const int64_t cap = (int64_t) f->ctx->sm_count * 8;
+    // on its own stream the transpose shares the SMs with the cuFFT kernels of the other transforms: a few
+    // resident CTAs per SM keep the link busy (the kernel waits on NVLink stores) without starving them
+    static int octas = -1;
+    if (octas < 0) { const char *e = getenv("PMB_FFT_OVERLAP_CTAS"); octas = e ? atoi(e) : 1; if (octas < 1) octas = 1; }
+    const int64_t cap = (int64_t) f->ctx->sm_count * (own_stream ? octas : 8);
     if (grid > cap) grid = cap;
     if (!own_stream) PMB_CHECK(lib_begin(f, 1));       // event brackets are taken on the compute stream only
     pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
@@ -951,14 +955,16 @@ extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, v
     PMB_REQUIRE(f && cplx_h && real_h && n >= 1 && n <= 4, "bad arguments");
     for (int d = 0; d < n; d++) PMB_REQUIRE(cplx_h[d] && real_h[d], "null field %d", d);
     static int overlap = -1;
-    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 0; }
     if (!(f->P > 1 && f->P1 == 1 && f->p2p && n >= 2 && overlap && f->work1)) {
         for (int d = 0; d < n; d++) PMB_CHECK(pmb_fft_c2r(f, cplx_h[d], real_h[d]));
         return PMB_OK;
     }
     pmb_ctx *ctx = f->ctx;
     if (!f->have_xstream) {
-        PMB_CUDA(cudaStreamCreateWithFlags(&f->xstream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        PMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        PMB_CUDA(cudaStreamCreateWithPriority(&f->xstream, cudaStreamNonBlocking, prio_hi));
         for (int i = 0; i < 16; i++) PMB_CUDA(cudaEventCreateWithFlags(&f->xev[i], cudaEventDisableTiming));
         f->have_xstream = true;
     }

@@ -65,6 +65,21 @@ struct pmb_ctx {
     uint64_t perm_sig;
     int perm_uses;
     int perm_state;          // verdict of the last probe: 0 chunks are compact, 1 scattered (permutation in perm_ids)
+    // tile-sorted copy of a particle array without spatial order (pmb_bin.cuh)
+    void *bin_pos;           // (npart, 4) float64 records (x, y, z, particle number) in tile order
+    size_t bin_pos_bytes;
+    void *bin_dest;          // uint32 slot of original particle i
+    size_t bin_dest_bytes;
+    void *bin_col;           // a per-particle column (mass) in tile order
+    size_t bin_col_bytes;
+    void *bin_small;         // hash words, probe counter, tile counts and cursors
+    int64_t bin_npart;
+    uint64_t bin_sig;
+    unsigned long long bin_hash[2];   // content hash of the array the copy was made from
+    int bin_state;           // 0: the array's chunks are compact (nothing cached), 1: sorted copy in bin_pos / bin_dest
+    int bin_uses;
+    int bin_bypass;          // set while the ordinary kernels run on the sorted copy
+    int64_t bin_builds;      // reorders done (diagnostics)
 };
 
 void pmb_set_error(const char *fmt, ...);

@@ -159,16 +159,17 @@ static int pmb_perm_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &
 // ---- kernels that walk the particles through the permutation -----------------------------------------
 // CIC, 32-bit element indices (the lean arithmetic of pmb_k_paint_cic_carry32); plain reds: the tile's
 // mesh lines are L2 resident
+// `ticket` non-NULL: 256-particle chunks are handed out through a ticket counter instead of the grid-stride loop
+// (all CTAs stay inside one compact window of the array)
 template <typename MeshT, bool CHECK>
 __global__ void __launch_bounds__(256)
-pmb_k_paint_cic32_perm(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart, const uint32_t *__restrict__ perm)
+pmb_k_paint_cic32_perm(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart, const uint32_t *__restrict__ perm,
+                       unsigned long long *ticket)
 {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (; j < npart; j += stride) {
-        const int64_t i = perm[j];
+    auto body = [&](int64_t j) {
+        const int64_t i = perm ? (int64_t) perm[j] : j;     // NULL: the array is already in tile order (pmb_bin.cuh)
         double x[3];
         pmb_load_pos<3>(p, i, x);
         const double m = pmb_load_mass(p, i);
@@ -186,7 +187,22 @@ pmb_k_paint_cic32_perm(PmbGeom32 g, PmbParticles p, MeshT *mesh, int64_t npart, 
                     if (CHECK && (ex[a] < 0 || ey[b] < 0 || ez[c] < 0)) continue;
                     pmb_red<MeshT>((char *) mesh, (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), ((Vx[a] * m) * Vy[b]) * Vz[c], policy);
                 }
+    };
+    if (ticket) {
+        __shared__ unsigned long long s_tk;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tk = atomicAdd(ticket, 1ull);
+            __syncthreads();
+            const int64_t j = (int64_t) s_tk * 256 + threadIdx.x;
+            if ((int64_t) s_tk * 256 >= npart) break;
+            if (j < npart) body(j);
+        }
+        return;
     }
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < npart; j += stride) body(j);
 }
 
 template <typename MeshT, bool CHECK, int NF>
@@ -198,7 +214,7 @@ pmb_k_readout_cic32_perm(PmbGeom32 g, PmbParticles p, PmbFields f, int64_t npart
     int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (; j < npart; j += stride) {
-        const int64_t i = perm[j];
+        const int64_t i = perm ? (int64_t) perm[j] : j;     // NULL: the array is already in tile order (pmb_bin.cuh)
         double x[3];
         pmb_load_pos<3>(p, i, x);
         double Vx[2], Vy[2], Vz[2];
@@ -227,14 +243,13 @@ pmb_k_readout_cic32_perm(PmbGeom32 g, PmbParticles p, PmbFields f, int64_t npart
 // every tuned window (and gradient windows): the generic fixed-support stencil walk
 template <typename MeshT, int FAM, bool CHECK>
 __global__ void __launch_bounds__(256)
-pmb_k_paint_perm(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix, const uint32_t *__restrict__ perm)
+pmb_k_paint_perm(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfix, const uint32_t *__restrict__ perm,
+                 unsigned long long *ticket)
 {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (; j < npart; j += stride) {
-        const int64_t i = perm[j];
+    auto body = [&](int64_t j) {
+        const int64_t i = perm ? (int64_t) perm[j] : j;     // NULL: the array is already in tile order (pmb_bin.cuh)
         double x[3];
         pmb_load_pos<3>(p, i, x);
         const double m = pmb_load_mass(p, i);
@@ -243,7 +258,22 @@ pmb_k_paint_perm(PmbGeom g, PmbParticles p, char *mesh, int64_t npart, int pcsfi
         pmb_for_points_fixed<3, FAM, CHECK>(A, [&](int, int64_t off, double v0, double v1, double v2) {
             if (!CHECK || off != PMB_OFF_INVALID) pmb_red<MeshT>(mesh, off, pmb_paint_value(true, m, v0, v1, v2), policy);
         });
+    };
+    if (ticket) {
+        __shared__ unsigned long long s_tk;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tk = atomicAdd(ticket, 1ull);
+            __syncthreads();
+            const int64_t j = (int64_t) s_tk * 256 + threadIdx.x;
+            if ((int64_t) s_tk * 256 >= npart) break;
+            if (j < npart) body(j);
+        }
+        return;
     }
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < npart; j += stride) body(j);
 }
 
 template <typename MeshT, int FAM, bool CHECK>
@@ -256,7 +286,7 @@ pmb_k_readout_perm(PmbGeom g, PmbParticles p, const char *mesh, int64_t npart, i
     int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (; j < npart; j += stride) {
-        const int64_t i = perm[j];
+        const int64_t i = perm ? (int64_t) perm[j] : j;     // NULL: the array is already in tile order (pmb_bin.cuh)
         double x[3];
         pmb_load_pos<3>(p, i, x);
         PmbAxes<3, FAM> A;

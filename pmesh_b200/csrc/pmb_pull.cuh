@@ -1,0 +1,294 @@
+// pmb_pull.cuh -- the deterministic paint at size: particles sorted by the cell of their FIRST stencil point,
+// every mesh cell then sums its own contributions, in ascending particle number.
+//
+// The reference paints with one sequential loop over the particles (_window_imp.c, _window_tuned_*.h): cell c
+// receives `*(FLOAT *) p += f` once per (particle, stencil point) that lands on it, in particle order, a
+// particle's own points in C order.  Round 1 reproduced that by expanding every particle into support^3
+// (cell, value) pairs and radix-sorting the PAIRS (8 / 27 / 64 x the data; CIC 2.6 G particles/s).  Here only the
+// particles are sorted:
+//
+//   keys     key = linear number of the cell of the particle's first stencil point (per axis: wrapped into the
+//            period when the canvas covers the whole period, else relative to the canvas with room for points
+//            that enter it from below), value = particle number                       1 pass over the positions
+//   sort     stable LSD radix sort of the (key, number) pairs on the bits of the key space (cub, library):
+//            inside a cell the particle numbers ascend
+//   runs     (first, last + 1) of every non-empty cell, from the boundaries of the sorted keys
+//   records  (x, y, z, number) of the sorted particles as 32-byte records (+ the sorted mass column)
+//   pull     one thread per mesh cell: the support^3 cells whose particles can reach it are the neighbours at
+//            offsets (ka, kb, kc) < support below it; their runs are merged by particle number (ties -- the same
+//            particle reaching the cell twice through a period shorter than its stencil cannot happen here, such
+//            canvases take the pairs path -- would break towards the lower offset, the reference's point order)
+//            and summed as acc = (T) ((double) acc + f), f = ((V0 * m) * V1) * V2 evaluated like every other
+//            tuned kernel.  No atomics, every mesh cell is read and written once, coalesced.
+//
+// Bit-identical to the reference and to the pairs path for every tuned window (nnb, cic, tsc, pcs, and their
+// gradient windows) on 3-D canvases; everything else (run-time supports, per-particle hsml, 1-D / 2-D, periods
+// shorter than the stencil, key spaces >= 2^31) keeps the pairs path.
+#pragma once
+#include <cub/cub.cuh>
+
+#include "pmb_sched.cuh"
+
+struct PmbPullGeom {
+    int full[3];           // 1: the canvas covers the whole period of the axis (keys wrap), 0: keys relative to the canvas
+    int E[3];              // key extent per axis: period (full) or size + S - 1
+};
+
+// first stencil index of a coordinate -> key coordinate in [0, E), or -1 when no stencil point can land on the canvas
+template <int FAM>
+__device__ __forceinline__ int pmb_pull_base(int I0, int full, int per, int sz)
+{
+    if (full) return pmb_wrap32(I0, per);
+    int cb = I0;
+    if (per > 0) {
+        cb = pmb_wrap32(I0, per);
+        if (cb > per - FAM) cb -= per;         // the stencil runs across the period: it enters the canvas from below
+    }
+    if (cb <= -FAM || cb >= sz) return -1;
+    return cb + FAM - 1;
+}
+
+template <typename KeyT, int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_pull_keys(PmbGeom g, PmbPullGeom pg, PmbParticles p, int64_t npart, int pcsfix, KeyT *keys, uint32_t *ids)
+{
+    int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < npart; i += stride) {
+        double x[3];
+        pmb_load_pos<3>(p, i, x);
+        int64_t key = 0;
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double X = pmb_gridpos(x[d], g.scale[d], g.translate[d]);
+            int I[FAM];
+            double V[FAM];
+            pmb_axis_tuned<FAM>(X, g.order[d], g.scale[d], pcsfix, I, V);
+            const int b = pmb_pull_base<FAM>(I[0], pg.full[d], (int) g.period[d], (int) g.size[d]);
+            ok = ok && b >= 0;
+            key = key * pg.E[d] + b;
+        }
+        keys[i] = ok ? (KeyT) key : (KeyT) ~(KeyT) 0;
+        ids[i] = (uint32_t) i;
+    }
+}
+
+// runs of equal keys: se[key] = (first, last + 1); cells without particles keep (0, 0) from the memset
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+pmb_k_pull_runs(const KeyT *__restrict__ keys, int64_t n, int64_t nkeys, uint2 *se)
+{
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        const KeyT k = keys[j];
+        if ((int64_t) k >= nkeys) continue;           // particles that reach no cell of the canvas sort last
+        if (j == 0 || keys[j - 1] != k) se[k].x = (uint32_t) j;
+        if (j + 1 == n || keys[j + 1] != k) se[k].y = (uint32_t) (j + 1);
+    }
+}
+
+// sorted records: (x, y, z, particle number) as one 32-byte store, and the mass column in the same order
+__global__ void __launch_bounds__(256)
+pmb_k_pull_records(PmbParticles p, const uint32_t *__restrict__ ids, int64_t n, double *__restrict__ recs, double *__restrict__ smass)
+{
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        const int64_t i = ids[j];
+        double x[3];
+        pmb_load_pos<3>(p, i, x);
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(recs + 4 * j), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                     "d"(__longlong_as_double((long long) i)) : "memory");
+        if (smass) smass[j] = pmb_load_mass(p, i);
+    }
+}
+
+template <int FAM>
+__device__ __forceinline__ double pmb_pull_pick(const double *V, int k)
+{
+    double v = V[0];
+#pragma unroll
+    for (int s = 1; s < FAM; s++) if (k == s) v = V[s];
+    return v;
+}
+
+// contribution of sorted particle j to the cell at stencil offsets (ka, kb, kc) above its first point
+template <int FAM>
+__device__ __forceinline__ double pmb_pull_value(const PmbGeom &g, int pcsfix, const double *__restrict__ recs,
+                                                 const double *__restrict__ smass, double mass_scalar, uint32_t j,
+                                                 int ka, int kb, int kc)
+{
+    double x0, x1, x2, idb;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(idb) : "l"(recs + 4 * (int64_t) j));
+    (void) idb;
+    const double m = smass ? smass[j] : mass_scalar;
+    int I[FAM];
+    double V0[FAM], V1[FAM], V2[FAM];
+    pmb_axis_tuned<FAM>(pmb_gridpos(x0, g.scale[0], g.translate[0]), g.order[0], g.scale[0], pcsfix, I, V0);
+    pmb_axis_tuned<FAM>(pmb_gridpos(x1, g.scale[1], g.translate[1]), g.order[1], g.scale[1], pcsfix, I, V1);
+    pmb_axis_tuned<FAM>(pmb_gridpos(x2, g.scale[2], g.translate[2]), g.order[2], g.scale[2], pcsfix, I, V2);
+    return pmb_paint_value(true, m, pmb_pull_pick<FAM>(V0, ka), pmb_pull_pick<FAM>(V1, kb), pmb_pull_pick<FAM>(V2, kc));
+}
+
+__device__ __forceinline__ uint32_t pmb_pull_id(const double *__restrict__ recs, uint32_t j)
+{
+    return (uint32_t) __double_as_longlong(__ldg(recs + 4 * (int64_t) j + 3));
+}
+
+template <typename MeshT, int FAM>
+__global__ void __launch_bounds__(128)
+pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, const double *__restrict__ recs,
+           const double *__restrict__ smass, double mass_scalar, char *mesh)
+{
+    constexpr int NR = FAM * FAM * FAM;
+    const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t lin = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; lin < ncell; lin += stride) {
+        const int c2 = (int) (lin % g.size[2]);
+        const int64_t r01 = lin / g.size[2];
+        const int c1 = (int) (r01 % g.size[1]);
+        const int c0 = (int) (r01 / g.size[1]);
+        // the runs that can reach this cell, in C order of the stencil offsets
+        uint32_t cur[NR], end[NR];
+        int nonempty = 0;
+#pragma unroll
+        for (int ka = 0; ka < FAM; ka++) {
+            int b0 = pg.full[0] ? c0 - ka : c0 - ka + FAM - 1;
+            if (pg.full[0] && b0 < 0) b0 += pg.E[0];
+#pragma unroll
+            for (int kb = 0; kb < FAM; kb++) {
+                int b1 = pg.full[1] ? c1 - kb : c1 - kb + FAM - 1;
+                if (pg.full[1] && b1 < 0) b1 += pg.E[1];
+#pragma unroll
+                for (int kc = 0; kc < FAM; kc++) {
+                    int b2 = pg.full[2] ? c2 - kc : c2 - kc + FAM - 1;
+                    if (pg.full[2] && b2 < 0) b2 += pg.E[2];
+                    const uint2 r = __ldg(se + (((int64_t) b0 * pg.E[1] + b1) * pg.E[2] + b2));
+                    const int q = (ka * FAM + kb) * FAM + kc;
+                    cur[q] = r.x; end[q] = r.y;
+                    nonempty += r.y > r.x;
+                }
+            }
+        }
+        if (!nonempty) continue;
+        MeshT *cell = (MeshT *) (mesh + c0 * g.strides[0] + c1 * g.strides[1] + c2 * g.strides[2]);
+        MeshT acc = *cell;
+        // merge by particle number; on equal numbers the lower offset goes first.  CIC keeps the 8 run heads in
+        // registers (unrolled, predicated updates); wider stencils index them in local memory.
+        uint32_t head[NR];
+#pragma unroll
+        for (int q = 0; q < NR; q++) head[q] = cur[q] < end[q] ? pmb_pull_id(recs, cur[q]) : 0xFFFFFFFFu;
+        for (;;) {
+            int best = -1;
+            uint32_t bid = 0xFFFFFFFFu;
+#pragma unroll (FAM <= 2 ? NR : 1)
+            for (int q = 0; q < NR; q++) {
+                const bool take = cur[q] < end[q] && (best < 0 || head[q] < bid);
+                if (take) { best = q; bid = head[q]; }
+            }
+            if (best < 0) break;
+            uint32_t j = 0;
+            if (FAM <= 2) {
+#pragma unroll
+                for (int q = 0; q < NR; q++) if (q == best) j = cur[q];
+            } else {
+                j = cur[best];
+            }
+            acc = (MeshT) ((double) acc + pmb_pull_value<FAM>(g, pcsfix, recs, smass, mass_scalar, j, best / (FAM * FAM), (best / FAM) % FAM, best % FAM));
+            if (FAM <= 2) {
+#pragma unroll
+                for (int q = 0; q < NR; q++)
+                    if (q == best) {
+                        cur[q] = j + 1;
+                        head[q] = j + 1 < end[q] ? pmb_pull_id(recs, j + 1) : 0xFFFFFFFFu;
+                    }
+            } else {
+                cur[best] = j + 1;
+                head[best] = j + 1 < end[best] ? pmb_pull_id(recs, j + 1) : 0xFFFFFFFFu;
+            }
+        }
+        *cell = acc;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+// *done = false: this canvas / input takes the pairs path
+template <typename MeshT, int FAM>
+static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbParticles &p, bool *done)
+{
+    *done = false;
+    PmbPullGeom pg;
+    int64_t nkeys = 1;
+    for (int d = 0; d < 3; d++) {
+        const int64_t per = g.period[d], sz = g.size[d];
+        if (per > 0 && sz == per) {
+            if (per < FAM) return PMB_OK;                 // a stencil longer than the period lands on a cell twice
+            pg.full[d] = 1; pg.E[d] = (int) per;
+        } else {
+            if (per > 0 && sz + FAM - 1 > per) return PMB_OK;
+            pg.full[d] = 0; pg.E[d] = (int) (sz + FAM - 1);
+        }
+        nkeys *= pg.E[d];
+        if (nkeys >= ((int64_t) 1 << 31) - 1) return PMB_OK;
+    }
+    const int64_t n = a->npart;
+    if (n >= ((int64_t) 1 << 31)) return PMB_OK;
+    int bits = 1;
+    while (((int64_t) 1 << bits) <= nkeys) bits++;        // the all-ones key of dropped particles stays above every real key
+    typedef uint32_t KeyT;
+    size_t temp = 0;
+    PMB_CUDA(cub::DeviceRadixSort::SortPairs(NULL, temp, (KeyT *) NULL, (KeyT *) NULL, (uint32_t *) NULL, (uint32_t *) NULL,
+                                             (int) n, 0, bits, ctx->stream));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+    const size_t b_keys = up(sizeof(KeyT) * n), b_ids = up(sizeof(uint32_t) * n), b_se = up(sizeof(uint2) * (size_t) nkeys);
+    const size_t b_recs = up(32 * (size_t) n), b_mass = a->mass ? up(sizeof(double) * n) : 0, b_temp = up(temp);
+    // keys in | keys out | ids in | ids out | cub temp | runs | records | mass   (records overlay nothing: simple and safe)
+    const size_t total = 2 * b_keys + 2 * b_ids + b_temp + b_se + b_recs + b_mass + 256;
+    void *ws = NULL;
+    if (pmb_scratch(ctx, total, &ws) != PMB_OK) { cudaGetLastError(); return PMB_OK; }
+    char *b = (char *) ws;
+    KeyT *k0 = (KeyT *) b, *k1 = (KeyT *) (b + b_keys);
+    uint32_t *i0 = (uint32_t *) (b + 2 * b_keys), *i1 = (uint32_t *) (b + 2 * b_keys + b_ids);
+    void *tmp = b + 2 * b_keys + 2 * b_ids;
+    uint2 *se = (uint2 *) (b + 2 * b_keys + 2 * b_ids + b_temp);
+    double *recs = (double *) ((char *) se + b_se);
+    double *smass = a->mass ? (double *) ((char *) recs + b_recs) : NULL;
+    pmb_k_pull_keys<KeyT, FAM><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(g, pg, p, n, a->pcs_gradient_scale_fix, k0, i0);
+    PMB_LAUNCH_CHECK(ctx);
+    PMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, k0, k1, i0, i1, (int) n, 0, bits, ctx->stream));
+    ctx->launches += 4;
+    PMB_CUDA(cudaMemsetAsync(se, 0, sizeof(uint2) * (size_t) nkeys, ctx->stream));
+    pmb_k_pull_runs<KeyT><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(k1, n, nkeys, se);
+    PMB_LAUNCH_CHECK(ctx);
+    pmb_k_pull_records<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(p, i1, n, recs, smass);
+    PMB_LAUNCH_CHECK(ctx);
+    const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
+    pmb_k_pull<MeshT, FAM><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
+                                                                                     a->mass_scalar, (char *) a->mesh);
+    PMB_LAUNCH_CHECK(ctx);
+    if (total > ((size_t) 4 << 30)) {
+        // a large workspace goes back to the device instead of staying in the context's scratch
+        PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PMB_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = NULL;
+        ctx->scratch_bytes = 0;
+    }
+    *done = true;
+    return PMB_OK;
+}
+
+template <typename MeshT>
+static int pmb_pull_paint(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbParticles &p, int fam, bool *done)
+{
+    *done = false;
+    if (a->ndim != 3 || fam < 1 || fam > 4 || !pmb_env_flag("PMB_PULL", 1)) return PMB_OK;
+    if (a->npart < pmb_env_flag("PMB_PULL_MIN", 1 << 15)) return PMB_OK;
+    switch (fam) {
+    case 1: return pmb_pull_paint_fam<MeshT, 1>(ctx, a, g, p, done);
+    case 2: return pmb_pull_paint_fam<MeshT, 2>(ctx, a, g, p, done);
+    case 3: return pmb_pull_paint_fam<MeshT, 3>(ctx, a, g, p, done);
+    default: return pmb_pull_paint_fam<MeshT, 4>(ctx, a, g, p, done);
+    }
+}

@@ -13,7 +13,8 @@
 
 #include "pmb_sched.cuh"
 #include "pmb_ring.cuh"
-#include "pmb_perm.cuh"
+#include "pmb_bin.cuh"
+#include "pmb_pull.cuh"
 
 // ------------------------------------------------------------------ atomic paint
 // L2 residency control: mesh cells are re-touched by particles of neighbouring lattice rows /
@@ -478,6 +479,38 @@ static bool geom32(const pmb_resample_args *a, const PmbGeom &g, PmbGeom32 *g32)
     return span < ((int64_t) 1 << 31) - 1;
 }
 
+// How a large 3-D particle array is traversed.  bn->pos: a tile-sorted copy of the records serves it
+// (pmb_bin.cuh); *walk: the kernels that walk the array through *perm do (pmb_perm.cuh; *perm NULL: the array
+// IS the sorted copy and the plain kernels serve it); neither: the chunk-scheduled kernels.
+// On the sorted copy (measured at 1024^3 uniform random, B200): the scatter takes the plain kernel with chunk
+// tickets (PMB_BIN_PAINT=2: 46 ms with the algorithmic DRAM traffic; the carry kernels' static chunk stride puts
+// every CTA into a tile of its own: 98 ms, 190 GB of DRAM traffic; 1: grid-stride loop, 0: carry kernels), the
+// gather takes the bulk-copy ring (PMB_BIN_READOUT=0: 21 ms; 1: plain walk 24 ms).
+static int pmb_traversal(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart, PmbBinned *bn,
+                         const uint32_t **perm, bool *walk, bool is_paint)
+{
+    bn->pos = NULL; bn->dest = NULL; bn->verdict = 2;
+    *perm = NULL;
+    *walk = false;
+    if (ctx->bin_bypass) {
+        *walk = is_paint ? pmb_env_flag("PMB_BIN_PAINT", 2) != 0 : pmb_env_flag("PMB_BIN_READOUT", 0) != 0;
+        return PMB_OK;
+    }
+    PMB_CHECK(pmb_bin_prepare(ctx, g, p, npart, bn));
+    if (bn->verdict == 2) {
+        PMB_CHECK(pmb_perm_prepare(ctx, g, p, npart, perm));
+        *walk = *perm != NULL;
+    }
+    return PMB_OK;
+}
+
+// the arguments of a call on the sorted copy
+static void pmb_binned_args(const pmb_resample_args *a, const PmbBinned &bn, pmb_resample_args *b)
+{
+    *b = *a;
+    b->pos = bn.pos; b->pos_elsize = 8; b->pos_stride0 = 32; b->pos_stride1 = 8;      // (x, y, z, particle number) records
+}
+
 template <typename MeshT>
 static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom &g, const PmbWindow &w,
                         const PmbParticles &p)
@@ -490,17 +523,37 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         int64_t nchunks;
         const bool chk = pmb_geom_needs_check(g);
         const int unit = pmb_env_flag("PMB_CARRY_UNIT", 128);
-        // particle arrays without spatial order: walk them through a tile-binned permutation (pmb_perm.cuh)
+        // particle arrays without spatial order: a tile-sorted copy of the records (pmb_bin.cuh), else a walk
+        // through a tile-binned permutation (pmb_perm.cuh)
         const uint32_t *perm;
-        PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
-        if (perm) {
+        PmbBinned bn;
+        bool walk;
+        PMB_CHECK(pmb_traversal(ctx, g, p, a->npart, &bn, &perm, &walk, true));
+        if (bn.pos) {
+            pmb_resample_args b;
+            pmb_binned_args(a, bn, &b);
+            if (a->mass) {
+                const double *smass;
+                PMB_CHECK(pmb_bin_column(ctx, bn, a->mass, a->mass_elsize, a->mass_stride, a->npart, &smass));
+                b.mass = smass; b.mass_elsize = 8; b.mass_stride = 8;
+            }
+            PmbParticles p2;
+            fill_particles(&b, &p2);
+            ctx->bin_bypass = 1;
+            const int r = paint_atomic<MeshT>(ctx, &b, g, w, p2);
+            ctx->bin_bypass = 0;
+            return r;
+        }
+        if (walk) {
             const int gridp = pmb_grid(ctx, a->npart, 256, 8);
             PmbGeom32 g32;
+            unsigned long long *ticket = NULL;
+            if (!perm && pmb_env_flag("PMB_BIN_PAINT", 2) >= 2) PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
             if (fam == 2 && !(a->order[0] | a->order[1] | a->order[2]) && geom32<MeshT>(a, g, &g32)) {
-                PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic32_perm<MeshT, CHECK><<<gridp, 256, 0, ctx->stream>>>(g32, p, (MeshT *) mesh, a->npart, perm)));
+                PMB_DISPATCH_CHECK(chk, (pmb_k_paint_cic32_perm<MeshT, CHECK><<<gridp, 256, 0, ctx->stream>>>(g32, p, (MeshT *) mesh, a->npart, perm, ticket)));
             } else {
                 PMB_DISPATCH_CHECK(chk, PMB_DISPATCH_FAM(fam, 3,
-                    (pmb_k_paint_perm<MeshT, FAM, CHECK><<<gridp, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix, perm))));
+                    (pmb_k_paint_perm<MeshT, FAM, CHECK><<<gridp, 256, 0, ctx->stream>>>(g, p, mesh, a->npart, a->pcs_gradient_scale_fix, perm, ticket))));
             }
             PMB_LAUNCH_CHECK(ctx);
             return PMB_OK;
@@ -648,6 +701,12 @@ static int paint_deterministic(pmb_ctx *ctx, const pmb_resample_args *a, const P
     int64_t ncell = acc;
     if (ncell == 0) return PMB_OK;
     const int fam = fixed_family(w, a);
+    {
+        // tuned windows on 3-D canvases: sort the PARTICLES by cell, every cell sums its own contributions (pmb_pull.cuh)
+        bool done = false;
+        PMB_CHECK((pmb_pull_paint<MeshT>(ctx, a, g_in, p, fam, &done)));
+        if (done) return PMB_OK;
+    }
 
     // widest per-particle stencil
     int64_t smax;
@@ -776,10 +835,20 @@ static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &
     PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
     // resident CTAs per SM, measured at 1024^3 (ms): one field 4 -> 8.99, 5 -> 9.34, 6 -> 9.57 (11.13 without
     // the ring); three fields 2 -> 21.0, 3 -> 20.0, 4 -> 28.6 (spills) (33.4 as three separate gathers)
-    const int minb = pmb_env_flag(nf == 1 ? "PMB_RING_READOUT_MINB" : "PMB_RING_READOUT3_MINB", nf == 1 ? 4 : 3);
+    const int minb = pmb_pos_is_f8_rec4(p) ? (nf == 1 ? 4 : 3)
+                                           : pmb_env_flag(nf == 1 ? "PMB_RING_READOUT_MINB" : "PMB_RING_READOUT3_MINB", nf == 1 ? 4 : 3);
     const int64_t cap = (int64_t) ctx->sm_count * minb;
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     const double *pos = (const double *) p.pos;
+    if (pmb_pos_is_f8_rec4(p)) {
+        // 32-byte records of the tile-sorted copy
+#define PMB_RING_READ4(NFV, MB) PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_ring<MeshT, CHECK, NFV, MB, 4><<<grid, PMB_RING_THREADS, 0, ctx->stream>>>( \
+            g32, pos, f, npart, nchunks, ticket)))
+        if (nf == 1) { PMB_RING_READ4(1, 4); } else if (nf == 2) { PMB_RING_READ4(2, 3); } else { PMB_RING_READ4(3, 3); }
+#undef PMB_RING_READ4
+        PMB_LAUNCH_CHECK(ctx);
+        return PMB_OK;
+    }
 #define PMB_RING_READ(NFV, MB) PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_ring<MeshT, CHECK, NFV, MB><<<grid, PMB_RING_THREADS, 0, ctx->stream>>>( \
         g32, pos, f, npart, nchunks, ticket)))
     if (nf == 1) {
@@ -809,10 +878,33 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
         const uint32_t *order = NULL;
         int64_t nchunks = (a->npart + PMB_CHUNK - 1) / PMB_CHUNK;
         {
-            // particle arrays without spatial order: tile-binned permutation (pmb_perm.cuh)
+            // particle arrays without spatial order: tile-sorted copy (pmb_bin.cuh), else permutation walk (pmb_perm.cuh)
             const uint32_t *perm;
-            PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
-            if (perm) {
+            PmbBinned bn;
+            bool walk;
+            PMB_CHECK(pmb_traversal(ctx, g, p, a->npart, &bn, &perm, &walk, false));
+            double *stage = bn.pos ? (double *) pmb_bin_try_scratch(ctx, sizeof(double) * (size_t) a->npart) : NULL;
+            if (bn.pos && !stage) {       // no room for the staging column: the permutation walk serves the array
+                PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
+                walk = perm != NULL;
+            }
+            if (stage) {
+                // gather on the sorted copy into the staging column, then back to the caller's order
+                pmb_resample_args b;
+                pmb_binned_args(a, bn, &b);
+                b.out = stage; b.out_elsize = 8; b.out_stride = 8;
+                PmbParticles p2;
+                fill_particles(&b, &p2);
+                ctx->bin_bypass = 1;
+                const int r = readout_impl<MeshT>(ctx, &b, g, w, p2);
+                ctx->bin_bypass = 0;
+                PMB_CHECK(r);
+                PmbFields f;
+                memset(&f, 0, sizeof(f));
+                f.out[0] = a->out; f.out_stride[0] = a->out_stride; f.out_elsize = a->out_elsize;
+                return pmb_bin_unsort(ctx, bn, f, 1, stage, a->npart);
+            }
+            if (walk) {
                 const int gridp = pmb_grid(ctx, a->npart, 256, 8);
                 const bool chkp = pmb_geom_needs_check(g);
                 PmbGeom32 g32;
@@ -851,7 +943,7 @@ static int readout_impl(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
                     g32.period[d] = (int) g.period[d]; g32.size[d] = (int) g.size[d];
                     g32.estride[d] = (int) (a->strides[d] / (int64_t) sizeof(MeshT));
                 }
-                if (pmb_env_flag("PMB_RING", 1) && pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) {
+                if (pmb_env_flag("PMB_RING", 1) && ((pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) || pmb_pos_is_f8_rec4(p))) {
                     PmbFields f;
                     memset(&f, 0, sizeof(f));
                     f.mesh[0] = mesh; f.out[0] = a->out; f.out_stride[0] = a->out_stride; f.out_elsize = a->out_elsize;
@@ -959,8 +1051,31 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
         f.sel1 = gf->own_begin + gf->own_count;
     }
     const uint32_t *perm;
-    PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
-    if (perm) {
+    PmbBinned bn;
+    bool walk;
+    PMB_CHECK(pmb_traversal(ctx, g, p, a->npart, &bn, &perm, &walk, false));
+    double *stage = bn.pos ? (double *) pmb_bin_try_scratch(ctx, sizeof(double) * (size_t) nf * (size_t) a->npart) : NULL;
+    if (bn.pos && !stage) {
+        PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
+        walk = perm != NULL;
+    }
+    if (stage) {
+        // the nf gathers on the sorted copy into (npart, nf) staging rows, then back to the caller's order -- through
+        // pmb_store_result, so that the fused ghost sum sees the caller's particle numbers
+        pmb_resample_args b;
+        pmb_binned_args(a, bn, &b);
+        b.out_elsize = 8;
+        void *outs2[3];
+        int64_t strides2[3];
+        for (int q = 0; q < nf; q++) { outs2[q] = stage + q; strides2[q] = (int64_t) sizeof(double) * nf; }
+        ctx->bin_bypass = 1;
+        const int r = readout_multi_impl<MeshT>(ctx, &b, nf, meshes, outs2, strides2, done, NULL);
+        ctx->bin_bypass = 0;
+        PMB_CHECK(r);
+        if (!*done) return PMB_OK;
+        return pmb_bin_unsort(ctx, bn, f, nf, stage, a->npart);
+    }
+    if (walk) {
         const int gridp = pmb_grid(ctx, a->npart, 256, 8);
         const bool chk = pmb_geom_needs_check(g);
         if (nf == 1) { PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_perm<MeshT, CHECK, 1><<<gridp, 256, 0, ctx->stream>>>(g32, p, f, a->npart, perm))); }
@@ -970,7 +1085,7 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
         *done = true;
         return PMB_OK;
     }
-    if (!pmb_env_flag("PMB_RING", 1) || !pmb_pos_is_f8_rows(p) || ((uintptr_t) p.pos & 15)) return PMB_OK;
+    if (!pmb_env_flag("PMB_RING", 1) || !((pmb_pos_is_f8_rows(p) && ((uintptr_t) p.pos & 15) == 0) || pmb_pos_is_f8_rec4(p))) return PMB_OK;
     *done = true;
     return readout_ring<MeshT>(ctx, g32, p, f, nf, a->npart, pmb_geom_needs_check(g));
 }
@@ -1090,5 +1205,21 @@ extern "C" int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *
                 g, p, mesh, a->npart, a->pcs_gradient_scale_fix, a->out, a->out_elsize, a->out_stride, out_grad, gs0, gs1)))));
     }
     PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+extern "C" int pmb_bin_stats(pmb_ctx *ctx, int64_t *builds, int64_t *bytes_held)
+{
+    PMB_REQUIRE(ctx, "null context");
+    if (builds) *builds = ctx->bin_builds;
+    if (bytes_held) *bytes_held = (int64_t) (ctx->bin_pos_bytes + ctx->bin_dest_bytes + ctx->bin_col_bytes);
+    return PMB_OK;
+}
+
+extern "C" int pmb_bin_release(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    pmb_bin_free(ctx);
     return PMB_OK;
 }

@@ -19,8 +19,11 @@
 #define PMB_RING 4
 #define PMB_RING_THREADS (PMB_CHUNK + 32)
 
+// RW: float64 words per particle record -- 3: (N, 3) position rows; 4: the 32-byte records of the tile-sorted
+// copy (pmb_bin.cuh: x, y, z, particle number)
+template <int RW>
 struct PmbRingSmem {
-    double pos[PMB_RING][PMB_CHUNK * 3];     // 4 x 6 KB
+    double pos[PMB_RING][PMB_CHUNK * RW];    // 4 x 6 KB (RW = 3)
     uint64_t full[PMB_RING], empty[PMB_RING];
     long long chunk[PMB_RING];               // chunk id of the stage, -1: end of work
     int first[PMB_RING];                     // paint: the chunk starts a new run (carry must be flushed)
@@ -28,16 +31,17 @@ struct PmbRingSmem {
 
 // producer side: copy chunk `c` (particles [c * CHUNK, ...)) into stage s.  A chunk whose byte count is
 // not a multiple of 16 (odd particle count at the very end) gets its last 8 bytes by a plain store.
-__device__ __forceinline__ void pmb_ring_fill(PmbRingSmem &sm, int s, const double *pos, int64_t c, int64_t npart, uint64_t policy)
+template <int RW>
+__device__ __forceinline__ void pmb_ring_fill(PmbRingSmem<RW> &sm, int s, const double *pos, int64_t c, int64_t npart, uint64_t policy)
 {
     const int64_t first = c * PMB_CHUNK;
     const int cnt = (int) min((int64_t) PMB_CHUNK, npart - first);
-    const uint32_t bytes = (uint32_t) cnt * 24u;
+    const uint32_t bytes = (uint32_t) cnt * (8u * RW);
     const uint32_t b16 = bytes & ~15u;
-    if (bytes != b16) sm.pos[s][cnt * 3 - 1] = __ldcs(pos + 3 * first + cnt * 3 - 1);
+    if (bytes != b16) sm.pos[s][cnt * RW - 1] = __ldcs(pos + RW * first + cnt * RW - 1);
     if (b16) {
         pmb_mbar_arrive_expect_tx(&sm.full[s], b16);
-        pmb_bulk_g2s(sm.pos[s], pos + 3 * first, b16, &sm.full[s], policy);
+        pmb_bulk_g2s(sm.pos[s], pos + RW * first, b16, &sm.full[s], policy);
     } else {
         pmb_mbar_arrive(&sm.full[s]);
     }
@@ -74,12 +78,12 @@ __device__ __forceinline__ void pmb_store_result(const PmbFields &f, int q, int6
 // ---- readout of NF fields in one sweep ---------------------------------------------------------------
 // indices and weights are computed once per particle and used for NF gathers (the three force components
 // of the PM step share one pass over the positions: 24 + NF * 16 bytes per particle instead of NF * 40)
-template <typename MeshT, bool CHECK, int NF, int MINB>
+template <typename MeshT, bool CHECK, int NF, int MINB, int RW = 3>
 __global__ void __launch_bounds__(PMB_RING_THREADS, MINB)
 pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields f, int64_t npart,
                          int64_t nchunks, unsigned long long *ticket)
 {
-    __shared__ __align__(128) PmbRingSmem sm;
+    __shared__ __align__(128) PmbRingSmem<RW> sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < PMB_RING; s++) { pmb_mbar_init(&sm.full[s], 1); pmb_mbar_init(&sm.empty[s], PMB_CHUNK / 32); }
@@ -116,9 +120,9 @@ pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields 
         const bool active = i < npart;
         double x0 = 0, x1 = 0, x2 = 0;
         if (active) {
-            x0 = sm.pos[s][3 * threadIdx.x];
-            x1 = sm.pos[s][3 * threadIdx.x + 1];
-            x2 = sm.pos[s][3 * threadIdx.x + 2];
+            x0 = sm.pos[s][RW * threadIdx.x];
+            x1 = sm.pos[s][RW * threadIdx.x + 1];
+            x2 = sm.pos[s][RW * threadIdx.x + 2];
         }
         __syncwarp();
         if (lane == 0) pmb_mbar_arrive(&sm.empty[s]);
@@ -168,12 +172,12 @@ pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields 
 }
 
 // ---- paint: y-carry + z aggregation (pmb_k_paint_cic_carry32) fed by the ring -------------------------
-template <typename MeshT, bool CHECK, int MINB>
+template <typename MeshT, bool CHECK, int MINB, int RW = 3>
 __global__ void __launch_bounds__(PMB_RING_THREADS, MINB)
 pmb_k_paint_cic_carry32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbParticles p, MeshT *mesh, int64_t npart,
                              const uint32_t *__restrict__ order, int64_t nchunks, int unit)
 {
-    __shared__ __align__(128) PmbRingSmem sm;
+    __shared__ __align__(128) PmbRingSmem<RW> sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < PMB_RING; s++) { pmb_mbar_init(&sm.full[s], 1); pmb_mbar_init(&sm.empty[s], PMB_CHUNK / 32); }
@@ -216,9 +220,9 @@ pmb_k_paint_cic_carry32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbPar
         const int64_t i = c * PMB_CHUNK + threadIdx.x;
         const bool active = c >= 0 && i < npart;
         if (active) {
-            x0 = sm.pos[s][3 * threadIdx.x];
-            x1 = sm.pos[s][3 * threadIdx.x + 1];
-            x2 = sm.pos[s][3 * threadIdx.x + 2];
+            x0 = sm.pos[s][RW * threadIdx.x];
+            x1 = sm.pos[s][RW * threadIdx.x + 1];
+            x2 = sm.pos[s][RW * threadIdx.x + 2];
         }
         __syncwarp();
         if (lane == 0 && c >= 0) pmb_mbar_arrive(&sm.empty[s]);

@@ -385,6 +385,11 @@ static inline bool pmb_pos_is_f8_rows(const PmbParticles &p)
 {
     return p.pos_elsize == 8 && p.ps1 == 8 && p.ps0 == 24 && ((uintptr_t) p.pos & 7) == 0;
 }
+// the 32-byte records (x, y, z, particle number) of the tile-sorted copy (pmb_bin.cuh)
+static inline bool pmb_pos_is_f8_rec4(const PmbParticles &p)
+{
+    return p.pos_elsize == 8 && p.ps1 == 8 && p.ps0 == 32 && ((uintptr_t) p.pos & 31) == 0;
+}
 
 template <bool CHECK>
 __device__ __forceinline__ void pmb_cic_axis32(double xin, double scale, double translate, int per, int sz, int es,
