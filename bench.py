@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-double", action="store_true", help="e2e: upload || compute || download with two position buffers")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=256,
                     help="side of the sample problem of the cpu_baseline leg of the default arm (a few seconds on all cores)")
@@ -248,12 +249,30 @@ def time_paint_readout(pm, args, comm, X, peak, R=5):
     nl = lpos.shape[0]
     ncell_local = int(numpy.prod(pm._layout['i_shape']))
     rho = pm.create("real")
+    import ctypes
+    from pmesh_b200 import _lib
+
+    def reorders():
+        b = ctypes.c_int64(0)
+        _lib.check(ctx.lib.pmb_bin_stats(ctx.handle, ctypes.byref(b), None))
+        return b.value
+    b0 = reorders()
     for _ in range(2):
         pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
     ctx.timer_start(2)
     for _ in range(R):
         pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
     t_paint = ctx.timer_stop(2) / R
+    # particle arrays without spatial order are painted / read through a tile-sorted copy kept by the library
+    # (pmb_bin.cuh): the calls above reuse it (content hash + kernel); a force evaluation pays the reorder ONCE,
+    # in its paint.  t_first = a paint that has to build the copy.
+    reordered = reorders() > b0
+    t_first = t_paint
+    if reordered:
+        _lib.check(ctx.lib.pmb_bin_release(ctx.handle))
+        ctx.timer_start(2)
+        pm.resampler.paint(rho._device(), lpos, transform=pm.affine, mode=args.paint_mode)
+        t_first = ctx.timer_stop(2)
     out = DeviceArray.empty((nl,), "f8")
     for _ in range(2):
         pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
@@ -261,16 +280,24 @@ def time_paint_readout(pm, args, comm, X, peak, R=5):
     for _ in range(R):
         pm.resampler.readout(rho._device(), lpos, out=out, transform=pm.affine)
     t_read = ctx.timer_stop(2) / R
+    if reordered:
+        _lib.check(ctx.lib.pmb_bin_release(ctx.handle))     # the copy's memory goes back before the next input
     ab_paint = nl * 24.0 + ncell_local * es          # pos (3 x f8) read + one mesh write pass
     ab_read = nl * (24.0 + 8.0) + ncell_local * es   # pos read + f8 result write + one mesh read pass
     nsum = comm.allreduce(nl, op=C.SUM)
     tp, tr = comm.allreduce(t_paint, op=C.MAX), comm.allreduce(t_read, op=C.MAX)
+    tf = comm.allreduce(t_first, op=C.MAX)
     row = {"paint_ms": round(tp, 4), "readout_ms": round(tr, 4),
            "paint_frac": round(ab_paint / (t_paint * 1e-3) / 1e9 / peak, 4),
            "readout_frac": round(ab_read / (t_read * 1e-3) / 1e9 / peak, 4),
-           "paint_readout_gparticles_per_s": round(nsum / ((tp + tr) * 1e-3) / 1e9, 3),
-           "paint_readout_frac": round((ab_paint + ab_read) / ((t_paint + t_read) * 1e-3) / 1e9 / peak, 4),
+           "paint_readout_gparticles_per_s": round(nsum / ((tf + tr) * 1e-3) / 1e9, 3),
+           "paint_readout_frac": round((ab_paint + ab_read) / ((t_first + t_read) * 1e-3) / 1e9 / peak, 4),
            "local_particles": int(nl)}
+    if reordered:
+        row["reordered"] = ("tile-sorted copy of the records: paint_ms / readout_ms reuse it (content hash + kernel "
+                            "[+ return to the caller's order]); paint_first_ms builds it; paint_readout_* count paint_first_ms + readout_ms")
+        row["paint_first_ms"] = round(tf, 4)
+        row["reorder_ms"] = round(max(tf - tp, 0.0), 4)
     return row, (t_paint, ab_paint, t_read, ab_read, nl)
 
 
@@ -454,34 +481,102 @@ def run_ours(args):
         ctx.d2h(Xh.array, X.ptr, X.nbytes)
         nb, fb = X.nbytes, F[0].nbytes
         del F
-        Xd = X                                    # the device buffer the uploads land in
+        _lib.check(ctx.lib.pmb_bin_release(ctx.handle))
         ke = max(1, min(args.steps, 8))
+
+        def stream_single():
+            """upload k + 1 || download k, compute between them; single device buffers"""
+            Xd = X
+            ctx.h2d_async(Xd.ptr, Xh.array, nb)
+            ctx.stream_record(1, 0)                   # event 0: upload of the coming step is complete
+            Fk = None
+            for it in range(ke):
+                ctx.stream_wait(0, 0)                 # compute waits for its positions ...
+                if it > 0:
+                    ctx.stream_wait(0, 2)             # ... and for the previous download: its F buffers are recycled now
+                Fk = None
+                Fk = step(Xd, ntot, [None] * 3)
+                ctx.stream_record(0, 1)               # event 1: forces of this step are complete
+                ctx.stream_wait(2, 1)
+                for d in range(3):
+                    ctx.d2h_async(Fh.array[d], Fk[d].ptr, fb)
+                ctx.stream_record(2, 2)               # event 2: download complete
+                if it + 1 < ke:
+                    ctx.stream_wait(1, 1)             # the next upload overwrites Xd: after the compute that reads it
+                    ctx.h2d_async(Xd.ptr, Xh.array, nb)
+                    ctx.stream_record(1, 0)
+            ctx.stream_sync(2)
+            ctx.stream_sync(1)
+            ctx.sync()
+            return Fk
+
+        def stream_double(X2):
+            """upload k + 1 || compute k || download k - 1: two position buffers, the force columns of a step stay
+            alive until their download has completed (events: 0 / 1 upload into buffer b complete, 2 / 3 compute of
+            a step on buffer b complete, 4 / 5 its download complete)"""
+            Xd = [X, X2]
+            ctx.h2d_async(Xd[0].ptr, Xh.array, nb)
+            ctx.stream_record(1, 0)
+            hold = {}
+            Fk = None
+            for it in range(ke):
+                b = it & 1
+                if it + 1 < ke:
+                    if it >= 1:
+                        ctx.stream_wait(1, 2 + (1 - b))   # buffer 1 - b was read by the compute of step it - 1
+                    ctx.h2d_async(Xd[1 - b].ptr, Xh.array, nb)
+                    ctx.stream_record(1, 1 - b)
+                ctx.stream_wait(0, b)
+                if it >= 2:
+                    ctx.stream_wait(0, 4 + b)             # the columns of step it - 2 go back to the pool only now
+                    hold.pop(it - 2)
+                Fk = step(Xd[b], ntot, [None] * 3)
+                ctx.stream_record(0, 2 + b)
+                ctx.stream_wait(2, 2 + b)
+                for d in range(3):
+                    ctx.d2h_async(Fh.array[d], Fk[d].ptr, fb)
+                ctx.stream_record(2, 4 + b)
+                hold[it] = Fk
+            ctx.stream_sync(2)
+            ctx.stream_sync(1)
+            ctx.sync()
+            hold.clear()
+            return Fk
+
+        overlap = "upload of step k+1 || download of step k (independent evaluations); compute between them"
+        Fk = None
+        X2 = None
+        # measured at 1 GPU, 1024^3 (ms per step): single buffers 727 - 753; three-way overlap 773 -- the copies and the
+        # HBM-bound kernels slow each other down; --e2e-double selects it
+        try:
+            free_b = ctx.mem_info()[0] + ctx._pooled
+            # two more sets of force columns and one more position buffer have to fit beside the step's own fields
+            if args.e2e_double and comm.allreduce(1 if free_b > 2.6 * nb + (8 << 30) else 0, op=C.MIN):
+                X2 = DeviceArray.empty(X.shape, "f8")
+        except Exception:
+            X2 = None
         comm.Barrier()
         ctx.sync()
         t0 = time.perf_counter()
-        ctx.h2d_async(Xd.ptr, Xh.array, nb)
-        ctx.stream_record(1, 0)                   # event 0: upload of the coming step is complete
-        Fk = None
-        for it in range(ke):
-            ctx.stream_wait(0, 0)                 # compute waits for its positions ...
-            if it > 0:
-                ctx.stream_wait(0, 2)             # ... and for the previous download: its F buffers are recycled now
-            Fk = None
-            Fk = step(Xd, ntot, [None] * 3)
-            ctx.stream_record(0, 1)               # event 1: forces of this step are complete
-            ctx.stream_wait(2, 1)
-            for d in range(3):
-                ctx.d2h_async(Fh.array[d], Fk[d].ptr, fb)
-            ctx.stream_record(2, 2)               # event 2: download complete
-            if it + 1 < ke:
-                ctx.stream_wait(1, 1)             # the next upload overwrites Xd: after the compute that reads it
-                ctx.h2d_async(Xd.ptr, Xh.array, nb)
-                ctx.stream_record(1, 0)
-        ctx.stream_sync(2)
-        ctx.stream_sync(1)
-        ctx.sync()
+        if X2 is not None:
+            try:
+                Fk = stream_double(X2)
+                overlap = "upload of step k+1 || compute of step k || download of step k-1 (independent evaluations, two position buffers)"
+            except Exception as e:      # out of device memory on a single large rank: fall back, time again
+                sys.stderr.write("e2e: double-buffered stream failed (%s); single buffers\n" % e)
+                Fk = None
+                X2 = None
+                ctx.stream_sync(2)
+                ctx.stream_sync(1)
+                ctx.sync()
+                ctx.empty_cache()
+                t0 = time.perf_counter()
+        if X2 is None:
+            Fk = stream_single()
         comm.Barrier()
         e2e_ms = comm.allreduce((time.perf_counter() - t0) * 1e3 / ke, op=C.MAX)
+        del X2
+        Xd = X
         # one strictly serial step for comparison
         comm.Barrier()
         t0 = time.perf_counter()
@@ -495,7 +590,7 @@ def run_ours(args):
         serial_ms = comm.allreduce((time.perf_counter() - t0) * 1e3, op=C.MAX)
         e2e = {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(nb),
                "d2h_bytes_per_step": int(3 * fb), "steps": ke, "serial_ms": round(serial_ms, 3),
-               "overlap": "upload of step k+1 || download of step k (independent evaluations); compute between them"}
+               "overlap": overlap}
         F = Fk
         del Xh, Fh, Xd, Fk
 

@@ -153,6 +153,10 @@ int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, i
  * pmb_bin_stats: reorders done so far and bytes held; pmb_bin_release frees the copy.  PMB_BIN=0 switches the
  * reorder off (the kernels then walk the array through a permutation), PMB_BIN=2 reorders every large array. */
 int pmb_bin_stats(pmb_ctx *ctx, int64_t *builds, int64_t *bytes_held);
+/* Memory-pressure hook: a host side that caches device blocks (the caching allocator of pmesh_b200/_lib.py; the
+ * reference's numpy arrays have no equivalent) registers a function that gives them back; the library calls it when
+ * an allocation of its own work space (scratch, sorted particle copies) fails and then tries once more. */
+int pmb_set_trim_callback(pmb_ctx *ctx, void (*cb)(void *), void *arg);
 int pmb_bin_release(pmb_ctx *ctx);
 
 /* elementwise helpers on (strided, up to 3-D) fields */
@@ -290,7 +294,7 @@ int pmb_fft_r2c(pmb_fft *plan, const void *real, void *cplx, double scale);
 int pmb_fft_c2r(pmb_fft *plan, const void *cplx, void *real);
 /* n (<= 4) backward transforms, results equal to n pmb_fft_c2r calls.  On slab decompositions with peer-memory
  * transposes the NVLink stores of every transform run on a second stream, under the cuFFT kernels of the others
- * (the three c2r of a force evaluation, examples/nbody.py:211-213); with PMB_FFT_OVERLAP=1 (default 0: one by one; measured at 2 GPUs, profiles/README.md). */
+ * (the three c2r of a force evaluation, examples/nbody.py:211-213); PMB_FFT_OVERLAP=0 runs them one by one. */
 int pmb_fft_c2r_multi(pmb_fft *plan, int n, const void *const *cplx_h, void *const *real_h);
 /* milliseconds spent inside the transpose kernels of the distributed transforms (events on the stream) and
  * the bytes they stored into other ranks' landing buffers over NVLink since the last reset */

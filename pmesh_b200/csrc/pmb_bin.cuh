@@ -64,11 +64,23 @@ static void pmb_bin_tiling(const PmbGeom &g, PmbBinTiling *t)
     }
 }
 
+// cell of a coordinate wrapped into the period and clamped to the canvas, 32-bit arithmetic (pmb_cell_of's 64-bit
+// modulo made the counting pass instruction-bound: ncu, 73 % issue active)
+__device__ __forceinline__ int pmb_bin_cell(double x, double scale, double translate, int per, int sz)
+{
+    double X = floor(pmb_gridpos(x, scale, translate));
+    X = fmin(fmax(X, -2.0e9), 2.0e9);
+    int t = (int) X;
+    const int p = per > 0 ? per : (sz > 0 ? sz : 1);
+    if ((unsigned) t >= (unsigned) p) t = pmb_wrap32(t, p);
+    return t >= sz ? sz - 1 : t;
+}
+
 __device__ __forceinline__ uint32_t pmb_bin_tile(const PmbGeom &g, const PmbBinTiling &t, const double *x)
 {
-    const int c0 = pmb_cell_of(x[0], g.scale[0], g.translate[0], g.period[0], g.size[0]) >> t.s0;
-    const int c1 = pmb_cell_of(x[1], g.scale[1], g.translate[1], g.period[1], g.size[1]) >> t.s1;
-    const int c2 = pmb_cell_of(x[2], g.scale[2], g.translate[2], g.period[2], g.size[2]) >> t.s2;
+    const int c0 = pmb_bin_cell(x[0], g.scale[0], g.translate[0], (int) g.period[0], (int) g.size[0]) >> t.s0;
+    const int c1 = pmb_bin_cell(x[1], g.scale[1], g.translate[1], (int) g.period[1], (int) g.size[1]) >> t.s1;
+    const int c2 = pmb_bin_cell(x[2], g.scale[2], g.translate[2], (int) g.period[2], (int) g.size[2]) >> t.s2;
     return (uint32_t) ((c0 * t.n1 + c1) * t.n2 + c2);
 }
 
@@ -165,7 +177,7 @@ pmb_k_bin_scan(const uint32_t *__restrict__ counts, uint32_t *__restrict__ curso
 // caller's order and the return pass (same traversal) finds its rows near the fronts it reads.
 // `variant` (PMB_BIN_VARIANT, measurements only -- anything but 0 does NOT sort): 1 slot = i (no atomics),
 // 2 atomics but slot = i, 3 pseudo-random slot (no atomics).  `cstride`: words between two cursors.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 pmb_k_bin_scatter(PmbGeom g, PmbParticles p, int64_t npart, PmbBinTiling t, uint32_t *cursors, int cstride,
                   double *__restrict__ spos, uint32_t *__restrict__ dest, unsigned long long *ticket, int variant)
 {
@@ -285,7 +297,7 @@ static int pmb_bin_grow(pmb_ctx *ctx, void **buf, size_t *have, size_t need)
 {
     if (need <= *have) return PMB_OK;
     if (*buf) { PMB_CUDA(cudaStreamSynchronize(ctx->stream)); PMB_CUDA(cudaFree(*buf)); *buf = NULL; *have = 0; }
-    cudaError_t e = cudaMalloc(buf, need);
+    cudaError_t e = pmb_work_alloc(ctx, buf, need);
     if (e != cudaSuccess) { cudaGetLastError(); *buf = NULL; return PMB_ENOMEM; }
     *have = need;
     return PMB_OK;
@@ -377,7 +389,7 @@ static int pmb_bin_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p
     const int cstride = 1;     // measured: cursors one per 128-byte line change nothing
     pmb_k_bin_scan<<<1, 1024, 0, ctx->stream>>>(d_counts, d_cursors, t.ntiles, cstride);
     PMB_LAUNCH_CHECK(ctx);
-    pmb_k_bin_scatter<<<pmb_grid(ctx, npart, 256 * 4, pmb_env_flag("PMB_BIN_SCATTER_CTAS", 4)), 256, 0, ctx->stream>>>(
+    pmb_k_bin_scatter<<<pmb_grid(ctx, npart, 256 * 4, pmb_env_flag("PMB_BIN_SCATTER_CTAS", 6)), 256, 0, ctx->stream>>>(
         g, p, npart, t, d_cursors, cstride, (double *) ctx->bin_pos, (uint32_t *) ctx->bin_dest,
         (unsigned long long *) ((char *) ctx->bin_small + 64), pmb_env_flag("PMB_BIN_VARIANT", 0));
     PMB_LAUNCH_CHECK(ctx);

@@ -273,6 +273,27 @@ extern "C" int pmb_set_workspace_limit(pmb_ctx *ctx, size_t nbytes)
     return PMB_OK;
 }
 
+// work space of the library itself (scratch, sorted particle copies): when the device is full the host side is
+// asked to give cached blocks back (pmb_set_trim_callback), then the allocation is tried once more
+cudaError_t pmb_work_alloc(pmb_ctx *ctx, void **out, size_t nbytes)
+{
+    cudaError_t e = cudaMalloc(out, nbytes);
+    if (e == cudaErrorMemoryAllocation && ctx->trim_cb) {
+        cudaGetLastError();
+        ctx->trim_cb(ctx->trim_arg);
+        e = cudaMalloc(out, nbytes);
+    }
+    return e;
+}
+
+extern "C" int pmb_set_trim_callback(pmb_ctx *ctx, void (*cb)(void *), void *arg)
+{
+    PMB_REQUIRE(ctx, "null context");
+    ctx->trim_cb = cb;
+    ctx->trim_arg = arg;
+    return PMB_OK;
+}
+
 int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out)
 {
     if (nbytes > ctx->scratch_bytes) {
@@ -283,7 +304,7 @@ int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out)
             ctx->scratch_bytes = 0;
         }
         size_t want = nbytes + (nbytes >> 3) + 256;
-        PMB_CUDA(cudaMalloc(&ctx->scratch, want));
+        PMB_CUDA(pmb_work_alloc(ctx, &ctx->scratch, want));
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;

@@ -658,10 +658,12 @@ static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, i
     if (R == 0 || cmax == 0 || nbatch == 0) return PMB_OK;
     const int64_t tr = (R + 31) / 32, tc = (cmax + 31) / 32;
     int64_t grid = tr * tc * ndest * nbatch;
-    // on its own stream the transpose shares the SMs with the cuFFT kernels of the other transforms: a few
-    // resident CTAs per SM keep the link busy (the kernel waits on NVLink stores) without starving them
+    // on its own (high-priority) stream the transpose shares the SMs with the cuFFT kernels of the other transforms:
+    // a few resident CTAs per SM keep the link busy (the kernel waits on NVLink stores) without starving them.
+    // Measured at 2 GPUs, 1024^3, the three c2r of a step (ms): one by one 26.4; overlapped with 1 / 2 / 4 CTAs per
+    // SM 33.0 / 24.6 / 23.0; 8 CTAs per SM at normal priority 39.6 (profiles/README.md)
     static int octas = -1;
-    if (octas < 0) { const char *e = getenv("PMB_FFT_OVERLAP_CTAS"); octas = e ? atoi(e) : 1; if (octas < 1) octas = 1; }
+    if (octas < 0) { const char *e = getenv("PMB_FFT_OVERLAP_CTAS"); octas = e ? atoi(e) : 4; if (octas < 1) octas = 1; }
     const int64_t cap = (int64_t) f->ctx->sm_count * (own_stream ? octas : 8);
     if (grid > cap) grid = cap;
     if (!own_stream) PMB_CHECK(lib_begin(f, 1));       // event brackets are taken on the compute stream only
@@ -955,7 +957,7 @@ extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, v
     PMB_REQUIRE(f && cplx_h && real_h && n >= 1 && n <= 4, "bad arguments");
     for (int d = 0; d < n; d++) PMB_REQUIRE(cplx_h[d] && real_h[d], "null field %d", d);
     static int overlap = -1;
-    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 0; }
+    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 1; }
     if (!(f->P > 1 && f->P1 == 1 && f->p2p && n >= 2 && overlap && f->work1)) {
         for (int d = 0; d < n; d++) PMB_CHECK(pmb_fft_c2r(f, cplx_h[d], real_h[d]));
         return PMB_OK;

@@ -80,11 +80,16 @@ struct pmb_ctx {
     int bin_uses;
     int bin_bypass;          // set while the ordinary kernels run on the sorted copy
     int64_t bin_builds;      // reorders done (diagnostics)
+    // memory-pressure hook of the host side (pmb_set_trim_callback): called when an allocation of the library's own
+    // work space fails, before it is tried once more
+    void (*trim_cb)(void *);
+    void *trim_arg;
 };
 
 void pmb_set_error(const char *fmt, ...);
 int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int pmb_scratch(pmb_ctx *ctx, size_t nbytes, void **out);
+cudaError_t pmb_work_alloc(pmb_ctx *ctx, void **out, size_t nbytes);
 int pmb_stream_barrier(pmb_ctx *ctx);
 int pmb_stream_barrier_on(pmb_ctx *ctx, cudaStream_t stream);
 int pmb_allgather_host(pmb_ctx *ctx, const void *send_h, void *recv_h, size_t nbytes);

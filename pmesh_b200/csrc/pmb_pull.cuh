@@ -115,6 +115,27 @@ __device__ __forceinline__ double pmb_pull_pick(const double *V, int k)
 }
 
 // contribution of sorted particle j to the cell at stencil offsets (ka, kb, kc) above its first point
+struct PmbPullRec { double x0, x1, x2, idb; };
+
+__device__ __forceinline__ PmbPullRec pmb_pull_load(const double *__restrict__ recs, uint32_t j)
+{
+    PmbPullRec r;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x0), "=d"(r.x1), "=d"(r.x2), "=d"(r.idb) : "l"(recs + 4 * (int64_t) j));
+    return r;
+}
+
+// contribution of a sorted particle (its record already loaded) to the cell at stencil offsets (ka, kb, kc)
+template <int FAM>
+__device__ __forceinline__ double pmb_pull_value_rec(const PmbGeom &g, int pcsfix, const PmbPullRec &r, double m, int ka, int kb, int kc)
+{
+    int I[FAM];
+    double V0[FAM], V1[FAM], V2[FAM];
+    pmb_axis_tuned<FAM>(pmb_gridpos(r.x0, g.scale[0], g.translate[0]), g.order[0], g.scale[0], pcsfix, I, V0);
+    pmb_axis_tuned<FAM>(pmb_gridpos(r.x1, g.scale[1], g.translate[1]), g.order[1], g.scale[1], pcsfix, I, V1);
+    pmb_axis_tuned<FAM>(pmb_gridpos(r.x2, g.scale[2], g.translate[2]), g.order[2], g.scale[2], pcsfix, I, V2);
+    return pmb_paint_value(true, m, pmb_pull_pick<FAM>(V0, ka), pmb_pull_pick<FAM>(V1, kb), pmb_pull_pick<FAM>(V2, kc));
+}
+
 template <int FAM>
 __device__ __forceinline__ double pmb_pull_value(const PmbGeom &g, int pcsfix, const double *__restrict__ recs,
                                                  const double *__restrict__ smass, double mass_scalar, uint32_t j,
@@ -137,12 +158,31 @@ __device__ __forceinline__ uint32_t pmb_pull_id(const double *__restrict__ recs,
     return (uint32_t) __double_as_longlong(__ldg(recs + 4 * (int64_t) j + 3));
 }
 
+// the run of neighbour q = (ka * FAM + kb) * FAM + kc of cell (c0, c1, c2)
+template <int FAM>
+__device__ __forceinline__ uint2 pmb_pull_run(const PmbPullGeom &pg, const uint2 *__restrict__ se, int c0, int c1, int c2, int q)
+{
+    const int ka = q / (FAM * FAM), kb = (q / FAM) % FAM, kc = q % FAM;
+    int b0 = pg.full[0] ? c0 - ka : c0 - ka + FAM - 1;
+    if (pg.full[0] && b0 < 0) b0 += pg.E[0];
+    int b1 = pg.full[1] ? c1 - kb : c1 - kb + FAM - 1;
+    if (pg.full[1] && b1 < 0) b1 += pg.E[1];
+    int b2 = pg.full[2] ? c2 - kc : c2 - kc + FAM - 1;
+    if (pg.full[2] && b2 < 0) b2 += pg.E[2];
+    return __ldg(se + (((int64_t) b0 * pg.E[1] + b1) * pg.E[2] + b2));
+}
+
+// One thread per mesh cell.  Common case (at most CAP contributions): gather (particle number, value) of every
+// contribution -- neighbours from the highest offset down, which for particles kept in lattice order is already
+// nearly ascending particle number -- insertion-sort by number, add in order.  Cells with more contributions
+// (clustered particles) merge their sorted runs head by head.  Both paths add in ascending particle number.
 template <typename MeshT, int FAM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (FAM <= 2 ? 8 : 5))
 pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, const double *__restrict__ recs,
            const double *__restrict__ smass, double mass_scalar, char *mesh)
 {
     constexpr int NR = FAM * FAM * FAM;
+    constexpr int CAP = FAM == 1 ? 8 : (FAM == 2 ? 24 : (FAM == 3 ? 56 : 112));
     const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t lin = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; lin < ncell; lin += stride) {
@@ -150,61 +190,75 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
         const int64_t r01 = lin / g.size[2];
         const int c1 = (int) (r01 % g.size[1]);
         const int c0 = (int) (r01 / g.size[1]);
-        // the runs that can reach this cell, in C order of the stencil offsets
-        uint32_t cur[NR], end[NR];
-        int nonempty = 0;
+        uint32_t ids[CAP];
+        double vals[CAP];
+        int cnt = 0;
+        uint32_t total = 0;
+        // one (ka, kb) row of neighbours at a time: its FAM run descriptors are requested together, then the first
+        // record of every non-empty run (independent loads); longer runs continue one record at a time
+#pragma unroll 1
+        for (int row = FAM * FAM - 1; row >= 0; row--) {
+            uint2 r[FAM];
 #pragma unroll
-        for (int ka = 0; ka < FAM; ka++) {
-            int b0 = pg.full[0] ? c0 - ka : c0 - ka + FAM - 1;
-            if (pg.full[0] && b0 < 0) b0 += pg.E[0];
+            for (int kc = 0; kc < FAM; kc++) r[kc] = pmb_pull_run<FAM>(pg, se, c0, c1, c2, row * FAM + kc);
+            PmbPullRec first[FAM];
+            double m[FAM];
 #pragma unroll
-            for (int kb = 0; kb < FAM; kb++) {
-                int b1 = pg.full[1] ? c1 - kb : c1 - kb + FAM - 1;
-                if (pg.full[1] && b1 < 0) b1 += pg.E[1];
+            for (int kc = 0; kc < FAM; kc++) {
+                total += r[kc].y - r[kc].x;
+                if (r[kc].x < r[kc].y) {
+                    first[kc] = pmb_pull_load(recs, r[kc].x);
+                    m[kc] = smass ? smass[r[kc].x] : mass_scalar;
+                }
+            }
 #pragma unroll
-                for (int kc = 0; kc < FAM; kc++) {
-                    int b2 = pg.full[2] ? c2 - kc : c2 - kc + FAM - 1;
-                    if (pg.full[2] && b2 < 0) b2 += pg.E[2];
-                    const uint2 r = __ldg(se + (((int64_t) b0 * pg.E[1] + b1) * pg.E[2] + b2));
-                    const int q = (ka * FAM + kb) * FAM + kc;
-                    cur[q] = r.x; end[q] = r.y;
-                    nonempty += r.y > r.x;
+            for (int kc = FAM - 1; kc >= 0; kc--) {
+                if (r[kc].x >= r[kc].y) continue;
+                if (cnt < CAP) {
+                    ids[cnt] = (uint32_t) __double_as_longlong(first[kc].idb);
+                    vals[cnt] = pmb_pull_value_rec<FAM>(g, pcsfix, first[kc], m[kc], row / FAM, row % FAM, kc);
+                    cnt++;
+                }
+                for (uint32_t j = r[kc].x + 1; j < r[kc].y && cnt < CAP; j++) {
+                    const PmbPullRec rr = pmb_pull_load(recs, j);
+                    ids[cnt] = (uint32_t) __double_as_longlong(rr.idb);
+                    vals[cnt] = pmb_pull_value_rec<FAM>(g, pcsfix, rr, smass ? smass[j] : mass_scalar, row / FAM, row % FAM, kc);
+                    cnt++;
                 }
             }
         }
-        if (!nonempty) continue;
+        if (!total) continue;
         MeshT *cell = (MeshT *) (mesh + c0 * g.strides[0] + c1 * g.strides[1] + c2 * g.strides[2]);
         MeshT acc = *cell;
-        // merge by particle number; on equal numbers the lower offset goes first.  CIC keeps the 8 run heads in
-        // registers (unrolled, predicated updates); wider stencils index them in local memory.
-        uint32_t head[NR];
-#pragma unroll
-        for (int q = 0; q < NR; q++) head[q] = cur[q] < end[q] ? pmb_pull_id(recs, cur[q]) : 0xFFFFFFFFu;
-        for (;;) {
-            int best = -1;
-            uint32_t bid = 0xFFFFFFFFu;
-#pragma unroll (FAM <= 2 ? NR : 1)
+        if (total <= (uint32_t) CAP) {
+            for (int k = 1; k < cnt; k++) {
+                const uint32_t id = ids[k];
+                const double v = vals[k];
+                int m = k - 1;
+                while (m >= 0 && ids[m] > id) { ids[m + 1] = ids[m]; vals[m + 1] = vals[m]; m--; }
+                ids[m + 1] = id; vals[m + 1] = v;
+            }
+            for (int k = 0; k < cnt; k++) acc = (MeshT) ((double) acc + vals[k]);
+        } else {
+            // merge the runs by particle number; on equal numbers the lower offset goes first
+            uint32_t cur[NR], end[NR], head[NR];
+#pragma unroll 1
             for (int q = 0; q < NR; q++) {
-                const bool take = cur[q] < end[q] && (best < 0 || head[q] < bid);
-                if (take) { best = q; bid = head[q]; }
+                const uint2 r = pmb_pull_run<FAM>(pg, se, c0, c1, c2, q);
+                cur[q] = r.x; end[q] = r.y;
+                head[q] = r.x < r.y ? pmb_pull_id(recs, r.x) : 0xFFFFFFFFu;
             }
-            if (best < 0) break;
-            uint32_t j = 0;
-            if (FAM <= 2) {
-#pragma unroll
-                for (int q = 0; q < NR; q++) if (q == best) j = cur[q];
-            } else {
-                j = cur[best];
-            }
-            acc = (MeshT) ((double) acc + pmb_pull_value<FAM>(g, pcsfix, recs, smass, mass_scalar, j, best / (FAM * FAM), (best / FAM) % FAM, best % FAM));
-            if (FAM <= 2) {
-#pragma unroll
-                for (int q = 0; q < NR; q++)
-                    if (q == best) {
-                        cur[q] = j + 1;
-                        head[q] = j + 1 < end[q] ? pmb_pull_id(recs, j + 1) : 0xFFFFFFFFu;
-                    }
-            } else {
+            for (;;) {
+                int best = -1;
+                uint32_t bid = 0xFFFFFFFFu;
+#pragma unroll 1
+                for (int q = 0; q < NR; q++) {
+                    const bool take = cur[q] < end[q] && (best < 0 || head[q] < bid);
+                    if (take) { best = q; bid = head[q]; }
+                }
+                if (best < 0) break;
+                const uint32_t j = cur[best];
+                acc = (MeshT) ((double) acc + pmb_pull_value<FAM>(g, pcsfix, recs, smass, mass_scalar, j, best / (FAM * FAM), (best / FAM) % FAM, best % FAM));
                 cur[best] = j + 1;
                 head[best] = j + 1 < end[best] ? pmb_pull_id(recs, j + 1) : 0xFFFFFFFFu;
             }
@@ -268,7 +322,7 @@ static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const Pm
     pmb_k_pull<MeshT, FAM><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
                                                                                      a->mass_scalar, (char *) a->mesh);
     PMB_LAUNCH_CHECK(ctx);
-    if (total > ((size_t) 4 << 30)) {
+    if (total > ((size_t) 40 << 30)) {
         // a large workspace goes back to the device instead of staying in the context's scratch
         PMB_CUDA(cudaStreamSynchronize(ctx->stream));
         PMB_CUDA(cudaFree(ctx->scratch));
