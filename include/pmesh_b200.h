@@ -150,14 +150,18 @@ int pmb_readout_grad(pmb_ctx *ctx, const pmb_resample_args *a, void *out_grad, i
 /* Particle arrays WITHOUT spatial order (the reference makes no ordering assumption, _window.pyx:157-165): paint
  * and readout of >= 2^18 particles on 3-D meshes work on a tile-sorted COPY of the position records kept in the
  * context (a one-pass counting sort; reused only while a content hash of the caller's array is unchanged).
- * pmb_bin_stats: reorders done so far and bytes held; pmb_bin_release frees the copy.  PMB_BIN=0 switches the
+ * pmb_bin_stats: reorders done so far and bytes held; pmb_bin_release frees the copy; pmb_bin_invalidate keeps its
+ * memory but forgets its content (the next call sorts again).  PMB_BIN=0 switches the
  * reorder off (the kernels then walk the array through a permutation), PMB_BIN=2 reorders every large array. */
 int pmb_bin_stats(pmb_ctx *ctx, int64_t *builds, int64_t *bytes_held);
 /* Memory-pressure hook: a host side that caches device blocks (the caching allocator of pmesh_b200/_lib.py; the
  * reference's numpy arrays have no equivalent) registers a function that gives them back; the library calls it when
  * an allocation of its own work space (scratch, sorted particle copies) fails and then tries once more. */
 int pmb_set_trim_callback(pmb_ctx *ctx, void (*cb)(void *), void *arg);
+/* the other direction: the library gives back what it caches for itself (scratch, sorted particle copies, permutations) */
+int pmb_ctx_trim(pmb_ctx *ctx);
 int pmb_bin_release(pmb_ctx *ctx);
+int pmb_bin_invalidate(pmb_ctx *ctx);
 
 /* elementwise helpers on (strided, up to 3-D) fields */
 int pmb_field_fill(pmb_ctx *ctx, void *mesh, int elsize, int ndim, const int64_t *size,

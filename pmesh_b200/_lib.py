@@ -62,7 +62,7 @@ SYMBOLS = [
     "pmb_malloc", "pmb_free", "pmb_malloc_host", "pmb_free_host", "pmb_memcpy_h2d", "pmb_memcpy_d2h",
     "pmb_memcpy_d2d", "pmb_memset", "pmb_memcpy_h2d_async", "pmb_memcpy_d2h_async", "pmb_stream_record", "pmb_stream_wait", "pmb_stream_sync", "pmb_mem_info", "pmb_timer_start", "pmb_timer_stop", "pmb_launch_count",
     "pmb_flush_l2", "pmb_set_workspace_limit", "pmb_window_set_table", "pmb_window_query", "pmb_window_fwindow",
-    "pmb_paint", "pmb_readout", "pmb_readout_multi", "pmb_readout_multi_gather", "pmb_readout_grad", "pmb_bin_stats", "pmb_bin_release", "pmb_set_trim_callback", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum", "pmb_field_dot",
+    "pmb_paint", "pmb_readout", "pmb_readout_multi", "pmb_readout_multi_gather", "pmb_readout_grad", "pmb_bin_stats", "pmb_bin_release", "pmb_bin_invalidate", "pmb_set_trim_callback", "pmb_ctx_trim", "pmb_field_fill", "pmb_field_scale", "pmb_field_sum", "pmb_field_dot",
     "pmb_axpy", "pmb_lincomb", "pmb_column_mod", "pmb_kick_drift", "pmb_dot",
     "pmb_particles_uniform", "pmb_particles_lattice", "pmb_particles_replicate",
     "pmb_decompose_count", "pmb_decompose_fill", "pmb_decompose_identity", "pmb_take", "pmb_gather_sum", "pmb_gather_sum_segments", "pmb_gather_add_segments",
@@ -89,7 +89,7 @@ _ARGTYPES = {
     "pmb_flush_l2": [_P], "pmb_set_workspace_limit": [_P, _Z],
     "pmb_window_set_table": [_P, _I, _P, _I, _D, _D, _D],
     "pmb_window_query": [_I, _I, _P, _P], "pmb_window_fwindow": [_I, _I, _P, _P, _L],
-    "pmb_paint": [_P, _P], "pmb_readout": [_P, _P], "pmb_readout_grad": [_P, _P, _P, _L, _L], "pmb_bin_stats": [_P, _P, _P], "pmb_bin_release": [_P], "pmb_set_trim_callback": [_P, _P, _P],
+    "pmb_paint": [_P, _P], "pmb_readout": [_P, _P], "pmb_readout_grad": [_P, _P, _P, _L, _L], "pmb_bin_stats": [_P, _P, _P], "pmb_bin_release": [_P], "pmb_bin_invalidate": [_P], "pmb_ctx_trim": [_P], "pmb_set_trim_callback": [_P, _P, _P],
     "pmb_readout_multi": [_P, _P, _I, _P, _P, _P],
     "pmb_readout_multi_gather": [_P, _P, _I, _P, _P, _P, _P, _L, _L],
     "pmb_field_fill": [_P, _P, _I, _I, _P, _P, _D], "pmb_field_scale": [_P, _P, _I, _I, _I, _P, _P, _D],
@@ -212,6 +212,11 @@ class Context(object):
         rc = self.lib.pmb_malloc(self.handle, ctypes.c_size_t(size), ctypes.byref(p))
         if rc != 0 and pool:
             self.empty_cache()
+            rc = self.lib.pmb_malloc(self.handle, ctypes.c_size_t(size), ctypes.byref(p))
+        if rc != 0:
+            # the library's own caches (scratch, sorted particle copies) go last: the calls that use them fall back
+            # to slower paths instead of failing
+            self.lib.pmb_ctx_trim(self.handle)
             rc = self.lib.pmb_malloc(self.handle, ctypes.c_size_t(size), ctypes.byref(p))
         check(rc)
         sizes[p.value] = size

@@ -380,6 +380,19 @@ static int pmb_bin_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p
         ctx->bin_sig = 0;       // no room: the permutation walk serves this array
         return PMB_OK;
     }
+    {
+        // never take the device's last bytes: kernels that run for the first time still have to load their code
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < ((size_t) 1 << 30)) {
+            cudaGetLastError();
+            PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->bin_pos); cudaFree(ctx->bin_dest);
+            ctx->bin_pos = ctx->bin_dest = NULL;
+            ctx->bin_pos_bytes = ctx->bin_dest_bytes = 0;
+            ctx->bin_sig = 0;
+            return PMB_OK;
+        }
+    }
     PMB_CUDA(cudaMemsetAsync(ctx->bin_small, 0, 256 + sizeof(uint32_t) * t.ntiles, ctx->stream));
     if (t.ntiles <= PMB_BIN_MAXTILES)
         pmb_k_bin_count<1><<<ctx->sm_count, PMB_BIN_COUNT_THREADS, sizeof(uint32_t) * t.ntiles, ctx->stream>>>(g, p, npart, t, d_counts, d_hash);

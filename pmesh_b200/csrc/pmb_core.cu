@@ -17,6 +17,9 @@ void pmb_set_error(const char *fmt, ...)
 int pmb_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     pmb_set_error("CUDA error %d (%s) at %s:%d in %s", (int) e, cudaGetErrorString(e), file, line, what);
+    // the runtime remembers the last error until somebody reads it: a failed allocation that the caller recovers
+    // from (the host allocator empties its pool and retries) must not surface at the next kernel-launch check
+    cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? PMB_ENOMEM : PMB_ECUDA;
 }
 

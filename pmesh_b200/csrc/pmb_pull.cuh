@@ -172,57 +172,96 @@ __device__ __forceinline__ uint2 pmb_pull_run(const PmbPullGeom &pg, const uint2
     return __ldg(se + (((int64_t) b0 * pg.E[1] + b1) * pg.E[2] + b2));
 }
 
+// Weight records (PRE): per sorted particle RS doubles -- particle number, V0[k] * m, V1[k], V2[k] (k < FAM), padding to
+// whole 32-byte sectors -- written once by pmb_k_pull_records_w.  The pull kernel visits every particle FAM^3 times;
+// the position records make it evaluate 3 * FAM weights at every visit (CIC 8 x, PCS 64 x redundant arithmetic).
+// MEASURED (512^3, B200): slower -- CIC pull 12.4 ms against 8.5, PCS 160 against 115: the wider records (64 - 128 bytes,
+// each read FAM^3 times) double the L1 / L2 traffic the kernel is really bound by.  Kept behind PMB_PULL_WEIGHTS=1.
+template <int FAM>
+struct PmbPullW { static constexpr int RS = FAM == 1 ? 4 : (FAM == 2 ? 8 : (FAM == 3 ? 12 : 16)); };
+
+template <int FAM>
+__global__ void __launch_bounds__(256)
+pmb_k_pull_records_w(PmbGeom g, int pcsfix, PmbParticles p, const uint32_t *__restrict__ ids, int64_t n, double *__restrict__ recs)
+{
+    constexpr int RS = PmbPullW<FAM>::RS;
+    int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        const int64_t i = ids[j];
+        double x[3];
+        pmb_load_pos<3>(p, i, x);
+        const double m = pmb_load_mass(p, i);
+        int I[FAM];
+        double V0[FAM], V1[FAM], V2[FAM];
+        pmb_axis_tuned<FAM>(pmb_gridpos(x[0], g.scale[0], g.translate[0]), g.order[0], g.scale[0], pcsfix, I, V0);
+        pmb_axis_tuned<FAM>(pmb_gridpos(x[1], g.scale[1], g.translate[1]), g.order[1], g.scale[1], pcsfix, I, V1);
+        pmb_axis_tuned<FAM>(pmb_gridpos(x[2], g.scale[2], g.translate[2]), g.order[2], g.scale[2], pcsfix, I, V2);
+        double w[RS];
+#pragma unroll
+        for (int k = 0; k < RS; k++) w[k] = 0.0;
+        w[0] = __longlong_as_double((long long) i);
+#pragma unroll
+        for (int k = 0; k < FAM; k++) { w[1 + k] = V0[k] * m; w[1 + FAM + k] = V1[k]; w[1 + 2 * FAM + k] = V2[k]; }
+#pragma unroll
+        for (int k = 0; k < RS; k += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(recs + RS * j + k), "d"(w[k]), "d"(w[k + 1]), "d"(w[k + 2]), "d"(w[k + 3]) : "memory");
+    }
+}
+
+// (particle number, value) of the contribution of sorted particle j at stencil offsets (ka, kb, kc)
+template <int FAM, bool PRE>
+__device__ __forceinline__ void pmb_pull_contrib(const PmbGeom &g, int pcsfix, const double *__restrict__ recs,
+                                                 const double *__restrict__ smass, double mass_scalar, uint32_t j,
+                                                 int ka, int kb, int kc, uint32_t &id, double &val)
+{
+    if (PRE) {
+        const double *r = recs + (int64_t) PmbPullW<FAM>::RS * j;
+        id = (uint32_t) __double_as_longlong(__ldg(r));
+        val = (__ldg(r + 1 + ka) * __ldg(r + 1 + FAM + kb)) * __ldg(r + 1 + 2 * FAM + kc);      // ((V0 * m) * V1) * V2
+    } else {
+        const PmbPullRec rr = pmb_pull_load(recs, j);
+        id = (uint32_t) __double_as_longlong(rr.idb);
+        val = pmb_pull_value_rec<FAM>(g, pcsfix, rr, smass ? smass[j] : mass_scalar, ka, kb, kc);
+    }
+}
+
 // One thread per mesh cell.  Common case (at most CAP contributions): gather (particle number, value) of every
 // contribution -- neighbours from the highest offset down, which for particles kept in lattice order is already
 // nearly ascending particle number -- insertion-sort by number, add in order.  Cells with more contributions
 // (clustered particles) merge their sorted runs head by head.  Both paths add in ascending particle number.
-template <typename MeshT, int FAM>
+template <typename MeshT, int FAM, bool PRE>
 __global__ void __launch_bounds__(128, (FAM <= 2 ? 8 : 5))
 pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, const double *__restrict__ recs,
            const double *__restrict__ smass, double mass_scalar, char *mesh)
 {
     constexpr int NR = FAM * FAM * FAM;
     constexpr int CAP = FAM == 1 ? 8 : (FAM == 2 ? 24 : (FAM == 3 ? 56 : 112));
-    const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t lin = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; lin < ncell; lin += stride) {
-        const int c2 = (int) (lin % g.size[2]);
-        const int64_t r01 = lin / g.size[2];
-        const int c1 = (int) (r01 % g.size[1]);
-        const int c0 = (int) (r01 / g.size[1]);
+    constexpr int RW = PRE ? PmbPullW<FAM>::RS : 4;          // words per record; the particle number is word 0 (PRE) or 3
+    constexpr int IDW = PRE ? 0 : 3;
+    const uint32_t s1 = (uint32_t) g.size[1], s2 = (uint32_t) g.size[2];
+    const uint32_t ncell = (uint32_t) (g.size[0] * g.size[1] * g.size[2]);       // < 2^31: the key space is
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t lin = blockIdx.x * blockDim.x + threadIdx.x; lin < ncell; lin += stride) {
+        const int c2 = (int) (lin % s2);
+        const uint32_t r01 = lin / s2;
+        const int c1 = (int) (r01 % s1);
+        const int c0 = (int) (r01 / s1);
         uint32_t ids[CAP];
         double vals[CAP];
         int cnt = 0;
         uint32_t total = 0;
-        // one (ka, kb) row of neighbours at a time: its FAM run descriptors are requested together, then the first
-        // record of every non-empty run (independent loads); longer runs continue one record at a time
+        // one (ka, kb) row of neighbours at a time: its FAM run descriptors are requested together
 #pragma unroll 1
         for (int row = FAM * FAM - 1; row >= 0; row--) {
             uint2 r[FAM];
 #pragma unroll
             for (int kc = 0; kc < FAM; kc++) r[kc] = pmb_pull_run<FAM>(pg, se, c0, c1, c2, row * FAM + kc);
-            PmbPullRec first[FAM];
-            double m[FAM];
-#pragma unroll
-            for (int kc = 0; kc < FAM; kc++) {
-                total += r[kc].y - r[kc].x;
-                if (r[kc].x < r[kc].y) {
-                    first[kc] = pmb_pull_load(recs, r[kc].x);
-                    m[kc] = smass ? smass[r[kc].x] : mass_scalar;
-                }
-            }
 #pragma unroll
             for (int kc = FAM - 1; kc >= 0; kc--) {
-                if (r[kc].x >= r[kc].y) continue;
-                if (cnt < CAP) {
-                    ids[cnt] = (uint32_t) __double_as_longlong(first[kc].idb);
-                    vals[cnt] = pmb_pull_value_rec<FAM>(g, pcsfix, first[kc], m[kc], row / FAM, row % FAM, kc);
-                    cnt++;
-                }
-                for (uint32_t j = r[kc].x + 1; j < r[kc].y && cnt < CAP; j++) {
-                    const PmbPullRec rr = pmb_pull_load(recs, j);
-                    ids[cnt] = (uint32_t) __double_as_longlong(rr.idb);
-                    vals[cnt] = pmb_pull_value_rec<FAM>(g, pcsfix, rr, smass ? smass[j] : mass_scalar, row / FAM, row % FAM, kc);
+                total += r[kc].y - r[kc].x;
+                for (uint32_t j = r[kc].x; j < r[kc].y && cnt < CAP; j++) {
+                    pmb_pull_contrib<FAM, PRE>(g, pcsfix, recs, smass, mass_scalar, j, row / FAM, row % FAM, kc, ids[cnt], vals[cnt]);
                     cnt++;
                 }
             }
@@ -246,7 +285,7 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
             for (int q = 0; q < NR; q++) {
                 const uint2 r = pmb_pull_run<FAM>(pg, se, c0, c1, c2, q);
                 cur[q] = r.x; end[q] = r.y;
-                head[q] = r.x < r.y ? pmb_pull_id(recs, r.x) : 0xFFFFFFFFu;
+                head[q] = r.x < r.y ? (uint32_t) __double_as_longlong(__ldg(recs + (int64_t) RW * r.x + IDW)) : 0xFFFFFFFFu;
             }
             for (;;) {
                 int best = -1;
@@ -258,9 +297,12 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
                 }
                 if (best < 0) break;
                 const uint32_t j = cur[best];
-                acc = (MeshT) ((double) acc + pmb_pull_value<FAM>(g, pcsfix, recs, smass, mass_scalar, j, best / (FAM * FAM), (best / FAM) % FAM, best % FAM));
+                uint32_t id;
+                double v;
+                pmb_pull_contrib<FAM, PRE>(g, pcsfix, recs, smass, mass_scalar, j, best / (FAM * FAM), (best / FAM) % FAM, best % FAM, id, v);
+                acc = (MeshT) ((double) acc + v);
                 cur[best] = j + 1;
-                head[best] = j + 1 < end[best] ? pmb_pull_id(recs, j + 1) : 0xFFFFFFFFu;
+                head[best] = j + 1 < end[best] ? (uint32_t) __double_as_longlong(__ldg(recs + (int64_t) RW * (j + 1) + IDW)) : 0xFFFFFFFFu;
             }
         }
         *cell = acc;
@@ -297,9 +339,17 @@ static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const Pm
                                              (int) n, 0, bits, ctx->stream));
     auto up = [](size_t b) { return (b + 255) & ~(size_t) 255; };
     const size_t b_keys = up(sizeof(KeyT) * n), b_ids = up(sizeof(uint32_t) * n), b_se = up(sizeof(uint2) * (size_t) nkeys);
-    const size_t b_recs = up(32 * (size_t) n), b_mass = a->mass ? up(sizeof(double) * n) : 0, b_temp = up(temp);
+    const size_t b_temp = up(temp);
+    // weight records (3 * FAM + 1 doubles per particle, padded) when they fit beside everything else, else position
+    // records (32 bytes) whose weights are evaluated at every visit
+    size_t free_b = 0, total_b = 0;
+    PMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fixed = 2 * b_keys + 2 * b_ids + b_temp + b_se + 256;
+    const size_t b_wrecs = up(sizeof(double) * PmbPullW<FAM>::RS * (size_t) n);
+    const bool pre = pmb_env_flag("PMB_PULL_WEIGHTS", 0) && fixed + b_wrecs + ((size_t) 2 << 30) < free_b + ctx->scratch_bytes;
+    const size_t b_recs = pre ? b_wrecs : up(32 * (size_t) n), b_mass = (a->mass && !pre) ? up(sizeof(double) * n) : 0;
     // keys in | keys out | ids in | ids out | cub temp | runs | records | mass   (records overlay nothing: simple and safe)
-    const size_t total = 2 * b_keys + 2 * b_ids + b_temp + b_se + b_recs + b_mass + 256;
+    const size_t total = fixed + b_recs + b_mass;
     void *ws = NULL;
     if (pmb_scratch(ctx, total, &ws) != PMB_OK) { cudaGetLastError(); return PMB_OK; }
     char *b = (char *) ws;
@@ -308,7 +358,7 @@ static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const Pm
     void *tmp = b + 2 * b_keys + 2 * b_ids;
     uint2 *se = (uint2 *) (b + 2 * b_keys + 2 * b_ids + b_temp);
     double *recs = (double *) ((char *) se + b_se);
-    double *smass = a->mass ? (double *) ((char *) recs + b_recs) : NULL;
+    double *smass = (a->mass && !pre) ? (double *) ((char *) recs + b_recs) : NULL;
     pmb_k_pull_keys<KeyT, FAM><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(g, pg, p, n, a->pcs_gradient_scale_fix, k0, i0);
     PMB_LAUNCH_CHECK(ctx);
     PMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, temp, k0, k1, i0, i1, (int) n, 0, bits, ctx->stream));
@@ -316,11 +366,18 @@ static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const Pm
     PMB_CUDA(cudaMemsetAsync(se, 0, sizeof(uint2) * (size_t) nkeys, ctx->stream));
     pmb_k_pull_runs<KeyT><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(k1, n, nkeys, se);
     PMB_LAUNCH_CHECK(ctx);
-    pmb_k_pull_records<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(p, i1, n, recs, smass);
-    PMB_LAUNCH_CHECK(ctx);
     const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
-    pmb_k_pull<MeshT, FAM><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
-                                                                                     a->mass_scalar, (char *) a->mesh);
+    if (pre) {
+        pmb_k_pull_records_w<FAM><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(g, a->pcs_gradient_scale_fix, p, i1, n, recs);
+        PMB_LAUNCH_CHECK(ctx);
+        pmb_k_pull<MeshT, FAM, true><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, NULL,
+                                                                                               a->mass_scalar, (char *) a->mesh);
+    } else {
+        pmb_k_pull_records<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(p, i1, n, recs, smass);
+        PMB_LAUNCH_CHECK(ctx);
+        pmb_k_pull<MeshT, FAM, false><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
+                                                                                                a->mass_scalar, (char *) a->mesh);
+    }
     PMB_LAUNCH_CHECK(ctx);
     if (total > ((size_t) 40 << 30)) {
         // a large workspace goes back to the device instead of staying in the context's scratch

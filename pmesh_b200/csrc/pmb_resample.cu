@@ -1216,6 +1216,27 @@ extern "C" int pmb_bin_stats(pmb_ctx *ctx, int64_t *builds, int64_t *bytes_held)
     return PMB_OK;
 }
 
+// everything the library caches for itself goes back to the device (the host allocator calls this before it gives up)
+extern "C" int pmb_ctx_trim(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    PMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    pmb_bin_free(ctx);
+    if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = NULL; ctx->scratch_bytes = 0; }
+    if (ctx->perm_ids) { cudaFree(ctx->perm_ids); ctx->perm_ids = NULL; ctx->perm_bytes = 0; ctx->perm_sig = 0; }
+    cudaGetLastError();
+    return PMB_OK;
+}
+
+extern "C" int pmb_bin_invalidate(pmb_ctx *ctx)
+{
+    PMB_REQUIRE(ctx, "null context");
+    ctx->bin_sig = 0;
+    ctx->bin_state = 0;
+    ctx->bin_npart = -1;
+    return PMB_OK;
+}
+
 extern "C" int pmb_bin_release(pmb_ctx *ctx)
 {
     PMB_REQUIRE(ctx, "null context");
