@@ -201,6 +201,8 @@ class ForceStep(object):
         # arrays without spatial order, pmb_bin.cuh) must not be reused just because the bench repeats its input
         from pmesh_b200 import _lib
         _lib.check(pm.ctx.lib.pmb_bin_invalidate(pm.ctx.handle))
+        for d in range(3):
+            F[d] = None           # the previous evaluation's columns go back to the allocator before new ones are made
         layout = self._t("decompose", lambda: pm.decompose(X, smoothing=1.0 * pm.resampler.support))
         lpos = self._t("exchange", lambda: layout.exchange(X))
         self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))

@@ -178,6 +178,12 @@ __device__ __forceinline__ uint2 pmb_pull_run(const PmbPullGeom &pg, const uint2
 // MEASURED (512^3, B200): slower -- CIC pull 12.4 ms against 8.5, PCS 160 against 115: the wider records (64 - 128 bytes,
 // each read FAM^3 times) double the L1 / L2 traffic the kernel is really bound by.  Kept behind PMB_PULL_WEIGHTS=1.
 template <int FAM>
+struct PmbPullCap {
+    static constexpr bool SMEM = FAM <= 2;
+    static constexpr int CAP = FAM == 1 ? 8 : (FAM == 2 ? 16 : (FAM == 3 ? 56 : 112));
+};
+
+template <int FAM>
 struct PmbPullW { static constexpr int RS = FAM == 1 ? 4 : (FAM == 2 ? 8 : (FAM == 3 ? 12 : 16)); };
 
 template <int FAM>
@@ -236,19 +242,36 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
            const double *__restrict__ smass, double mass_scalar, char *mesh)
 {
     constexpr int NR = FAM * FAM * FAM;
-    constexpr int CAP = FAM == 1 ? 8 : (FAM == 2 ? 24 : (FAM == 3 ? 56 : 112));
+    // (particle number, value) of a cell's contributions live in SHARED memory, entry k of thread t at [k][t]: as
+    // per-thread local arrays they thrashed L1 (1024 threads x 384 bytes per SM; ncu: 28 % of the local loads missed,
+    // 5 L2 requests per cell) and spilled to DRAM for the wider windows
+    // (measured at 512^3: CIC 8.1 -> 7.5 ms).  The wider windows keep local arrays: their lists (56 / 112 entries) in
+    // shared memory leave 3 / 1 resident CTAs per SM and the kernel twice / three times slower (TSC 84 ms against 46).
+    constexpr int CAP = PmbPullCap<FAM>::CAP;
+    constexpr bool SM = PmbPullCap<FAM>::SMEM;
+    constexpr int ST = SM ? 128 : 1;
+    extern __shared__ double pull_smem[];
+    uint32_t lids[SM ? 1 : CAP];
+    double lvals[SM ? 1 : CAP];
+    double *vals = SM ? pull_smem + threadIdx.x : lvals;
+    uint32_t *ids = SM ? (uint32_t *) (pull_smem + CAP * 128) + threadIdx.x : lids;
     constexpr int RW = PRE ? PmbPullW<FAM>::RS : 4;          // words per record; the particle number is word 0 (PRE) or 3
     constexpr int IDW = PRE ? 0 : 3;
-    const uint32_t s1 = (uint32_t) g.size[1], s2 = (uint32_t) g.size[2];
-    const uint32_t ncell = (uint32_t) (g.size[0] * g.size[1] * g.size[2]);       // < 2^31: the key space is
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t lin = blockIdx.x * blockDim.x + threadIdx.x; lin < ncell; lin += stride) {
-        const int c2 = (int) (lin % s2);
-        const uint32_t r01 = lin / s2;
-        const int c1 = (int) (r01 % s1);
-        const int c0 = (int) (r01 / s1);
-        uint32_t ids[CAP];
-        double vals[CAP];
+    // a warp owns a block of 2 x 2 x 8 cells (8 along the contiguous axis: two full sectors per mesh row): the FAM^3
+    // neighbourhoods of its lanes overlap, so most of their run descriptors and records are the SAME sectors and the
+    // requests of one instruction coalesce (one cell per lane along z alone: 5 L2 requests per cell, each record
+    // fetched 2 x from DRAM).  Blocks are numbered z-fastest: the four warps of a CTA work on neighbouring blocks.
+    const uint32_t nt1 = (uint32_t) ((g.size[1] + 1) >> 1), nt2 = (uint32_t) ((g.size[2] + 7) >> 3);
+    const uint32_t nblk = (uint32_t) ((g.size[0] + 1) >> 1) * nt1 * nt2;       // < 2^31 / 8
+    const uint32_t wstride = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblk; blk += wstride) {
+        const uint32_t t01 = blk / nt2;
+        const int c2 = (int) ((blk - t01 * nt2) << 3) + (lane & 7);
+        const uint32_t t0 = t01 / nt1;
+        const int c1 = (int) ((t01 - t0 * nt1) << 1) + ((lane >> 3) & 1);
+        const int c0 = (int) (t0 << 1) + (lane >> 4);
+        if (c0 >= (int) g.size[0] || c1 >= (int) g.size[1] || c2 >= (int) g.size[2]) continue;
         int cnt = 0;
         uint32_t total = 0;
         // one (ka, kb) row of neighbours at a time: its FAM run descriptors are requested together
@@ -261,7 +284,11 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
             for (int kc = FAM - 1; kc >= 0; kc--) {
                 total += r[kc].y - r[kc].x;
                 for (uint32_t j = r[kc].x; j < r[kc].y && cnt < CAP; j++) {
-                    pmb_pull_contrib<FAM, PRE>(g, pcsfix, recs, smass, mass_scalar, j, row / FAM, row % FAM, kc, ids[cnt], vals[cnt]);
+                    uint32_t id;
+                    double v;
+                    pmb_pull_contrib<FAM, PRE>(g, pcsfix, recs, smass, mass_scalar, j, row / FAM, row % FAM, kc, id, v);
+                    ids[cnt * ST] = id;
+                    vals[cnt * ST] = v;
                     cnt++;
                 }
             }
@@ -271,13 +298,13 @@ pmb_k_pull(PmbGeom g, PmbPullGeom pg, int pcsfix, const uint2 *__restrict__ se, 
         MeshT acc = *cell;
         if (total <= (uint32_t) CAP) {
             for (int k = 1; k < cnt; k++) {
-                const uint32_t id = ids[k];
-                const double v = vals[k];
+                const uint32_t id = ids[k * ST];
+                const double v = vals[k * ST];
                 int m = k - 1;
-                while (m >= 0 && ids[m] > id) { ids[m + 1] = ids[m]; vals[m + 1] = vals[m]; m--; }
-                ids[m + 1] = id; vals[m + 1] = v;
+                while (m >= 0 && ids[m * ST] > id) { ids[(m + 1) * ST] = ids[m * ST]; vals[(m + 1) * ST] = vals[m * ST]; m--; }
+                ids[(m + 1) * ST] = id; vals[(m + 1) * ST] = v;
             }
-            for (int k = 0; k < cnt; k++) acc = (MeshT) ((double) acc + vals[k]);
+            for (int k = 0; k < cnt; k++) acc = (MeshT) ((double) acc + vals[k * ST]);
         } else {
             // merge the runs by particle number; on equal numbers the lower offset goes first
             uint32_t cur[NR], end[NR], head[NR];
@@ -367,15 +394,24 @@ static int pmb_pull_paint_fam(pmb_ctx *ctx, const pmb_resample_args *a, const Pm
     pmb_k_pull_runs<KeyT><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(k1, n, nkeys, se);
     PMB_LAUNCH_CHECK(ctx);
     const int64_t ncell = g.size[0] * g.size[1] * g.size[2];
+    const size_t smem = PmbPullCap<FAM>::SMEM ? (size_t) PmbPullCap<FAM>::CAP * 128 * (sizeof(double) + sizeof(uint32_t)) : 0;
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            PMB_CUDA(cudaFuncSetAttribute(pmb_k_pull<MeshT, FAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            PMB_CUDA(cudaFuncSetAttribute(pmb_k_pull<MeshT, FAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_done = true;
+        }
+    }
     if (pre) {
         pmb_k_pull_records_w<FAM><<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(g, a->pcs_gradient_scale_fix, p, i1, n, recs);
         PMB_LAUNCH_CHECK(ctx);
-        pmb_k_pull<MeshT, FAM, true><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, NULL,
+        pmb_k_pull<MeshT, FAM, true><<<pmb_grid(ctx, ncell, 128, 16), 128, smem, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, NULL,
                                                                                                a->mass_scalar, (char *) a->mesh);
     } else {
         pmb_k_pull_records<<<pmb_grid(ctx, n, 256, 8), 256, 0, ctx->stream>>>(p, i1, n, recs, smass);
         PMB_LAUNCH_CHECK(ctx);
-        pmb_k_pull<MeshT, FAM, false><<<pmb_grid(ctx, ncell, 128, 16), 128, 0, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
+        pmb_k_pull<MeshT, FAM, false><<<pmb_grid(ctx, ncell, 128, 16), 128, smem, ctx->stream>>>(g, pg, a->pcs_gradient_scale_fix, se, recs, smass,
                                                                                                 a->mass_scalar, (char *) a->mesh);
     }
     PMB_LAUNCH_CHECK(ctx);

@@ -1,0 +1,13 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_pull.py -x -q -m gpu > gpurun_out/r2g_tests.log 2>&1; tail -3 gpurun_out/r2g_tests.log
+timeout 600 python tools/bench_windows.py --n 512 --windows cic,tsc,pcs > gpurun_out/r2g_windows_512.json 2> gpurun_out/r2g_windows_512.err; python -c "
+import json
+d=json.load(open('gpurun_out/r2g_windows_512.json'))
+for k,v in d['windows'].items(): print(k, v['paint_deterministic'])
+"
+timeout 900 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --particles uniform --inputs uniform --breakdown > gpurun_out/r2g_bench1_step_uniform.json 2> gpurun_out/r2g_bench1_step_uniform.err; tail -c 300 gpurun_out/r2g_bench1_step_uniform.err; python -c "
+import json
+d=json.loads(open('gpurun_out/r2g_bench1_step_uniform.json').read().strip().splitlines()[-1])
+print(d['value'], d['stage_ms_per_step'], d['verify'].get('parity_rel_err'))
+"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests.sum --clock-control none -k regex:"pmb_k_pull" -c 24 --csv --log-file gpurun_out/r2g_pull_launches_512.csv python tools/bench_windows.py --n 512 --windows cic,tsc,pcs > gpurun_out/r2g_pull_ncu.log 2>&1
