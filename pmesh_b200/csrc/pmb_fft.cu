@@ -39,6 +39,8 @@ struct pmb_fft {
     int64_t s2, mc;         // complex space: my block of the half-complex axis 2 (over P1); slabs: 0, nc
     cufftHandle full_r2c, full_c2r;         // P == 1
     cufftHandle slab_r2c, slab_c2r, line;   // slabs
+    cufftHandle slab_r2c_part;              // 2-D r2c over m0 / r2c_chunks planes (pipelined forward transform)
+    int r2c_chunks;                         // 0: no partial plan
     cufftHandle pen_r2c, pen_c2r, pen_l1, pen_l0;   // pencils: 1-D transforms along axes 2, 1, 0
     bool have_full, have_slab, have_pen;
     void *work0, *work1;
@@ -368,6 +370,16 @@ extern "C" int pmb_fft_create_np(pmb_ctx *ctx, int ndim, const int64_t *nmesh, i
                                 dbl ? CUFFT_D2Z : CUFFT_R2C, f->m0));
             PMB_CHECK(make_plan(f, &f->slab_c2r, 2, n2, inc, f->n[1] * f->nc, inr, f->n[1] * 2 * f->nc,
                                 dbl ? CUFFT_Z2D : CUFFT_C2R, f->m0));
+            // forward transform in plane chunks: the NVLink transpose of chunk k runs under the 2-D FFT of chunk k + 1
+            int chunks = 4;
+            { const char *e = getenv("PMB_FFT_CHUNKS"); if (e) chunks = atoi(e); }
+            if (chunks > 4) chunks = 4;
+            f->r2c_chunks = 0;
+            if (f->P > 1 && chunks >= 2 && f->m0 % chunks == 0 && f->m0 / chunks >= 8) {
+                PMB_CHECK(make_plan(f, &f->slab_r2c_part, 2, n2, inr, f->n[1] * 2 * f->nc, inc, f->n[1] * f->nc,
+                                    dbl ? CUFFT_D2Z : CUFFT_R2C, f->m0 / chunks));
+                f->r2c_chunks = chunks;
+            }
         }
         if (f->m1 > 0) {
             long long n1[1] = {f->n[0]};
@@ -394,7 +406,7 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
     cudaStreamSynchronize(f->ctx->stream);
     if (f->have_full) { cufftDestroy(f->full_r2c); cufftDestroy(f->full_c2r); }
     if (f->have_slab) {
-        if (f->m0 > 0) { cufftDestroy(f->slab_r2c); cufftDestroy(f->slab_c2r); }
+        if (f->m0 > 0) { cufftDestroy(f->slab_r2c); cufftDestroy(f->slab_c2r); if (f->r2c_chunks) cufftDestroy(f->slab_r2c_part); }
         if (f->m1 > 0) cufftDestroy(f->line);
     }
     if (f->have_pen) {
@@ -451,25 +463,25 @@ extern "C" int pmb_fft_layout(pmb_fft *f, int64_t *i_start, int64_t *i_shape, in
 static int lib_flush(pmb_fft *f)
 {
     if (f->nev == 0) return PMB_OK;
-    PMB_CUDA(cudaEventSynchronize(f->ev[f->nev - 1][1]));
     for (int i = 0; i < f->nev; i++) {
         float ms = 0;
+        PMB_CUDA(cudaEventSynchronize(f->ev[i][1]));       // the brackets sit on two streams
         PMB_CUDA(cudaEventElapsedTime(&ms, f->ev[i][0], f->ev[i][1]));
         if (f->ev_kind[i] == 0) f->lib_ms += ms; else f->xpose_ms += ms;
     }
     f->nev = 0;
     return PMB_OK;
 }
-static int lib_begin(pmb_fft *f, int kind = 0)
+static int lib_begin(pmb_fft *f, int kind = 0, cudaStream_t stream = 0)
 {
     if (f->nev == FFT_NEV) PMB_CHECK(lib_flush(f));
     f->ev_kind[f->nev] = kind;
-    PMB_CUDA(cudaEventRecord(f->ev[f->nev][0], f->ctx->stream));
+    PMB_CUDA(cudaEventRecord(f->ev[f->nev][0], stream ? stream : f->ctx->stream));
     return PMB_OK;
 }
-static int lib_end(pmb_fft *f)
+static int lib_end(pmb_fft *f, cudaStream_t stream = 0)
 {
-    PMB_CUDA(cudaEventRecord(f->ev[f->nev][1], f->ctx->stream));
+    PMB_CUDA(cudaEventRecord(f->ev[f->nev][1], stream ? stream : f->ctx->stream));
     f->nev++;
     return PMB_OK;
 }
@@ -666,14 +678,12 @@ static int xpose_scatter(pmb_fft *f, const void *in, int64_t in_ld, int64_t R, i
     if (octas < 0) { const char *e = getenv("PMB_FFT_OVERLAP_CTAS"); octas = e ? atoi(e) : 4; if (octas < 1) octas = 1; }
     const int64_t cap = (int64_t) f->ctx->sm_count * (own_stream ? octas : 8);
     if (grid > cap) grid = cap;
-    if (!own_stream) PMB_CHECK(lib_begin(f, 1));       // event brackets are taken on the compute stream only
+    PMB_CHECK(lib_begin(f, 1, stream));       // events on the stream the kernel runs on (under other kernels when it is the transpose stream)
     pmb_k_xpose_scatter<C><<<(int) grid, 256, 0, stream>>>((const C *) in, in_ld, R, out_ld, d, ndest, me, s, tr, tc, nbatch, in_bs);
     PMB_LAUNCH_CHECK(f->ctx);
-    if (!own_stream) {
-        PMB_CHECK(lib_end(f));
-        for (int q = 0; q < ndest; q++)
-            if (q != me) f->xpose_remote_bytes += (double) R * (double) d.ncols[q] * (double) nbatch * (double) sizeof(C);
-    }
+    PMB_CHECK(lib_end(f, stream));
+    for (int q = 0; q < ndest; q++)
+        if (q != me) f->xpose_remote_bytes += (double) R * (double) d.ncols[q] * (double) nbatch * (double) sizeof(C);
     return PMB_OK;
 }
 template <typename C>
@@ -853,6 +863,18 @@ static int exec_c2c(pmb_fft *f, cufftHandle h, void *in, void *out, int dir)
     return PMB_OK;
 }
 
+// second, high-priority stream of the plan: transposes that run under cuFFT kernels (pipelined r2c, c2r_multi)
+static int ensure_xstream(pmb_fft *f)
+{
+    if (f->have_xstream) return PMB_OK;
+    int prio_lo = 0, prio_hi = 0;
+    PMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PMB_CUDA(cudaStreamCreateWithPriority(&f->xstream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 16; i++) PMB_CUDA(cudaEventCreateWithFlags(&f->xev[i], cudaEventDisableTiming));
+    f->have_xstream = true;
+    return PMB_OK;
+}
+
 extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scale)
 {
     PMB_REQUIRE(f && real && cplx, "null argument");
@@ -869,6 +891,40 @@ extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scal
         return PMB_OK;
     }
     if (f->P1 > 1) return f->elsize == 8 ? pencil_r2c<double2>(f, real, cplx, scale) : pencil_r2c<float2>(f, real, cplx, scale);
+    static int overlap = -1;
+    if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    if (f->p2p && f->r2c_chunks && overlap) {
+        // Pipelined: the planes go through the 2-D r2c in r2c_chunks batches on the compute stream; the transpose of
+        // every batch (NVLink stores into the owners' landing buffers) runs on the transpose stream under the FFT of
+        // the next batch.  One barrier after the last batch, issued on the transpose stream; the compute stream
+        // waits for it before the lines along axis 0.  Entry: the transpose stream starts after everything the
+        // compute stream has queued so far (the reads of this landing buffer two transforms ago included).
+        PMB_CHECK(ensure_xstream(f));
+        cudaStream_t ms = ctx->stream, xs = f->xstream;
+        const int b = f->xcur;
+        f->xcur ^= 1;
+        const int K = f->r2c_chunks;
+        const int64_t Rc = f->m0 / K;
+        PMB_CUDA(cudaEventRecord(f->xev[12], ms));
+        PMB_CUDA(cudaStreamWaitEvent(xs, f->xev[12], 0));
+        for (int k = 0; k < K; k++) {
+            const char *in = (const char *) real + (size_t) k * Rc * f->n[1] * 2 * f->nc * f->elsize;
+            char *wk = (char *) f->work0 + (size_t) k * Rc * f->n[1] * f->nc * csz;
+            PMB_CHECK(exec_r2c(f, f->slab_r2c_part, in, wk));
+            PMB_CUDA(cudaEventRecord(f->xev[k], ms));
+            PMB_CUDA(cudaStreamWaitEvent(xs, f->xev[k], 0));
+            XDest d;
+            xdest_fwd(f, b, &d);
+            for (int q = 0; q < f->P; q++) d.out[q] = (char *) d.out[q] + (size_t) k * Rc * csz;     // my planes [k Rc, (k + 1) Rc)
+            if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, wk, f->n[1] * f->nc, Rc, f->n[0], d, scale, -1, -1, 1, 0, xs));
+            else PMB_CHECK(xpose_scatter<float2>(f, wk, f->n[1] * f->nc, Rc, f->n[0], d, scale, -1, -1, 1, 0, xs));
+        }
+        PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
+        PMB_CUDA(cudaEventRecord(f->xev[13], xs));
+        PMB_CUDA(cudaStreamWaitEvent(ms, f->xev[13], 0));
+        if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, f->xbuf[b], cplx, CUFFT_FORWARD));
+        return PMB_OK;
+    }
     // 1. local planes: 2-D r2c over (n1, n2):  real (m0, n1, 2nc) -> work0 (m0, n1, nc)
     if (f->m0 > 0) PMB_CHECK(exec_r2c(f, f->slab_r2c, real, f->work0));
     if (f->p2p) {
@@ -963,13 +1019,7 @@ extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, v
         return PMB_OK;
     }
     pmb_ctx *ctx = f->ctx;
-    if (!f->have_xstream) {
-        int prio_lo = 0, prio_hi = 0;
-        PMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        PMB_CUDA(cudaStreamCreateWithPriority(&f->xstream, cudaStreamNonBlocking, prio_hi));
-        for (int i = 0; i < 16; i++) PMB_CUDA(cudaEventCreateWithFlags(&f->xev[i], cudaEventDisableTiming));
-        f->have_xstream = true;
-    }
+    PMB_CHECK(ensure_xstream(f));
     cudaStream_t ms = ctx->stream, xs = f->xstream;
     cudaEvent_t *evL = f->xev, *evS = f->xev + 4, *evP = f->xev + 8, evEntry = f->xev[12], evExit = f->xev[13];
     void *wk[2] = {f->work0, f->work1};
