@@ -370,8 +370,11 @@ extern "C" int pmb_fft_create_np(pmb_ctx *ctx, int ndim, const int64_t *nmesh, i
                                 dbl ? CUFFT_D2Z : CUFFT_R2C, f->m0));
             PMB_CHECK(make_plan(f, &f->slab_c2r, 2, n2, inc, f->n[1] * f->nc, inr, f->n[1] * 2 * f->nc,
                                 dbl ? CUFFT_Z2D : CUFFT_C2R, f->m0));
-            // forward transform in plane chunks: the NVLink transpose of chunk k runs under the 2-D FFT of chunk k + 1
-            int chunks = 4;
+            // forward transform in plane chunks: the NVLink transpose of chunk k runs under the 2-D FFT of chunk k + 1.
+            // Measured at 2 GPUs, 1024^3 (r2c, ms): whole 8.55; 2 chunks 8.09; 4 chunks 10.3 -- the 2-D cuFFT of a
+            // quarter of the planes and a transpose held to 4 CTAs per SM (444 GB/s instead of 589) lose what the overlap
+            // gains.  Off by default (PMB_FFT_CHUNKS=2 selects it).
+            int chunks = 0;
             { const char *e = getenv("PMB_FFT_CHUNKS"); if (e) chunks = atoi(e); }
             if (chunks > 4) chunks = 4;
             f->r2c_chunks = 0;
