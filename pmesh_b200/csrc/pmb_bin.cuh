@@ -39,17 +39,18 @@ struct PmbBinTiling {
     int ntiles;
 };
 
-// tiles of 8 x 8 x 2^PMB_BIN_TZ cells (default 64 along the contiguous axis), doubled along axes 0 / 1 until
-// at most PMB_BIN_TILES (default 262144) cover the canvas.  Measured at 1024^3 uniform random (B200, ms; tiles
+// tiles of 8 x 8 x 2^PMB_BIN_TZ cells (default 32 along the contiguous axis: a tile + halo of three fields is 63 KB
+// of shared memory for the tile kernels of pmb_tile.cuh), doubled along axes 0 / 1 until at most PMB_BIN_TILES
+// (default 2^20) cover the canvas.  Measured at 1024^3 uniform random (B200, ms; tiles
 // 16x16x128 / 8x8x64 / 8x8x32): scatter 24.1 / 24.2 / 25.0, ring gather 23.9 / 21.0 / 19.9, return pass 22.4 each with
 // 12.9 / 14.4 / 31.1 GB of DRAM reads (the read fronts of 2^20 tiles no longer fit in L2)
 static void pmb_bin_tiling(const PmbGeom &g, PmbBinTiling *t)
 {
-    int64_t maxtiles = pmb_env_flag("PMB_BIN_TILES", 262144);
+    int64_t maxtiles = pmb_env_flag("PMB_BIN_TILES", PMB_BIN_HARDTILES);
     if (maxtiles < 64) maxtiles = 64;
     if (maxtiles > PMB_BIN_HARDTILES) maxtiles = PMB_BIN_HARDTILES;
     t->s0 = t->s1 = 3;
-    t->s2 = pmb_env_flag("PMB_BIN_TZ", 6);
+    t->s2 = pmb_env_flag("PMB_BIN_TZ", 5);
     if (t->s2 < 3) t->s2 = 3;
     if (t->s2 > 10) t->s2 = 10;
     for (;;) {
@@ -410,6 +411,8 @@ static int pmb_bin_prepare(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p
     PMB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->bin_hash[0] = hash[0]; ctx->bin_hash[1] = hash[1];
     ctx->bin_state = 1;
+    ctx->bin_tiling[0] = t.s0; ctx->bin_tiling[1] = t.s1; ctx->bin_tiling[2] = t.s2;
+    ctx->bin_tiling[3] = t.n1; ctx->bin_tiling[4] = t.n2; ctx->bin_tiling[5] = t.ntiles;
     ctx->bin_builds++;
     b->pos = (const double *) ctx->bin_pos; b->dest = (const uint32_t *) ctx->bin_dest; b->verdict = 1;
     return PMB_OK;

@@ -76,6 +76,7 @@ struct pmb_ctx {
     int64_t bin_npart;
     uint64_t bin_sig;
     unsigned long long bin_hash[2];   // content hash of the array the copy was made from
+    int bin_tiling[6];       // s0, s1, s2, n1, n2, ntiles of the cached copy
     int bin_state;           // 0: the array's chunks are compact (nothing cached), 1: sorted copy in bin_pos / bin_dest
     int bin_uses;
     int bin_bypass;          // set while the ordinary kernels run on the sorted copy

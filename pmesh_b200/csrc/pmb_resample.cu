@@ -15,6 +15,7 @@
 #include "pmb_ring.cuh"
 #include "pmb_bin.cuh"
 #include "pmb_pull.cuh"
+#include "pmb_tile.cuh"
 
 // ------------------------------------------------------------------ atomic paint
 // L2 residency control: mesh cells are re-touched by particles of neighbouring lattice rows /
@@ -484,7 +485,8 @@ static bool geom32(const pmb_resample_args *a, const PmbGeom &g, PmbGeom32 *g32)
 // IS the sorted copy and the plain kernels serve it); neither: the chunk-scheduled kernels.
 // On the sorted copy (measured at 1024^3 uniform random, B200): the scatter takes the plain kernel with chunk
 // tickets (PMB_BIN_PAINT=2: 46 ms with the algorithmic DRAM traffic; the carry kernels' static chunk stride puts
-// every CTA into a tile of its own: 98 ms, 190 GB of DRAM traffic; 1: grid-stride loop, 0: carry kernels), the
+// every CTA into a tile of its own: 98 ms, 190 GB of DRAM traffic; 1: grid-stride loop, 0: carry kernels; 3, the
+// default for CIC: one CTA per tile with the tile in shared memory, pmb_tile.cuh), the
 // gather takes the bulk-copy ring (PMB_BIN_READOUT=0: 21 ms; 1: plain walk 24 ms).
 static int pmb_traversal(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart, PmbBinned *bn,
                          const uint32_t **perm, bool *walk, bool is_paint)
@@ -543,6 +545,38 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
             const int r = paint_atomic<MeshT>(ctx, &b, g, w, p2);
             ctx->bin_bypass = 0;
             return r;
+        }
+        if (ctx->bin_bypass && pmb_env_flag("PMB_BIN_PAINT", 3) >= 3 && fam == 2 && !(a->order[0] | a->order[1] | a->order[2])
+            && pmb_pos_is_f8_rec4(p) && (!p.mass || (p.mass_elsize == 8 && p.ms == 8))) {
+            // the tile-sorted copy: one CTA per tile, conflict-free deposit into a shared-memory tile (pmb_tile.cuh)
+            PmbGeom32 g32;
+            PmbTileGeom t;
+            t.s[0] = ctx->bin_tiling[0]; t.s[1] = ctx->bin_tiling[1]; t.s[2] = ctx->bin_tiling[2];
+            t.n1 = ctx->bin_tiling[3]; t.n2 = ctx->bin_tiling[4]; t.ntiles = ctx->bin_tiling[5];
+            const size_t nhalo = (size_t) ((1 << t.s[0]) + 1) * ((1 << t.s[1]) + 1) * ((1 << t.s[2]) + 1);
+            const size_t ncells = (size_t) 1 << (t.s[0] + t.s[1] + t.s[2]);
+            const size_t smem = nhalo * sizeof(double) + (2 * ncells + 1) * sizeof(uint32_t) + 2 * PMB_TILE_BATCH * sizeof(uint16_t);
+            if (geom32<MeshT>(a, g, &g32) && ncells <= 16384 && smem <= (size_t) 200 * 1024) {
+                unsigned long long *ticket;
+                PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
+                const uint32_t *counts = (const uint32_t *) ((const char *) ctx->bin_small + 256);
+                const uint32_t *ends = counts + PMB_BIN_HARDTILES;
+                int per_sm = (int) ((size_t) 220 * 1024 / (smem + 1024));
+                if (per_sm > 6) per_sm = 6;
+                if (per_sm < 1) per_sm = 1;
+                const int gridt = (int) (t.ntiles < ctx->sm_count * per_sm ? t.ntiles : ctx->sm_count * per_sm);
+                if (chk) {
+                    PMB_CUDA(cudaFuncSetAttribute(pmb_k_paint_cic_tile<MeshT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    pmb_k_paint_cic_tile<MeshT, true><<<gridt, 256, smem, ctx->stream>>>(g32, t, counts, ends, (const double *) p.pos,
+                        (const double *) p.mass, p.mass_scalar, (MeshT *) mesh, ticket);
+                } else {
+                    PMB_CUDA(cudaFuncSetAttribute(pmb_k_paint_cic_tile<MeshT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    pmb_k_paint_cic_tile<MeshT, false><<<gridt, 256, smem, ctx->stream>>>(g32, t, counts, ends, (const double *) p.pos,
+                        (const double *) p.mass, p.mass_scalar, (MeshT *) mesh, ticket);
+                }
+                PMB_LAUNCH_CHECK(ctx);
+                return PMB_OK;
+            }
         }
         if (walk) {
             const int gridp = pmb_grid(ctx, a->npart, 256, 8);
@@ -825,6 +859,21 @@ extern "C" int pmb_paint(pmb_ctx *ctx, const pmb_resample_args *a)
                  : paint_deterministic<uint64_t, float>(ctx, a, g, w, p);
 }
 
+template <typename MeshT, int NF>
+static int launch_readout_tile(pmb_ctx *ctx, bool chk, int grid, size_t smem, const PmbGeom32 &g32, const PmbTileGeom &t,
+                               const uint32_t *counts, const uint32_t *ends, const double *recs, const PmbFields &f,
+                               unsigned long long *ticket)
+{
+    if (chk) {
+        PMB_CUDA(cudaFuncSetAttribute(pmb_k_readout_cic_tile<MeshT, true, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        pmb_k_readout_cic_tile<MeshT, true, NF><<<grid, 256, smem, ctx->stream>>>(g32, t, counts, ends, recs, f, ticket);
+    } else {
+        PMB_CUDA(cudaFuncSetAttribute(pmb_k_readout_cic_tile<MeshT, false, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        pmb_k_readout_cic_tile<MeshT, false, NF><<<grid, 256, smem, ctx->stream>>>(g32, t, counts, ends, recs, f, ticket);
+    }
+    return PMB_OK;
+}
+
 // CIC gather of nf canvases in one sweep, particle stream through the bulk-copy ring (pmb_ring.cuh)
 template <typename MeshT>
 static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &p, const PmbFields &f, int nf,
@@ -840,6 +889,29 @@ static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &
     const int64_t cap = (int64_t) ctx->sm_count * minb;
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     const double *pos = (const double *) p.pos;
+    if (pmb_pos_is_f8_rec4(p) && ctx->bin_bypass && f.sel1 <= f.sel0 && pmb_env_flag("PMB_BIN_TILE_READOUT", 1)) {
+        // the tile-sorted copy: one CTA per tile, the tile's mesh cells (+ halo) of every field in shared memory (pmb_tile.cuh)
+        PmbTileGeom t;
+        t.s[0] = ctx->bin_tiling[0]; t.s[1] = ctx->bin_tiling[1]; t.s[2] = ctx->bin_tiling[2];
+        t.n1 = ctx->bin_tiling[3]; t.n2 = ctx->bin_tiling[4]; t.ntiles = ctx->bin_tiling[5];
+        const size_t cells = (size_t) ((1 << t.s[0]) + 1) * ((1 << t.s[1]) + 1) * ((1 << t.s[2]) + 1);
+        const size_t smem = cells * sizeof(double) * nf;
+        if (smem <= (size_t) 200 * 1024) {
+            const uint32_t *counts = (const uint32_t *) ((const char *) ctx->bin_small + 256);
+            const uint32_t *ends = counts + PMB_BIN_HARDTILES;
+            // resident CTAs per SM: what shared memory (227 KB) and 2048 threads allow; tiles in flight hide the latency
+            // of a CTA's phases (tile load -> barrier -> particles)
+            int per_sm = (int) ((size_t) 220 * 1024 / (smem + 1024));
+            if (per_sm > 8) per_sm = 8;
+            if (per_sm < 1) per_sm = 1;
+            const int gridt = (int) (t.ntiles < ctx->sm_count * per_sm ? t.ntiles : ctx->sm_count * per_sm);
+            if (nf == 1) PMB_CHECK((launch_readout_tile<MeshT, 1>(ctx, chk, gridt, smem, g32, t, counts, ends, pos, f, ticket)));
+            else if (nf == 2) PMB_CHECK((launch_readout_tile<MeshT, 2>(ctx, chk, gridt, smem, g32, t, counts, ends, pos, f, ticket)));
+            else PMB_CHECK((launch_readout_tile<MeshT, 3>(ctx, chk, gridt, smem, g32, t, counts, ends, pos, f, ticket)));
+            PMB_LAUNCH_CHECK(ctx);
+            return PMB_OK;
+        }
+    }
     if (pmb_pos_is_f8_rec4(p)) {
         // 32-byte records of the tile-sorted copy
 #define PMB_RING_READ4(NFV, MB) PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_ring<MeshT, CHECK, NFV, MB, 4><<<grid, PMB_RING_THREADS, 0, ctx->stream>>>( \
