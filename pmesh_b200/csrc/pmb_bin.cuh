@@ -236,10 +236,11 @@ pmb_k_bin_column(const void *col, int elsize, int64_t stride_bytes, int64_t npar
 }
 
 // results back to the original order: particle i's values are row dest[i] of the (npart, NF) staging array
+// rs: doubles per staging row (NF, or 4 for three fields: the row is then one aligned 32-byte load)
 template <int NF>
 __global__ void __launch_bounds__(256)
 pmb_k_bin_unsort(PmbFields f, const double *__restrict__ tmp, const uint32_t *__restrict__ dest, int64_t npart,
-                 unsigned long long *ticket)
+                 unsigned long long *ticket, int rs)
 {
     constexpr int U = 4;
     __shared__ unsigned long long s_tk[2];
@@ -256,9 +257,15 @@ pmb_k_bin_unsort(PmbFields f, const double *__restrict__ tmp, const uint32_t *__
         for (int u = 0; u < U; u++) {
             const int64_t i = i0 + u * 256;
             if (i < npart) {
-                const double *r = tmp + (int64_t) NF * __ldcs(dest + i);
+                const double *r = tmp + (int64_t) rs * __ldcs(dest + i);
+                if (NF == 3 && rs == 4) {
+                    double pad;
+                    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[u][0]), "=d"(v[u][1]), "=d"(v[u][NF - 1 > 1 ? 2 : 0]), "=d"(pad) : "l"(r));
+                    (void) pad;
+                } else {
 #pragma unroll
-                for (int q = 0; q < NF; q++) v[u][q] = r[q];
+                    for (int q = 0; q < NF; q++) v[u][q] = r[q];
+                }
             }
         }
 #pragma unroll
@@ -433,14 +440,17 @@ static int pmb_bin_column(pmb_ctx *ctx, const PmbBinned &b, const void *col, int
     return PMB_OK;
 }
 
+static inline int pmb_bin_rowwords(int nf) { return nf == 3 ? 4 : nf; }
+
 static int pmb_bin_unsort(pmb_ctx *ctx, const PmbBinned &b, const PmbFields &f, int nf, const double *tmp, int64_t npart)
 {
+    const int rs = pmb_bin_rowwords(nf);
     const int grid = pmb_grid(ctx, npart, 256 * 4, pmb_env_flag("PMB_BIN_UNSORT_CTAS", 6));
     unsigned long long *ticket = (unsigned long long *) ((char *) ctx->bin_small + 64);
     PMB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx->stream));
-    if (nf == 1) pmb_k_bin_unsort<1><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
-    else if (nf == 2) pmb_k_bin_unsort<2><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
-    else pmb_k_bin_unsort<3><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket);
+    if (nf == 1) pmb_k_bin_unsort<1><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket, rs);
+    else if (nf == 2) pmb_k_bin_unsort<2><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket, rs);
+    else pmb_k_bin_unsort<3><<<grid, 256, 0, ctx->stream>>>(f, tmp, b.dest, npart, ticket, rs);
     PMB_LAUNCH_CHECK(ctx);
     return PMB_OK;
 }

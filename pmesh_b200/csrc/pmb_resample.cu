@@ -485,9 +485,12 @@ static bool geom32(const pmb_resample_args *a, const PmbGeom &g, PmbGeom32 *g32)
 // IS the sorted copy and the plain kernels serve it); neither: the chunk-scheduled kernels.
 // On the sorted copy (measured at 1024^3 uniform random, B200): the scatter takes the plain kernel with chunk
 // tickets (PMB_BIN_PAINT=2: 46 ms with the algorithmic DRAM traffic; the carry kernels' static chunk stride puts
-// every CTA into a tile of its own: 98 ms, 190 GB of DRAM traffic; 1: grid-stride loop, 0: carry kernels; 3, the
-// default for CIC: one CTA per tile with the tile in shared memory, pmb_tile.cuh), the
-// gather takes the bulk-copy ring (PMB_BIN_READOUT=0: 21 ms; 1: plain walk 24 ms).
+// every CTA into a tile of its own: 98 ms, 190 GB of DRAM traffic; 1: grid-stride loop, 0: carry kernels; 3: one CTA
+// per tile, conflict-free deposit into a shared-memory tile, pmb_tile.cuh: 41 - 43 ms with 7 x fewer L2 requests -- the
+// serial phases of a tile leave it latency-bound; keeping the particles' weights in shared memory as well costs the
+// resident CTAs that hide that latency: 85 ms), the
+// gather takes the tile kernel of pmb_tile.cuh (12.8 ms one field, 32 ms three; PMB_BIN_TILE_READOUT=0: bulk-copy ring
+// 21 / 69 ms; PMB_BIN_READOUT=1: plain walk 24 ms).
 static int pmb_traversal(pmb_ctx *ctx, const PmbGeom &g, const PmbParticles &p, int64_t npart, PmbBinned *bn,
                          const uint32_t **perm, bool *walk, bool is_paint)
 {
@@ -546,7 +549,7 @@ static int paint_atomic(pmb_ctx *ctx, const pmb_resample_args *a, const PmbGeom 
             ctx->bin_bypass = 0;
             return r;
         }
-        if (ctx->bin_bypass && pmb_env_flag("PMB_BIN_PAINT", 3) >= 3 && fam == 2 && !(a->order[0] | a->order[1] | a->order[2])
+        if (ctx->bin_bypass && pmb_env_flag("PMB_BIN_PAINT", 2) >= 3 && fam == 2 && !(a->order[0] | a->order[1] | a->order[2])
             && pmb_pos_is_f8_rec4(p) && (!p.mass || (p.mass_elsize == 8 && p.ms == 8))) {
             // the tile-sorted copy: one CTA per tile, conflict-free deposit into a shared-memory tile (pmb_tile.cuh)
             PmbGeom32 g32;
@@ -1116,6 +1119,8 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
     memset(&f, 0, sizeof(f));
     for (int q = 0; q < nf; q++) { f.mesh[q] = meshes[q]; f.out[q] = outs[q]; f.out_stride[q] = out_strides[q]; }
     f.out_elsize = a->out_elsize;
+    f.packed_rows = nf == 3 && ctx->bin_bypass && !gf && a->out_elsize == 8 && out_strides[0] == 32 && ((uintptr_t) outs[0] & 31) == 0
+                    && (char *) outs[1] == (char *) outs[0] + 8 && (char *) outs[2] == (char *) outs[0] + 16;
     if (gf) {
         for (int q = 0; q < nf; q++) f.out2[q] = (double *) gf->own_outs[q];
         f.oidx = gf->own_index;
@@ -1126,7 +1131,8 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
     PmbBinned bn;
     bool walk;
     PMB_CHECK(pmb_traversal(ctx, g, p, a->npart, &bn, &perm, &walk, false));
-    double *stage = bn.pos ? (double *) pmb_bin_try_scratch(ctx, sizeof(double) * (size_t) nf * (size_t) a->npart) : NULL;
+    const int rs = pmb_bin_rowwords(nf);
+    double *stage = bn.pos ? (double *) pmb_bin_try_scratch(ctx, sizeof(double) * (size_t) rs * (size_t) a->npart) : NULL;
     if (bn.pos && !stage) {
         PMB_CHECK(pmb_perm_prepare(ctx, g, p, a->npart, &perm));
         walk = perm != NULL;
@@ -1139,7 +1145,7 @@ static int readout_multi_impl(pmb_ctx *ctx, const pmb_resample_args *a, int nf, 
         b.out_elsize = 8;
         void *outs2[3];
         int64_t strides2[3];
-        for (int q = 0; q < nf; q++) { outs2[q] = stage + q; strides2[q] = (int64_t) sizeof(double) * nf; }
+        for (int q = 0; q < nf; q++) { outs2[q] = stage + q; strides2[q] = (int64_t) sizeof(double) * rs; }
         ctx->bin_bypass = 1;
         const int r = readout_multi_impl<MeshT>(ctx, &b, nf, meshes, outs2, strides2, done, NULL);
         ctx->bin_bypass = 0;

@@ -60,6 +60,9 @@ struct PmbFields {
     double *out2[3];
     const int32_t *oidx;
     int64_t sel0, sel1;
+    // staging rows of the tile-sorted copy (pmb_bin.cuh): out[q] = row + q, rows of 4 doubles (32 bytes) for three
+    // fields -- a kernel that has the three values of a particle at hand writes / reads the row as ONE 32-byte access
+    int packed_rows;
 };
 
 // where the result of particle j for field q goes (see PmbFields)

@@ -106,6 +106,7 @@ pmb_k_readout_cic_tile(PmbGeom32 g, PmbTileGeom t, const uint32_t *__restrict__ 
                 for (int b = 0; b < 2; b++)
 #pragma unroll
                     for (int c = 0; c < 2; c++) w[a][b][c] = (Vx[a] * Vy[b]) * Vz[c];
+            double res[NF];
 #pragma unroll
             for (int q = 0; q < NF; q++) {
                 double value = 0;
@@ -128,7 +129,14 @@ pmb_k_readout_cic_tile(PmbGeom32 g, PmbTileGeom t, const uint32_t *__restrict__ 
                                 if (ok) value += pmb_mesh_load<MeshT, false>((const char *) f.mesh[q], (int64_t) (ex[a] + ey[b] + ez[c]) * sizeof(MeshT), policy) * w[a][b][c];
                             }
                 }
-                pmb_store_result(f, q, j, value);
+                res[q] = value;
+            }
+            if (NF == 3 && f.packed_rows) {
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"((double *) f.out[0] + 4 * j), "d"(res[0]), "d"(res[1]),
+                             "d"(res[NF - 1 > 1 ? 2 : 0]), "d"(0.0) : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < NF; q++) pmb_store_result(f, q, j, res[q]);
             }
         }
     }
