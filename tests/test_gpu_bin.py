@@ -126,7 +126,7 @@ def test_three_fields_in_one_sweep_on_the_sorted_copy(W, oracle):
                 assert_array_equal(o.to_host(), oracle.readout(f, pos, "cic", translate=translate, period=[N] * 3))
 
 
-@pytest.mark.parametrize("switch", ["PMB_BIN=0", "PMB_BIN=2", "PMB_BIN_PAINT=0", "PMB_BIN_PAINT=1", "PMB_BIN_READOUT=1", "PMB_BIN_TILES=4096", "PMB_BIN_TILE_READOUT=0", "PMB_BIN_TZ=4", "PMB_BIN_PAINT=3", "PMB_BIN_TZ=7"])
+@pytest.mark.parametrize("switch", ["PMB_BIN=0", "PMB_BIN=2", "PMB_BIN_PAINT=0", "PMB_BIN_PAINT=1", "PMB_BIN_READOUT=1", "PMB_BIN_TILES=4096", "PMB_BIN_TILE_READOUT=0", "PMB_BIN_TZ=4", "PMB_BIN_PAINT=3", "PMB_BIN_PAINT=2", "PMB_BIN_TZ=7"])
 def test_switches(W, oracle, switch):
     """PMB_BIN=0: permutation walk; PMB_BIN=2: lattice-ordered arrays are reordered too; PMB_BIN_PAINT / _READOUT:
     which kernels run on the sorted copy; PMB_BIN_TILES: coarser tiles.  Same results."""
