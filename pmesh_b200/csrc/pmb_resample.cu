@@ -924,8 +924,20 @@ static int readout_ring(pmb_ctx *ctx, const PmbGeom32 &g32, const PmbParticles &
         PMB_LAUNCH_CHECK(ctx);
         return PMB_OK;
     }
+    // PMB_RING_SCHED=1: chunks in the order of the spatial schedule (the cell of a chunk's middle particle) instead of
+    // memory order -- for particles displaced by several cells the mesh rows in flight then stay in L2
+    const uint32_t *order = NULL;
+    if (pmb_env_flag("PMB_RING_SCHED", nf >= 2 ? 1 : 0) && !ctx->bin_bypass) {
+        int64_t nch2;
+        PmbGeom gg;
+        memset(&gg, 0, sizeof(gg));
+        gg.ndim = 3;
+        for (int d = 0; d < 3; d++) { gg.scale[d] = g32.scale[d]; gg.translate[d] = g32.translate[d]; gg.period[d] = g32.period[d]; gg.size[d] = g32.size[d]; }
+        PMB_CHECK(pmb_sched_prepare(ctx, gg, p, npart, &order, &nch2, 1));      // the scatter's schedule: built once per array
+        PMB_CHECK(pmb_sched_ticket(ctx, &ticket));
+    }
 #define PMB_RING_READ(NFV, MB) PMB_DISPATCH_CHECK(chk, (pmb_k_readout_cic32_ring<MeshT, CHECK, NFV, MB><<<grid, PMB_RING_THREADS, 0, ctx->stream>>>( \
-        g32, pos, f, npart, nchunks, ticket)))
+        g32, pos, f, npart, nchunks, ticket, order)))
     if (nf == 1) {
         if (minb <= 4) { PMB_RING_READ(1, 4); } else if (minb == 5) { PMB_RING_READ(1, 5); } else { PMB_RING_READ(1, 6); }
     } else if (nf == 2) {

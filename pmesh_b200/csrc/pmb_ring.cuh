@@ -84,7 +84,7 @@ __device__ __forceinline__ void pmb_store_result(const PmbFields &f, int q, int6
 template <typename MeshT, bool CHECK, int NF, int MINB, int RW = 3>
 __global__ void __launch_bounds__(PMB_RING_THREADS, MINB)
 pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields f, int64_t npart,
-                         int64_t nchunks, unsigned long long *ticket)
+                         int64_t nchunks, unsigned long long *ticket, const uint32_t *__restrict__ order = NULL)
 {
     __shared__ __align__(128) PmbRingSmem<RW> sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,8 +106,10 @@ pmb_k_readout_cic32_ring(PmbGeom32 g, const double *__restrict__ pos, PmbFields 
                     pmb_mbar_arrive(&sm.full[s]);
                     break;
                 }
-                sm.chunk[s] = (long long) tk;
-                pmb_ring_fill(sm, s, pos, (int64_t) tk, npart, pol);
+                // `order`: the spatial schedule of the chunks (pmb_sched_prepare) instead of memory order
+                const int64_t c = order ? (int64_t) order[tk] : (int64_t) tk;
+                sm.chunk[s] = (long long) c;
+                pmb_ring_fill(sm, s, pos, c, npart, pol);
             }
         }
         return;
