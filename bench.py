@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused", action="store_true",
+                    help="transfer pass + cuFFT for all three axes of the backward transforms (the path before pmb_ifft.cuh)")
     ap.add_argument("--e2e-double", action="store_true", help="e2e: upload || compute || download with two position buffers")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=256,
@@ -183,6 +185,8 @@ class ForceStep(object):
         self.rho = pm.create("real")
         self.rhok = pm.create("complex")
         self.tmp = [pm.create("complex") for d in range(3)]
+        from pmesh_b200.pm import RealField
+        self.treal = [RealField(pm, t._base) for t in self.tmp]
         self.tf = [T.GravityFD4(d) for d in range(3)]
         self.stage = {}
 
@@ -208,11 +212,16 @@ class ForceStep(object):
         self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
         self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
         self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
-        from pmesh_b200.pm import apply_gradients, c2r_fields, readout_fields
-        # the three gravity transfers read the density modes once (pm.apply_gradients) ...
-        self._t("transfer", lambda: apply_gradients(self.rhok, self.tf, outs=self.tmp))
-        # ... the three backward transforms overlap their NVLink transposes with each other's local FFTs
-        real = self._t("c2r", lambda: c2r_fields(self.tmp, outs=[Ellipsis] * 3))
+        from pmesh_b200.pm import apply_gradients, c2r_fields, gradient_fields, readout_fields
+        if self.args.unfused:
+            # the three gravity transfers read the density modes once (pm.apply_gradients) ...
+            self._t("transfer", lambda: apply_gradients(self.rhok, self.tf, outs=self.tmp))
+            # ... the three backward transforms overlap their NVLink transposes with each other's local FFTs
+            real = self._t("c2r", lambda: c2r_fields(self.tmp, outs=[Ellipsis] * 3))
+        else:
+            # the gravity transfers are folded into the first (axis-0) pass of the three backward transforms, this
+            # library's own kernel (pmb_ifft.cuh); cuFFT does the remaining 2-D c2r over the planes
+            real = self._t("transfer+c2r", lambda: gradient_fields(self.rhok, self.tf, outs=self.treal))
         # the three force fields are read in ONE sweep over the particles (shared positions / weights)
         # ... and the ghost sum is fused into it: F[d] = layout.gather(real[d].readout(lpos)), nbody.py:214-216
         Fn = self._t("readout+gather", lambda: readout_fields(real, lpos, gather=layout))
@@ -230,6 +239,25 @@ def _strided_sum(ctx, a):
     st = (ctypes.c_int64 * 3)(*a.strides)
     _lib.check(ctx.lib.pmb_field_sum(ctx.handle, a.ptr, a.dtype.itemsize, len(a.shape), sz, st, ctypes.byref(out)))
     return out.value
+
+
+def fused_block(pm, ms, launches, args, peak):
+    """the transfer + axis-0 inverse transform kernel of this library (pmb_k_ifft_grad): CUDA-event time per launch and
+    its algorithmic bytes -- the local complex cells are read once (16 B at f8) and written once per direction"""
+    if not launches:
+        return None
+    lay = pm._layout
+    ncell = int(numpy.prod(lay['o_shape']))
+    csz = 2 * pm.dtype.itemsize
+    per_step = launches / float(args.steps)
+    ndir = 3.0 / per_step                      # directions served by one launch (3 on one rank, 1 on slabs)
+    nbytes = ncell * csz * (1 + ndir)
+    ms_launch = ms / launches
+    gbs = nbytes / (ms_launch * 1e-3) / 1e9
+    return {"kernel": "pmb_k_ifft_grad", "launches_per_step": per_step, "ms_per_launch": round(ms_launch, 3),
+            "algorithmic_gb_per_launch": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
+            "frac_of_hbm_peak": round(gbs / peak, 4),
+            "replaces": "pmb_k_transfer_grad3 (64 B per complex cell) + the axis-0 pass of cuFFT in each of the three c2r (96 B)"}
 
 
 def kernel_names(args, nl):
@@ -411,6 +439,7 @@ def run_ours(args):
     ctx.launch_count(reset=True)
     pm.fft_library_ms(reset=True)
     pm.fft_transpose_stats(reset=True)
+    pm.fft_fused_stats(reset=True)
     ctx.timer_start(0)
     for _ in range(args.steps):
         step(X, ntot, F)
@@ -420,6 +449,7 @@ def run_ours(args):
     launches = ctx.launch_count()
     fft_ms = pm.fft_library_ms()
     xp_ms, xp_bytes = pm.fft_transpose_stats()
+    fu_ms, fu_n = pm.fft_fused_stats()
     clk = clocks.stop()
     ms_step = comm.allreduce(ms / args.steps, op=C.MAX)
     fft_step = comm.allreduce(fft_ms / args.steps, op=C.MAX)
@@ -634,6 +664,7 @@ def run_ours(args):
                 "ms_per_step": round(xp_ms / args.steps, 3), "nvlink_gb_per_step": round(xp_bytes / args.steps / 1e9, 3),
                 "nvlink_gbs_achieved": round(xp_bytes / max(xp_ms, 1e-9) / 1e6, 1), "nvlink_gbs_peak_measured": 770.0,
                 "note": "rank 0: bytes the fused transpose kernels stored into peer memory / their CUDA-event time"},
+            "fused_transfer_ifft": fused_block(pm, fu_ms, fu_n, args, peak),
             "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "inputs": inputs, "e2e": e2e, "cpu_baseline": cpu,
             "verify": verify,

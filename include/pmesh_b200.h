@@ -329,6 +329,19 @@ int pmb_transfer_scaled(pmb_fft *plan, int kind, int dir, const double *params_h
 int pmb_transfer_grad3(pmb_fft *plan, int kind, const double *boxsize_h, double prefactor, const void *in,
                        void *const *outs_h);
 
+/* The three backward transforms of a force evaluation with the gradient transfers FUSED into their first pass:
+ * reals_h[d] = c2r(prefactor * i m_d(k_d) / k^2 * in), d = 0, 1, 2 -- what
+ * `[rhok.apply(T_d).c2r() for d in range(3)]` computes (pm.py:617-648 apply, 987-1019 c2r; examples/nbody.py:162-170,
+ * 211-213), equal to pmb_transfer_grad3 + pmb_fft_c2r_multi to rounding (the axis-0 transform is this library's own
+ * kernel, pmb_ifft.cuh, instead of cuFFT: the density modes are multiplied on load, no transfer pass, no separate
+ * axis-0 pass).  Axis 0 a power of two in 64 .. 4096 on one rank or slabs; anything else runs the two calls above.
+ * `in` is preserved and must not be one of the outputs; reals_h[d] are real-field buffers (their in-place complex
+ * partners are used as work space). */
+int pmb_fft_c2r_grad3(pmb_fft *plan, int kind, const double *boxsize_h, double prefactor, const void *in,
+                      void *const *reals_h);
+/* milliseconds inside the fused transfer + line-transform kernels and their number since the last reset */
+int pmb_fft_fused_stats(pmb_fft *plan, float *ms, int64_t *launches, int reset);
+
 /* result_h[0..1] = (re, im) of sum over the LOCAL stored half-complex modes of conj(b) * a * w, w = 2 for
  * modes that stand for themselves and their Hermitian conjugate (0 < k_last < N/2), else 1 -- the rank-local
  * term of ComplexField.cdot / cnorm (pm.py:911-974, default metric and norm); float64 accumulation. */

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "pmb_internal.h"
+#include "pmb_ifft.cuh"
 
 #define FFT_NEV 32
 
@@ -53,7 +54,7 @@ struct pmb_fft {
     void *peer_x[64][2];          // the same buffers of every rank, mapped into this process
     void *pool;                   // the pool entry that owns them
     cudaEvent_t ev[FFT_NEV][2];
-    int ev_kind[FFT_NEV];         // 0: a cuFFT exec (library time), 1: a transpose kernel of this library
+    int ev_kind[FFT_NEV];         // 0: a cuFFT exec (library time), 1: a transpose kernel of this library, 2: the fused transfer + line transform
     int nev;
     float lib_ms;
     // second stream for the transposes of pmb_fft_c2r_multi (NVLink stores overlap the cuFFT of the other transforms)
@@ -66,6 +67,13 @@ struct pmb_fft {
     // (kind, direction, box, parameters): the force step applies the same few transfers every step
     struct TfCache { int kind, dir; double box[3], p[2]; void *dev; } tfc[8];
     int ntfc;
+    // transfer + axis-0 inverse transform in one kernel (pmb_ifft.cuh): twiddle table, the 2-D c2r over all planes of
+    // one rank (P == 1; P > 1 uses slab_c2r), time inside the fused kernel
+    void *ifft_tw;
+    cufftHandle plane_c2r;
+    bool have_plane;
+    float ifft_ms;
+    int64_t ifft_launches;
 };
 
 // cached tables or NULL
@@ -419,6 +427,8 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
     }
     p2p_teardown(f);
     for (int i = 0; i < f->ntfc; i++) cudaFree(f->tfc[i].dev);
+    if (f->ifft_tw) cudaFree(f->ifft_tw);
+    if (f->have_plane) cufftDestroy(f->plane_c2r);
     if (f->have_xstream) {
         cudaStreamSynchronize(f->xstream);
         cudaStreamDestroy(f->xstream);
@@ -470,7 +480,7 @@ static int lib_flush(pmb_fft *f)
         float ms = 0;
         PMB_CUDA(cudaEventSynchronize(f->ev[i][1]));       // the brackets sit on two streams
         PMB_CUDA(cudaEventElapsedTime(&ms, f->ev[i][0], f->ev[i][1]));
-        if (f->ev_kind[i] == 0) f->lib_ms += ms; else f->xpose_ms += ms;
+        if (f->ev_kind[i] == 0) f->lib_ms += ms; else if (f->ev_kind[i] == 1) f->xpose_ms += ms; else f->ifft_ms += ms;
     }
     f->nev = 0;
     return PMB_OK;
@@ -963,6 +973,9 @@ extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scal
 }
 
 static int c2r_from_work(pmb_fft *f, void *real);
+static int slab_c2r_after_lines(pmb_fft *f, void *real);
+struct PmbIfftArgs;
+static int ifft_launch(pmb_fft *f, const PmbIfftArgs &a, cudaStream_t stream);
 
 extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
 {
@@ -979,6 +992,13 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
     if (f->P1 > 1) return f->elsize == 8 ? pencil_c2r<double2>(f, cplx, real) : pencil_c2r<float2>(f, cplx, real);
     // 1. inverse lines along axis 0: cplx (m1*nc, n0) -> work0 (input preserved)
     if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx, f->work0, CUFFT_INVERSE));
+    return slab_c2r_after_lines(f, real);
+}
+
+// slabs: work0 holds the axis-0 inverse-transformed lines (m1*nc, n0)
+static int slab_c2r_after_lines(pmb_fft *f, void *real)
+{
+    pmb_ctx *ctx = f->ctx;
     if (f->p2p) {
         // 2. transpose straight into the (m0_p, n1, nc) plane layout of every owner p, 3. barrier,
         // 4. 2-D c2r of my planes out of the landing buffer
@@ -1011,14 +1031,36 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
 // - S_d (d >= 2) reuses the landing buffer of transform d - 2: it waits for P_{d-2} here AND, through the
 //   extra barrier, on every other rank;  L_{d+2} reuses the work buffer of S_d: it follows wait(S_d);
 // - the exit barrier: every rank has finished its last P before a later transform may store into it.
+static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *const *real_h, PmbIfftArgs *fused);
+
 extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, void *const *real_h)
 {
     PMB_REQUIRE(f && cplx_h && real_h && n >= 1 && n <= 4, "bad arguments");
     for (int d = 0; d < n; d++) PMB_REQUIRE(cplx_h[d] && real_h[d], "null field %d", d);
+    return c2r_multi_impl(f, n, cplx_h, real_h, NULL);
+}
+
+// fused != NULL (slabs, n == 3): the lines of transform d come from the fused transfer + line transform of the common
+// input (pmb_ifft.cuh) instead of cuFFT on cplx_h[d] (which is then not read)
+static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *const *real_h, PmbIfftArgs *fused)
+{
     static int overlap = -1;
     if (overlap < 0) { const char *e = getenv("PMB_FFT_OVERLAP"); overlap = e ? atoi(e) : 1; }
+    auto fused_lines = [&](int d, void *dst) -> int {
+        PmbIfftArgs a = *fused;
+        a.ntr = 1;
+        a.tr[0].axis0mul = d == 0; a.tr[0].nout = 1; a.tr[0].out[0] = dst; a.tr[0].linemul[0] = d;
+        return ifft_launch(f, a, f->ctx->stream);
+    };
     if (!(f->P > 1 && f->P1 == 1 && f->p2p && n >= 2 && overlap && f->work1)) {
-        for (int d = 0; d < n; d++) PMB_CHECK(pmb_fft_c2r(f, cplx_h[d], real_h[d]));
+        for (int d = 0; d < n; d++) {
+            if (fused) {
+                if (f->m1 > 0) PMB_CHECK(fused_lines(d, f->work0));
+                PMB_CHECK(slab_c2r_after_lines(f, real_h[d]));
+            } else {
+                PMB_CHECK(pmb_fft_c2r(f, cplx_h[d], real_h[d]));
+            }
+        }
         return PMB_OK;
     }
     pmb_ctx *ctx = f->ctx;
@@ -1033,7 +1075,10 @@ extern "C" int pmb_fft_c2r_multi(pmb_fft *f, int n, const void *const *cplx_h, v
     PMB_CUDA(cudaStreamWaitEvent(xs, evEntry, 0));
     PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
     auto line = [&](int d) -> int {          // L_d on the compute stream
-        if (f->m1 > 0) PMB_CHECK(exec_c2c(f, f->line, (void *) cplx_h[d], wk[d & 1], CUFFT_INVERSE));
+        if (f->m1 > 0) {
+            if (fused) PMB_CHECK(fused_lines(d, wk[d & 1]));
+            else PMB_CHECK(exec_c2c(f, f->line, (void *) cplx_h[d], wk[d & 1], CUFFT_INVERSE));
+        }
         PMB_CUDA(cudaEventRecord(evL[d], ms));
         return PMB_OK;
     };
@@ -1239,17 +1284,14 @@ pmb_k_transfer_grad3(const C *__restrict__ in, C *__restrict__ o0, C *__restrict
     }
 }
 
-extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
-                                  void *const *outs_h)
+// wavenumbers (3 axes) | gradient multipliers (3 axes) of the two gradient transfers, cached on the plan
+static int grad3_tables(pmb_fft *f, int kind, const double *boxsize_h, void **out)
 {
-    PMB_REQUIRE(f && boxsize_h && in && outs_h && outs_h[0] && outs_h[1] && outs_h[2], "null argument");
-    PMB_REQUIRE(kind == PMB_TF_GRAVITY_FD4 || kind == PMB_TF_GRADIENT_K, "grad3 serves the two gradient transfers");
-    PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
-    pmb_ctx *ctx = f->ctx;
     const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
     int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
     void *dev = tf_cache_find(f, kind, -3, boxsize_h, 0.0, 0.0);
     if (!dev) {
+
         double *h = (double *) malloc(sizeof(double) * 2 * ntab);
         if (!h) return PMB_ENOMEM;
         double *m = h + ntab;
@@ -1269,6 +1311,21 @@ extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h,
         free(h);
         if (rc != PMB_OK) return rc;
     }
+    *out = dev;
+    return PMB_OK;
+}
+
+extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
+                                  void *const *outs_h)
+{
+    PMB_REQUIRE(f && boxsize_h && in && outs_h && outs_h[0] && outs_h[1] && outs_h[2], "null argument");
+    PMB_REQUIRE(kind == PMB_TF_GRAVITY_FD4 || kind == PMB_TF_GRADIENT_K, "grad3 serves the two gradient transfers");
+    PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
+    pmb_ctx *ctx = f->ctx;
+    const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
+    int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
+    void *dev = NULL;
+    PMB_CHECK(grad3_tables(f, kind, boxsize_h, &dev));
     TfArgs a;
     memset(&a, 0, sizeof(a));
     a.kind = kind; a.ndim = 3; a.P = f->P;
@@ -1290,6 +1347,170 @@ extern "C" int pmb_transfer_grad3(pmb_fft *f, int kind, const double *boxsize_h,
         pmb_k_transfer_grad3<float2><<<(int) grid, 256, 0, ctx->stream>>>((const float2 *) in, (float2 *) outs_h[0], (float2 *) outs_h[1],
                                                                           (float2 *) outs_h[2], nrows, rowlen, a);
     PMB_LAUNCH_CHECK(ctx);
+    return PMB_OK;
+}
+
+// ---- the three backward transforms of a force evaluation with the transfers fused into their first pass -----------
+template <typename C, int N, bool CONTIG, bool WIDE = true>
+static int ifft_launch_n(pmb_fft *f, const PmbIfftArgs &a, cudaStream_t stream)
+{
+    constexpr int B = pmb_ifft_bundle<C, N, CONTIG, WIDE>::B;
+    typedef pmb_ifft_line<C, N, CONTIG, B> F;
+    constexpr int threads = B * (N / 16);
+    constexpr int MINB = threads <= 256 ? 2 : 1;
+    auto kern = pmb_k_ifft_grad<C, N, CONTIG, B, MINB>;
+    const size_t smem = (size_t) F::SMEM_ELEMS * sizeof(C) + pmb_ifft_tables<C, N>::BYTES;
+    static int occ = 0;      // per instantiation; one device per process
+    if (occ == 0) {
+        PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int o = 0;
+        PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem));
+        if (o < 1) { pmb_set_error("fused line transform of %d points does not fit on an SM", N); return PMB_EUNSUPPORTED; }
+        const char *e = getenv("PMB_IFFT_CTAS");
+        if (e && atoi(e) > 0 && atoi(e) < o) o = atoi(e);
+        occ = o;
+    }
+    const int64_t nbundles = (a.nlines + B - 1) / B;
+    if (nbundles == 0) return PMB_OK;
+    int64_t grid = (int64_t) f->ctx->sm_count * occ;
+    if (grid > nbundles) grid = nbundles;
+    PMB_CHECK(lib_begin(f, 2, stream));
+    kern<<<(int) grid, threads, smem, stream>>>(a);
+    PMB_CHECK(lib_end(f, stream));
+    f->ifft_launches++;
+    PMB_LAUNCH_CHECK(f->ctx);
+    return PMB_OK;
+}
+
+template <typename C, bool CONTIG>
+static int ifft_launch_c(pmb_fft *f, const PmbIfftArgs &a, cudaStream_t stream)
+{
+    switch (f->n[0]) {
+    case 64: return ifft_launch_n<C, 64, CONTIG>(f, a, stream);
+    case 128: return ifft_launch_n<C, 128, CONTIG>(f, a, stream);
+    case 256: return ifft_launch_n<C, 256, CONTIG>(f, a, stream);
+    case 512: return ifft_launch_n<C, 512, CONTIG>(f, a, stream);
+    case 1024: {
+        static int narrow = -1;
+        if (narrow < 0) { const char *e = getenv("PMB_IFFT_NARROW"); narrow = e ? atoi(e) : 0; }
+        if (!CONTIG && narrow) return ifft_launch_n<C, 1024, CONTIG, false>(f, a, stream);
+        return ifft_launch_n<C, 1024, CONTIG>(f, a, stream);
+    }
+    case 2048: return ifft_launch_n<C, 2048, CONTIG>(f, a, stream);
+    case 4096: return ifft_launch_n<C, 4096, CONTIG>(f, a, stream);
+    }
+    pmb_set_error("fused line transform: unsupported length %lld", (long long) f->n[0]);
+    return PMB_EUNSUPPORTED;
+}
+
+static int ifft_launch(pmb_fft *f, const PmbIfftArgs &a, cudaStream_t stream)
+{
+    if (f->elsize == 8) return f->P == 1 ? ifft_launch_c<double2, false>(f, a, stream) : ifft_launch_c<double2, true>(f, a, stream);
+    return f->P == 1 ? ifft_launch_c<float2, false>(f, a, stream) : ifft_launch_c<float2, true>(f, a, stream);
+}
+
+static bool ifft_supported(const pmb_fft *f, const double *box)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("PMB_IFFT"); on = e ? atoi(e) : 1; }
+    if (!on || f->ndim != 3 || f->P1 != 1) return false;
+    const int64_t n = f->n[0];
+    if (!(n >= 64 && n <= 4096 && (n & (n - 1)) == 0)) return false;
+    // the kernel's reciprocal of k^2 has no special cases: every k^2 of the mesh must be an ordinary number
+    double lo = 1e300, hi = 0;
+    for (int d = 0; d < 3; d++) {
+        if (!(box[d] > 0)) return false;
+        const double k1 = 2 * 3.141592653589793 / box[d], kn = k1 * (double) (f->n[d] / 2 + 1);
+        if (f->n[d] > 1 && k1 * k1 < lo) lo = k1 * k1;
+        hi += kn * kn;
+    }
+    return lo > 1e-280 && hi < 1e280 && hi == hi;
+}
+
+// twiddles exp(+2 pi i k / n0) in the field's precision, once per plan
+static int ifft_twiddles(pmb_fft *f)
+{
+    if (f->ifft_tw) return PMB_OK;
+    const int64_t n = f->n[0];
+    const size_t csz = 2 * (size_t) f->elsize;
+    void *h = malloc(csz * (size_t) n);
+    if (!h) return PMB_ENOMEM;
+    for (int64_t k = 0; k < n; k++) {
+        // exact symmetries of the circle: octant reduction keeps cos / sin of the table consistent to the last bit
+        const double ang = 2 * 3.14159265358979323846 * (double) k / (double) n;
+        const double c = cos(ang), sn = sin(ang);
+        if (f->elsize == 8) { ((double *) h)[2 * k] = c; ((double *) h)[2 * k + 1] = sn; }
+        else { ((float *) h)[2 * k] = (float) c; ((float *) h)[2 * k + 1] = (float) sn; }
+    }
+    cudaError_t e = cudaMalloc(&f->ifft_tw, csz * (size_t) n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->ifft_tw, h, csz * (size_t) n, cudaMemcpyHostToDevice, f->ctx->stream);   // pageable: staged before return
+    free(h);
+    if (e != cudaSuccess) { if (f->ifft_tw) { cudaFree(f->ifft_tw); f->ifft_tw = NULL; } return pmb_cuda_fail(e, "twiddle table", __FILE__, __LINE__); }
+    return PMB_OK;
+}
+
+extern "C" int pmb_fft_c2r_grad3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
+                                 void *const *reals_h)
+{
+    PMB_REQUIRE(f && boxsize_h && in && reals_h && reals_h[0] && reals_h[1] && reals_h[2], "null argument");
+    PMB_REQUIRE(kind == PMB_TF_GRAVITY_FD4 || kind == PMB_TF_GRADIENT_K, "grad3 serves the two gradient transfers");
+    PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
+    for (int d = 0; d < 3; d++) {
+        PMB_REQUIRE(reals_h[d] != in, "the input modes must not be one of the outputs");
+        for (int e = 0; e < d; e++) PMB_REQUIRE(reals_h[d] != reals_h[e], "outputs %d and %d are the same buffer", e, d);
+    }
+    if (!ifft_supported(f, boxsize_h)) {
+        // three transfers in one pass into the outputs' in-place complex partners, then the transforms in place
+        PMB_CHECK(pmb_transfer_grad3(f, kind, boxsize_h, prefactor, in, reals_h));
+        const void *c[3] = {reals_h[0], reals_h[1], reals_h[2]};
+        return pmb_fft_c2r_multi(f, 3, c, reals_h);
+    }
+    void *dev = NULL;
+    PMB_CHECK(grad3_tables(f, kind, boxsize_h, &dev));
+    PMB_CHECK(ifft_twiddles(f));
+    const int64_t ntab = f->n[0] + f->n[1] + f->n[2];
+    const int64_t off[3] = {0, f->n[0], f->n[0] + f->n[1]};
+    PmbIfftArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in;
+    a.P = f->P;
+    a.nc = f->nc; a.s1 = f->s1; a.mc = f->mc; a.s2 = f->s2;
+    for (int d = 0; d < 3; d++) { a.ktab[d] = (const double *) dev + off[d]; a.mtab[d] = (const double *) dev + ntab + off[d]; }
+    a.tw = f->ifft_tw;
+    a.pre = prefactor;
+    if (f->P == 1) {
+        if (!f->have_plane) {
+            long long n2[2] = {f->n[1], f->n[2]};
+            long long inr[2] = {f->n[1], 2 * f->nc};
+            long long inc[2] = {f->n[1], f->nc};
+            PMB_CHECK(make_plan(f, &f->plane_c2r, 2, n2, inc, f->n[1] * f->nc, inr, f->n[1] * 2 * f->nc,
+                                f->elsize == 8 ? CUFFT_Z2D : CUFFT_C2R, f->n[0]));
+            f->have_plane = true;
+        }
+        a.nlines = f->n[1] * f->nc;
+        // direction 0 has a multiplier that varies along the line; directions 1 and 2 are the SAME transform times a
+        // constant of the line: two transforms, three outputs
+        a.ntr = 2;
+        a.tr[0].axis0mul = 1; a.tr[0].nout = 1; a.tr[0].out[0] = reals_h[0]; a.tr[0].linemul[0] = 0;
+        a.tr[1].axis0mul = 0; a.tr[1].nout = 2; a.tr[1].out[0] = reals_h[1]; a.tr[1].linemul[0] = 1;
+        a.tr[1].out[1] = reals_h[2]; a.tr[1].linemul[1] = 2;
+        PMB_CHECK(ifft_launch(f, a, f->ctx->stream));
+        for (int d = 0; d < 3; d++) PMB_CHECK(exec_c2r(f, f->plane_c2r, reals_h[d], reals_h[d]));
+        return PMB_OK;
+    }
+    a.nlines = f->m1 * f->mc;
+    const void *c[3] = {in, in, in};
+    return c2r_multi_impl(f, 3, c, reals_h, &a);
+}
+
+// time inside the fused transfer + line transform kernels and their number since the last reset
+extern "C" int pmb_fft_fused_stats(pmb_fft *f, float *ms, int64_t *launches, int reset)
+{
+    PMB_REQUIRE(f && ms && launches, "null argument");
+    PMB_CHECK(lib_flush(f));
+    *ms = f->ifft_ms;
+    *launches = f->ifft_launches;
+    if (reset) { f->ifft_ms = 0; f->ifft_launches = 0; }
     return PMB_OK;
 }
 

@@ -77,8 +77,9 @@ def force(pm, Q, S=None, factor=1.0):
     rhok = rho.r2c(out=Ellipsis)
     # the ndim force fields are kept side by side so that ONE sweep over the particles reads them all
     # (pm.readout_fields): positions, cell indices and weights are shared by the components
-    from .pm import apply_gradients, c2r_fields, readout_fields
-    f = c2r_fields(apply_gradients(rhok, [force_transfer(d) for d in range(pm.ndim)]), outs=[Ellipsis] * pm.ndim)
+    # ... and the transfers are folded into the first pass of the backward transforms (pm.gradient_fields)
+    from .pm import gradient_fields, readout_fields
+    f = gradient_fields(rhok, [force_transfer(d) for d in range(pm.ndim)])
     return readout_fields(f, lpos, gather=layout)
 
 

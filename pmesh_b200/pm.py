@@ -865,6 +865,37 @@ def apply_gradients(field, transfers, outs=None):
     return list(outs)
 
 
+def gradient_fields(field, transfers, outs=None):
+    """
+    ``[field.apply(t).c2r(out=o) for t, o in zip(transfers, outs)]`` for the three gradient transfers of a force or
+    displacement evaluation (``GravityFD4(0..2)`` or ``GradientK(0..2)``; examples/nbody.py:154-170, 211-213) with
+    the transfers FUSED into the first pass of the backward transforms (engine extension, pmb_fft_c2r_grad3: the
+    density modes are multiplied as the axis-0 transform loads them; no pass over the modes for the transfer, no
+    intermediate complex fields).  ``outs``: RealFields (None: new ones).  Equals
+    ``c2r_fields(apply_gradients(field, transfers))`` to rounding, and runs exactly that for any other combination.
+    """
+    pm = field.pm
+    n = len(transfers)
+    if outs is None:
+        outs = [None] * n
+    outs = [RealField(pm) if o is None else o for o in outs]
+    tfs = [find_transfer(t) for t in transfers]
+    same = (n == 3 and pm.ndim == 3 and all(t is not None for t in tfs)
+            and tfs[0].kind in (_lib.TF_GRAVITY_FD4, _lib.TF_GRADIENT_K) and all(t.kind == tfs[0].kind for t in tfs)
+            and [int(t.direction) for t in tfs] == [0, 1, 2] and isinstance(field, BaseComplexField)
+            and all(isinstance(o, RealField) and o.pm is pm and o._base is not field._base for o in outs)
+            and len(set(id(o._base) for o in outs)) == 3)
+    if not same:
+        return c2r_fields(apply_gradients(field, transfers), outs=outs)
+    src = field._device(absorb=True)
+    box = (ctypes.c_double * 3)(*[float(b) for b in field.BoxSize])
+    ptrs = (ctypes.c_void_p * 3)(*[o._dev.ptr for o in outs])
+    _lib.check(pm.ctx.lib.pmb_fft_c2r_grad3(pm._plan, tfs[0].kind, box, float(field._pending), src.ptr, ptrs))
+    for o in outs:
+        o._mark_device_written()
+    return list(outs)
+
+
 def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None):
     """
     Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles
@@ -1105,6 +1136,13 @@ class ParticleMesh(object):
         ms = ctypes.c_float()
         _lib.check(self.ctx.lib.pmb_fft_library_ms(self._plan, ctypes.byref(ms), int(reset)))
         return ms.value
+
+    def fft_fused_stats(self, reset=False):
+        """ (ms, launches): time inside the fused transfer + axis-0 transform kernels (pmb_ifft.cuh) since the last reset """
+        ms = ctypes.c_float()
+        nl = ctypes.c_int64()
+        _lib.check(self.ctx.lib.pmb_fft_fused_stats(self._plan, ctypes.byref(ms), ctypes.byref(nl), int(reset)))
+        return ms.value, nl.value
 
     def fft_transpose_stats(self, reset=False):
         """ (ms, bytes): time inside the transpose kernels of the distributed transforms and the bytes they

@@ -68,7 +68,7 @@ def harness():
     """host build of the device stencil code (tests/harness/host_harness.cpp)"""
     src = os.path.join(ROOT, "tests", "harness", "host_harness.cpp")
     so = os.path.join(ROOT, "tests", "harness", "libhost_harness.so")
-    deps = [src] + [os.path.join(ROOT, "pmesh_b200", "csrc", f) for f in ("pmb_window.h", "pmb_stencil.cuh", "pmb_internal.h", "pmb_wnrng.h", "pmb_route.h")]
+    deps = [src] + [os.path.join(ROOT, "pmesh_b200", "csrc", f) for f in ("pmb_window.h", "pmb_stencil.cuh", "pmb_internal.h", "pmb_wnrng.h", "pmb_route.h", "pmb_ifft.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
                                "-I/usr/local/cuda/include", "-o", so, src])

@@ -302,3 +302,64 @@ extern "C" int64_t hh_decompose(const void *pos, int pos_elsize, int64_t npart, 
     }
     return n;
 }
+
+// ---- the line transform of pmb_ifft.cuh, "thread" by "thread" and phase by phase on the host --------------
+#include "../../pmesh_b200/csrc/pmb_ifft.cuh"
+
+template <typename C, int N, bool CONTIG>
+static int hh_ifft_run(const C *in, C *out, const C *twtab)
+{
+    constexpr int B = pmb_ifft_bundle<C, N, CONTIG>::B;
+    typedef pmb_ifft_line<C, N, CONTIG, B> F;
+    std::vector<C> sm((size_t) F::SMEM_ELEMS);
+    std::vector<C> regs((size_t) B * F::TPL * 16);
+    auto tw2 = [&](int r, int k) -> C { return twtab[k * r * F::R3]; };
+    auto tw3 = [&](int r, int j) -> C { return twtab[j * r]; };
+    auto V = [&](int b, int t) -> C * { return regs.data() + ((size_t) b * F::TPL + t) * 16; };
+    for (int b = 0; b < B; b++)
+        for (int t = 0; t < F::TPL; t++) {
+            C *v = V(b, t);
+            for (int r = 0; r < 16; r++) v[r] = in[(size_t) b * N + t + r * F::TPL];
+            F::p1(sm.data(), b, t, v);
+        }
+    for (int b = 0; b < B; b++) for (int t = 0; t < F::TPL; t++) F::p2_load(sm.data(), b, t, V(b, t));
+    for (int b = 0; b < B; b++)
+        for (int t = 0; t < F::TPL; t++) {
+            C *v = V(b, t);
+            F::p2_compute(t, v, tw2);
+            if (F::R3 == 1) {
+                for (int m = 0; m < 16 / F::R2; m++)
+                    for (int q = 0; q < F::R2; q++) out[(size_t) b * N + F::p2_out(t, m, q)] = v[m * F::R2 + q];
+            } else {
+                F::p2_store(sm.data(), b, t, v);
+            }
+        }
+    if (F::R3 > 1) {
+        for (int b = 0; b < B; b++) for (int t = 0; t < F::TPL; t++) F::p3_load(sm.data(), b, t, V(b, t));
+        for (int b = 0; b < B; b++)
+            for (int t = 0; t < F::TPL; t++) {
+                C *v = V(b, t);
+                F::p3_compute(t, v, tw3);
+                for (int m = 0; m < 16 / F::R3; m++)
+                    for (int q = 0; q < F::R3; q++) out[(size_t) b * N + F::p3_out(t, m, q)] = v[m * F::R3 + q];
+            }
+    }
+    return B;
+}
+
+// inverse transform of a bundle of lines of n points ([line][point], complex, elsize 8 or 16 bytes per complex);
+// returns the number of lines in a bundle (the caller supplies at least that many), -1: unsupported n
+extern "C" int hh_ifft_lines(int n, int elsize, int contig, const void *in, void *out, const void *tw)
+{
+#define HH_IFFT_CASE(NN)                                                                                              \
+    case NN:                                                                                                          \
+        if (elsize == 16) return contig ? hh_ifft_run<double2, NN, true>((const double2 *) in, (double2 *) out, (const double2 *) tw) \
+                                        : hh_ifft_run<double2, NN, false>((const double2 *) in, (double2 *) out, (const double2 *) tw); \
+        return contig ? hh_ifft_run<float2, NN, true>((const float2 *) in, (float2 *) out, (const float2 *) tw)      \
+                      : hh_ifft_run<float2, NN, false>((const float2 *) in, (float2 *) out, (const float2 *) tw);
+    switch (n) {
+        HH_IFFT_CASE(64) HH_IFFT_CASE(128) HH_IFFT_CASE(256) HH_IFFT_CASE(512) HH_IFFT_CASE(1024) HH_IFFT_CASE(2048) HH_IFFT_CASE(4096)
+    }
+#undef HH_IFFT_CASE
+    return -1;
+}

@@ -193,6 +193,29 @@ def main():
     comm.Barrier()
     if r == 0:
         print("fused gather ok on %d ranks" % P)
+    # 6d. transfers folded into the axis-0 pass of the backward transforms (pm.gradient_fields, pmb_ifft.cuh) on slabs:
+    #     == transfer pass + cuFFT lines, for a fused length (64) and an unfused one (48, above), twice in a row
+    from pmesh_b200.pm import gradient_fields
+    for dt, tol in (("f8", 1e-12), ("f4", 2e-5)):
+        pm64 = ParticleMesh(BoxSize=[L, 0.9 * L, 1.1 * L], Nmesh=[64, 40, 24], dtype=dt, comm=comm)
+        rk = pm64.generate_whitenoise(seed=77, type="complex")
+        rk.scale(0.5)
+        for make in (T.GravityFD4, T.GradientK):
+            tf3 = [make(d) for d in range(3)]
+            ref = c2r_fields(apply_gradients(rk, tf3), outs=[Ellipsis] * 3)
+            for rep in range(2):
+                got = gradient_fields(rk, tf3)
+                for d in range(3):
+                    sc = comm.allreduce(float(abs(ref[d].value).max()) if ref[d].value.size else 0.0, op=C.MAX)
+                    err = float(abs(got[d].value - ref[d].value).max()) if ref[d].value.size else 0.0
+                    assert err <= tol * sc, ("fused transfer + first pass", dt, d, err, sc)
+        del pm64, rk, ref, got
+    got = gradient_fields(rhok, [T.GravityFD4(d) for d in range(3)])      # n = 48: the unfused calls
+    for d in range(3):
+        assert numpy.array_equal(got[d].value, fields[d].value)
+    comm.Barrier()
+    if r == 0:
+        print("fused transfer + first pass ok on %d ranks" % P)
     del pm, layout, lpos, rhok, fields, fused, two
 
     # 7. pencil (2-D) process meshes, the reference's default for 3-D fields (pm.py:1319-1327): real space

@@ -263,6 +263,46 @@ def test_conservation_properties_at_scale():
 
 
 @pytest.mark.parametrize("dtype", ["f8", "f4"])
+@pytest.mark.parametrize("n0", [64, 128, 256, 512, 1024, 2048, 4096, 48])
+def test_gradient_fields_fused_transfer_and_first_pass(P, oracle, dtype, n0):
+    """pm.gradient_fields (pmb_fft_c2r_grad3: transfers folded into this library's own axis-0 inverse transform,
+    pmb_ifft.cuh; cuFFT for the planes) == [rhok.apply(T_d).c2r()] and == the numpy oracle; every supported line
+    length (64 .. 4096), and a length that takes the unfused calls (48)"""
+    from pmesh_b200 import transfer as T
+    n = (n0, 12, 10) if n0 >= 512 else (n0, 20, 18)
+    box = [7.0, 9.0, 11.0]
+    pm = P.ParticleMesh(BoxSize=box, Nmesh=n, dtype=dtype)
+    tol = 1e-12 if dtype == "f8" else 2e-5
+    x = numpy.random.default_rng(n0).normal(size=n).astype(dtype)
+    rx = pm.create(type="real", value=x)
+    rx.scale(1.75)                  # a pending scalar of the input rides along
+    cx = rx.r2c()
+    keep = cx.value.copy()
+    ck = oracle.r2c(1.75 * x.astype("f8"))
+    for make, name in ((T.GravityFD4, "gravity_fd4"), (T.GradientK, "gradient_k")):
+        tfs = [make(d) for d in range(3)]
+        fused = P.gradient_fields(cx, tfs)
+        for d in range(3):
+            one = cx.apply(tfs[d]).c2r()
+            scale = abs(one.value).max()
+            assert abs(fused[d].value - one.value).max() <= tol * scale, (name, d)
+            want = oracle.c2r(oracle.transfer(ck, list(n), box, name, d), list(n))
+            assert abs(fused[d].value - want).max() <= max(tol, 1e-6 if dtype == "f8" else 1e-4) * abs(want).max(), (name, d)
+    assert numpy.array_equal(cx.value, keep), "the input modes are preserved"
+    # into given RealFields, twice in a row (work buffers and plans are reused)
+    outs = [pm.create(type="real") for d in range(3)]
+    again = P.gradient_fields(cx, [T.GravityFD4(d) for d in range(3)], outs=outs)
+    assert all(a is o for a, o in zip(again, outs))
+    first = [o.value.copy() for o in outs]
+    P.gradient_fields(cx, [T.GravityFD4(d) for d in range(3)], outs=outs)
+    for d in range(3):
+        assert numpy.array_equal(outs[d].value, first[d])
+    # any other combination of transfers goes through apply + c2r
+    mixed = P.gradient_fields(cx, [T.GravityFD4(0), T.GradientK(1)])
+    assert abs(mixed[1].value - cx.apply(T.GradientK(1)).c2r().value).max() <= tol * abs(mixed[1].value).max()
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
 def test_apply_gradients_and_device_reductions(P, oracle, dtype):
     """pm.apply_gradients (three gradient transfers in one pass over the modes) == three apply calls;
     csum / cdot / cnorm reduce on the device (pmb_field_sum / pmb_field_dot / pmb_cdot) == numpy"""

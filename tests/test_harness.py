@@ -193,3 +193,21 @@ def test_routing_arithmetic_bit_exact(harness, oracle):
         got_c, got_i = _hh_decompose(harness, pos, edges, P, smoothing, periodic, scale=scale)
         assert_array_equal(got_c, want_c, err_msg="trial %d" % trial)
         assert_array_equal(got_i, want_i, err_msg="trial %d" % trial)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_line_transform_of_the_fused_backward_pass(harness, n):
+    """pmb_ifft.cuh -- the Stockham passes (radices 16, R2, R3), their shared-memory index maps (both layouts) and the
+    register butterflies, run "thread" by "thread" on the host -- against numpy.fft.ifft * n"""
+    rng = numpy.random.default_rng(n)
+    for es, dt, tol in ((16, numpy.complex128, 2e-15), (8, numpy.complex64, 1e-6)):
+        for contig in (0, 1):
+            x = (rng.standard_normal((64, n)) + 1j * rng.standard_normal((64, n))).astype(dt)
+            out = numpy.zeros_like(x)
+            tw = numpy.exp(2j * numpy.pi * numpy.arange(n) / n).astype(dt)
+            nb = harness.hh_ifft_lines(ctypes.c_int(n), ctypes.c_int(es), ctypes.c_int(contig), ctypes.c_void_p(x.ctypes.data),
+                                       ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(tw.ctypes.data))
+            assert 1 <= nb <= 64
+            want = numpy.fft.ifft(x[:nb].astype(numpy.complex128), axis=1) * n
+            assert abs(out[:nb] - want).max() <= tol * abs(want).max()
+    assert harness.hh_ifft_lines(ctypes.c_int(96), ctypes.c_int(16), ctypes.c_int(0), None, None, None) == -1

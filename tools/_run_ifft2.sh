@@ -1,0 +1,11 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_pm.py -x -q -m gpu -k "gradient_fields or force" > gpurun_out/r2s_pytest_pm.log 2>&1; tail -3 gpurun_out/r2s_pytest_pm.log
+for mode in ""; do
+timeout 600 python bench.py --steps 5 --warmup 3 --breakdown --no-cpu --no-e2e --inputs zeldovich $mode > gpurun_out/r2s_bench1$mode.json 2> gpurun_out/r2s_bench1$mode.err; tail -c 400 gpurun_out/r2s_bench1$mode.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2s_bench1$mode.json').read().strip().splitlines()[-1])
+print(d['value'], d['stage_ms_per_step'], d['cufft_library_ms_per_step'], d.get('fused_transfer_ifft'), d['verify'].get('parity_rel_err'), d['gpu_launches'])
+"
+done
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:pmb_k_ifft -c 1 -f -o gpurun_out/r2s_ifft_ncu2 python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-verify --inputs zeldovich > gpurun_out/r2s_ifft_ncu2.log 2>&1
