@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-split", action="store_true",
+                    help="P > 1: move every particle through take + alltoallv (Layout.exchange) instead of painting / reading the "
+                         "rank's own particles where they lie (Layout.exchange_remote)")
     ap.add_argument("--unfused", action="store_true",
                     help="transfer pass + cuFFT for all three axes of the backward transforms (the path before pmb_ifft.cuh)")
     ap.add_argument("--e2e-double", action="store_true", help="e2e: upload || compute || download with two position buffers")
@@ -208,8 +211,21 @@ class ForceStep(object):
         for d in range(3):
             F[d] = None           # the previous evaluation's columns go back to the allocator before new ones are made
         layout = self._t("decompose", lambda: pm.decompose(X, smoothing=1.0 * pm.resampler.support))
-        lpos = self._t("exchange", lambda: layout.exchange(X))
-        self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
+        split = pm.comm.size > 1 and not self.args.no_split and self.args.paint_mode == "atomic"
+        if split:
+            # the particles a rank keeps are painted and read WHERE THEY LIE (the kernels clip to the local slab):
+            # only the records that change rank are packed and travel (Layout.exchange_remote)
+            lrem = self._t("exchange", lambda: layout.exchange_remote(X))
+            lpos = X
+
+            def paint2():
+                pm.paint(X, out=self.rho, mode=self.args.paint_mode)
+                if lrem.shape[0]:
+                    pm.paint(lrem, out=self.rho, mode=self.args.paint_mode, hold=True)
+            self._t("paint", paint2)
+        else:
+            lpos = self._t("exchange", lambda: layout.exchange(X))
+            self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
         self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
         self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
         from pmesh_b200.pm import apply_gradients, c2r_fields, gradient_fields, readout_fields
@@ -224,7 +240,10 @@ class ForceStep(object):
             real = self._t("transfer+c2r", lambda: gradient_fields(self.rhok, self.tf, outs=self.treal))
         # the three force fields are read in ONE sweep over the particles (shared positions / weights)
         # ... and the ghost sum is fused into it: F[d] = layout.gather(real[d].readout(lpos)), nbody.py:214-216
-        Fn = self._t("readout+gather", lambda: readout_fields(real, lpos, gather=layout))
+        if split:
+            Fn = self._t("readout+gather", lambda: readout_fields(real, X, remote=(layout, lrem)))
+        else:
+            Fn = self._t("readout+gather", lambda: readout_fields(real, lpos, gather=layout))
         for d in range(3):
             F[d] = Fn[d]
         return F

@@ -215,6 +215,42 @@ class Layout(object):
             return out.to_host()
         return out
 
+    def exchange_remote(self, data):
+        """
+        The records OTHER ranks deliver to this rank, in rank order -- ``exchange(data)`` without the block this
+        rank sends to itself (engine extension; device arrays only).
+
+        For kernels that clip to the local canvas (every paint / readout of a decomposed mesh does) the block a
+        rank keeps need not be gathered at all: painting ``data`` where it lies deposits exactly what the own
+        block would -- a particle of ``data`` that does not touch the local domain is not in that block and
+        deposits nothing here -- so ``paint(exchange(pos)) == paint(pos) + paint(exchange_remote(pos))`` and
+        likewise for readout followed by :py:meth:`gather_add_ghosts`.  Only the few records that really change
+        rank are packed and travel (domain.py:173-206 moves every record through ``take`` + ``Alltoallv``).
+        """
+        ddata, dtype, trailing, was_host = self._to_device_records(
+            data, self.sendlength, 'the length of data does not match that used to build the layout')
+        assert not was_host, "exchange_remote serves device arrays"
+        ctx = ddata.ctx
+        itemsize = int(numpy.prod(trailing, dtype='i8')) * dtype.itemsize
+        me, P = self.comm.rank, self.comm.size
+        rn, sn = int(self.recvcounts[me]), int(self.sendcounts[me])
+        nrem = int(self.recvlength) - rn
+        recv = DeviceArray.empty((max(nrem, 1), itemsize), 'u1')
+        if P > 1:
+            nsend = int(self.sendcounts.sum())
+            s0 = int(self.sendoffsets[me])
+            send = DeviceArray.empty((max(nsend - sn, 1), itemsize), 'u1')
+            soff = self._remote_offsets(self.sendoffsets, sn)
+            roff = self._remote_offsets(self.recvoffsets, rn)
+            ip = self._indices_ptr()
+            for a, b, dst in ((0, s0, send.ptr), (s0 + sn, nsend, send.ptr + s0 * itemsize)):
+                if b > a:
+                    src_idx = None if ip is None else ip + 4 * a
+                    src = ddata.ptr + (a * itemsize if ip is None else 0)
+                    _lib.check(ctx.lib.pmb_take(ctx.handle, src, itemsize, src_idx, b - a, dst))
+            self._alltoallv(ctx, send, self.sendcounts, soff, recv, self.recvcounts, roff, itemsize, skip_self=True)
+        return DeviceArray((nrem,) + tuple(trailing), dtype, ptr=recv.ptr, base=recv, ctx=ctx)
+
     # ------------------------------------------------------------------ fused readout + gather
     def fused_gather_plan(self):
         """(own_begin, own_count, pointer to the indices of the own block) for kernels that write the results of

@@ -70,8 +70,17 @@ def force(pm, Q, S=None, factor=1.0):
     Q = _dev(Q)
     X = Q if S is None else DeviceArray.empty(Q.shape, Q.dtype).assign_lincomb(_dev(S), 1.0, Q, 1.0)
     layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
-    lpos = layout.exchange(X)
-    rho = pm.paint(lpos)
+    # P > 1: the particles a rank keeps are painted and read where they lie (every kernel clips to the local canvas);
+    # only the records that change rank travel (Layout.exchange_remote)
+    split = pm.comm.size > 1
+    if split:
+        lrem = layout.exchange_remote(X)
+        rho = pm.paint(X)
+        if lrem.shape[0]:
+            pm.paint(lrem, out=rho, hold=True)
+    else:
+        lpos = layout.exchange(X)
+        rho = pm.paint(lpos)
     N = pm.comm.allreduce(len(X))
     rho.scale(1.0 * pm.Nmesh.prod() / N * factor)
     rhok = rho.r2c(out=Ellipsis)
@@ -80,6 +89,8 @@ def force(pm, Q, S=None, factor=1.0):
     # ... and the transfers are folded into the first pass of the backward transforms (pm.gradient_fields)
     from .pm import gradient_fields, readout_fields
     f = gradient_fields(rhok, [force_transfer(d) for d in range(pm.ndim)])
+    if split:
+        return readout_fields(f, X, remote=(layout, lrem))
     return readout_fields(f, lpos, gather=layout)
 
 

@@ -896,7 +896,7 @@ def gradient_fields(field, transfers, outs=None):
     return list(outs)
 
 
-def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None):
+def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None, remote=None):
     """
     Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles
     (engine extension; the force step's three components, examples/nbody.py:211-216, share the pass
@@ -909,6 +909,10 @@ def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gat
              the particles: the kernel writes the results of the rank's own particles straight into the
              gathered columns and only the ghosts travel (sums agree with Layout.gather to rounding: the
              own value is added first instead of in rank order)
+    remote : ``(layout, layout.exchange_remote(pos))`` with ``pos`` the ORIGINAL particles: nothing of the rank's own
+             block is moved -- every particle is read where it lies (the kernels clip to the local canvas), the ghosts
+             received from other ranks are read separately, their partial sums travel back and are added in rank order
+             (same sums as ``gather=``; Layout.exchange_remote)
     """
     pm = fields[0].pm
     if not transform:
@@ -917,6 +921,17 @@ def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gat
     if layout is not None:
         pos = layout.exchange(pos)
         gather = layout
+    if remote is not None:
+        # pos are the ORIGINAL particles (never moved), remote = (layout, layout.exchange_remote(pos)): every particle is
+        # read where it lies -- the kernels clip to the local canvas, so a particle gets the partial sum of its points
+        # on this rank -- the ghosts received from other ranks are read separately and their partial sums travel back
+        lay, rpos = remote
+        own = resampler.readout_multi([f._device() for f in fields], pos, transform=transform)
+        if lay.comm.size == 1:
+            return own
+        ghosts = (resampler.readout_multi([f._device() for f in fields], rpos, transform=transform) if rpos.shape[0]
+                  else [DeviceArray.empty((1,), 'f8') for _ in fields])
+        return lay.gather_add_ghosts(ghosts, own)
     plan = gather.fused_gather_plan() if (gather is not None and is_device(pos)) else None
     # the fused kernel exists for the CIC window on 3-D meshes with at least 2^18 particles (pmb_readout_multi_gather)
     if plan is not None and len(fields) <= 3 and resampler.kind == 'tunedcic' and pm.ndim == 3 and pos.shape[0] >= (1 << 18):

@@ -193,6 +193,26 @@ def main():
     comm.Barrier()
     if r == 0:
         print("fused gather ok on %d ranks" % P)
+    # 6c'. the rank's own particles painted / read where they lie, only the records that change rank travel
+    #      (Layout.exchange_remote) == the full exchange
+    lrem = layout.exchange_remote(dmine)
+    me_cnt = int(layout.recvcounts[r])
+    assert lrem.shape[0] == lpos.shape[0] - me_cnt
+    full = lpos.to_host()
+    off = int(layout.recvoffsets[r])
+    assert numpy.array_equal(lrem.to_host(), numpy.concatenate([full[:off], full[off + me_cnt:]])), "exchange_remote records"
+    rho_a = pm.paint(lpos)
+    rho_b = pm.paint(dmine)
+    if lrem.shape[0]:
+        pm.paint(lrem, out=rho_b, hold=True)
+    sc = comm.allreduce(float(abs(rho_a.value).max()), op=C.MAX)
+    assert float(abs(rho_a.value - rho_b.value).max()) <= 1e-12 * sc, "paint in place + remote ghosts"
+    split = readout_fields(fields, dmine, remote=(layout, lrem))
+    for d in range(3):
+        assert rel(split[d].to_host(), fused[d].to_host()) < 1e-13, "readout in place + ghost sum"
+    comm.Barrier()
+    if r == 0:
+        print("split exchange ok on %d ranks" % P)
     # 6d. transfers folded into the axis-0 pass of the backward transforms (pm.gradient_fields, pmb_ifft.cuh) on slabs:
     #     == transfer pass + cuFFT lines, for a fused length (64) and an unfused one (48, above), twice in a row
     from pmesh_b200.pm import gradient_fields
