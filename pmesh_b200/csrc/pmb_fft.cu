@@ -1490,10 +1490,24 @@ extern "C" int pmb_fft_c2r_grad3(pmb_fft *f, int kind, const double *boxsize_h, 
         a.nlines = f->n[1] * f->nc;
         // direction 0 has a multiplier that varies along the line; directions 1 and 2 are the SAME transform times a
         // constant of the line: two transforms, three outputs
-        a.ntr = 2;
-        a.tr[0].axis0mul = 1; a.tr[0].nout = 1; a.tr[0].out[0] = reals_h[0]; a.tr[0].linemul[0] = 0;
-        a.tr[1].axis0mul = 0; a.tr[1].nout = 2; a.tr[1].out[0] = reals_h[1]; a.tr[1].linemul[0] = 1;
-        a.tr[1].out[1] = reals_h[2]; a.tr[1].linemul[1] = 2;
+        static int use_stencil = -1;
+        if (use_stencil < 0) { const char *e = getenv("PMB_IFFT_STENCIL"); use_stencil = e ? atoi(e) : 1; }
+        // (float64 fields only: the differences of neighbouring phi values cancel ~ 1 / (k C) leading digits on the
+        // longest waves -- nothing against 1e-16, too much of float32's 6e-8 on long axes)
+        if (kind == PMB_TF_GRAVITY_FD4 && use_stencil && f->elsize == 8) {
+            // ... and with the finite-difference gradient direction 0 is a 5-point stencil along the line of the very
+            // same transform: ONE transform, three outputs
+            a.ntr = 1;
+            a.tr[0].axis0mul = 0; a.tr[0].nout = 2; a.tr[0].out[0] = reals_h[1]; a.tr[0].linemul[0] = 1;
+            a.tr[0].out[1] = reals_h[2]; a.tr[0].linemul[1] = 2;
+            a.tr[0].sten_out = reals_h[0];
+            a.tr[0].sten_c = 1.0 / (12.0 * (boxsize_h[0] / (double) f->n[0]));
+        } else {
+            a.ntr = 2;
+            a.tr[0].axis0mul = 1; a.tr[0].nout = 1; a.tr[0].out[0] = reals_h[0]; a.tr[0].linemul[0] = 0;
+            a.tr[1].axis0mul = 0; a.tr[1].nout = 2; a.tr[1].out[0] = reals_h[1]; a.tr[1].linemul[0] = 1;
+            a.tr[1].out[1] = reals_h[2]; a.tr[1].linemul[1] = 2;
+        }
         PMB_CHECK(ifft_launch(f, a, f->ctx->stream));
         for (int d = 0; d < 3; d++) PMB_CHECK(exec_c2r(f, f->plane_c2r, reals_h[d], reals_h[d]));
         return PMB_OK;

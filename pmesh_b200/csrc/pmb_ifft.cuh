@@ -182,14 +182,21 @@ template <typename C, int N, bool CONTIG = true, bool WIDE = true> struct pmb_if
 
 #if defined(__CUDACC__)
 
-// One TRANSFORM of a launch: IDFT_axis0( i * pre / k^2 * [m_0(i0)] * in ), stored to `nout` outputs, output o multiplied
-// by a constant of the LINE (nothing, m_1(i1) or m_2(i2)).  The multipliers of directions 1 and 2 do not depend on the
+// One TRANSFORM of a launch: phi = IDFT_axis0( pre / k^2 * [m_0(i0)] * in ); output o = i * c_o * phi with c_o a constant
+// of the LINE (1, m_1(i1) or m_2(i2)).  The multipliers of directions 1 and 2 do not depend on the
 // position along the line, so ONE transform serves both: a force evaluation costs two transforms per line, not three.
 struct PmbIfftTransform {
     int axis0mul;            // 1: the input is multiplied by mtab[0][i0] (direction 0)
-    int nout;                // 1 or 2
+    int nout;                // 0, 1 or 2
     void *out[2];
     int linemul[2];          // 0: none, 1: mtab[1][i1], 2: mtab[2][i2]
+    // direction 0 of the FINITE-DIFFERENCE gradient (PMB_TF_GRAVITY_FD4): i kfinite(k_0) = i (8 sin w - sin 2w) / (6 C)
+    // is the symbol of the 4th-order central difference, so direction 0 is that stencil applied ALONG THE LINE to the
+    // transform phi of pre / k^2 * in that directions 1 and 2 store anyway:
+    //   sten_out(x) = sten_c * (8 (phi(x+1) - phi(x-1)) - (phi(x+2) - phi(x-2))),  sten_c = 1 / (12 C), periodic in x.
+    // One transform of the line then serves all three directions.
+    void *sten_out;          // NULL: no stencil output
+    double sten_c;
 };
 
 struct PmbIfftArgs {
@@ -289,9 +296,8 @@ pmb_k_ifft_grad(PmbIfftArgs a)
                 kk = kk == 0 ? 1.0 : kk;
                 double g = pmb_fast_rcp(kk) * a.pre;
                 g = ax0 ? g * m0 : g;
-                const T im = (T) g;
-                // i * im * v
-                v[r] = pmb_cx<C>(-(v[r].y * im), v[r].x * im);
+                const T gr = (T) g;
+                v[r] = pmb_cx<C>(v[r].x * gr, v[r].y * gr);
             }
             F::p1(sm, b, t, v);
             __syncthreads();
@@ -305,11 +311,21 @@ pmb_k_ifft_grad(PmbIfftArgs a)
                 __syncthreads();
                 F::p3_compute(t, v, tw3);
             }
+            constexpr int RL = F::R3 > 1 ? F::R3 : F::R2;
+            // output q of butterfly m sits at idx0(m) + q * QS points of the line
+            constexpr int QS = F::R3 > 1 ? N / F::R3 : 16;
+            C *__restrict__ sten = (C *) a.tr[tr].sten_out;
+            if (sten) {
+                // park phi in the exchange buffer (every thread has read its last pass out of it: the barrier above)
+#pragma unroll
+                for (int m = 0; m < 16 / RL; m++) {
+                    const int idx0 = F::R3 > 1 ? F::p3_out(t, m, 0) : F::p2_out(t, m, 0);
+#pragma unroll
+                    for (int q = 0; q < RL; q++) sm[F::sidx(b, idx0 + q * QS)] = v[m * RL + q];
+                }
+            }
             if (live) {
                 const int nout = a.tr[tr].nout;
-                constexpr int RL = F::R3 > 1 ? F::R3 : F::R2;
-                // output q of butterfly m sits at idx0(m) + q * QS points of the line
-                constexpr int QS = F::R3 > 1 ? N / F::R3 : 16;
                 const int64_t qstep = (int64_t) QS * estr;
 #pragma unroll 1
                 for (int o = 0; o < nout; o++) {
@@ -323,11 +339,30 @@ pmb_k_ifft_grad(PmbIfftArgs a)
 #pragma unroll
                         for (int q = 0; q < RL; q++) {
                             const C w = v[m * RL + q];
-                            *p = pmb_cx<C>(w.x * ml, w.y * ml);
+                            *p = pmb_cx<C>(-(w.y * ml), w.x * ml);       // i * ml * phi
                             p += qstep;
                         }
                     }
                 }
+            }
+            if (sten) {
+                __syncthreads();
+                // thread t of the line now owns the 16 CONSECUTIVE points 16 t .. 16 t + 15
+                const T c = (T) a.tr[tr].sten_c;
+                const int x0 = 16 * t;
+                auto at = [&](int x) -> C { return sm[F::sidx(b, (x + N) & (N - 1))]; };
+                C pm2 = at(x0 - 2), pm1 = at(x0 - 1), p0 = at(x0), pp1 = at(x0 + 1);
+                C *__restrict__ p = sten + base + (int64_t) x0 * estr;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const C pp2 = at(x0 + j + 2);
+                    const T dx = (T) 8 * (pp1.x - pm1.x) - (pp2.x - pm2.x);
+                    const T dy = (T) 8 * (pp1.y - pm1.y) - (pp2.y - pm2.y);
+                    if (live) *p = pmb_cx<C>(dx * c, dy * c);
+                    p += estr;
+                    pm2 = pm1; pm1 = p0; p0 = pp1; pp1 = pp2;
+                }
+                __syncthreads();       // before the next transform's pass 1 overwrites the buffer
             }
         }
     }
