@@ -45,6 +45,7 @@ struct pmb_fft {
     cufftHandle pen_r2c, pen_c2r, pen_l1, pen_l0;   // pencils: 1-D transforms along axes 2, 1, 0
     bool have_full, have_slab, have_pen;
     void *work0, *work1;
+    void *work2;                  // third line buffer of the one-launch fused backward pass (slabs), made on first use
     size_t work_bytes;
     // direct peer-memory global transpose (P > 1): every rank exposes two landing buffers through
     // CUDA IPC; the transpose kernels of the other ranks store straight into them over NVLink
@@ -436,6 +437,7 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
     }
     if (f->work0) cudaFree(f->work0);
     if (f->work1) cudaFree(f->work1);
+    if (f->work2) cudaFree(f->work2);
     for (int i = 0; i < FFT_NEV; i++) { cudaEventDestroy(f->ev[i][0]); cudaEventDestroy(f->ev[i][1]); }
     free(f);
     return PMB_OK;
@@ -1050,6 +1052,7 @@ static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *co
         PmbIfftArgs a = *fused;
         a.ntr = 1;
         a.tr[0].axis0mul = d == 0; a.tr[0].nout = 1; a.tr[0].out[0] = dst; a.tr[0].linemul[0] = d;
+        a.tr[0].sten_out = NULL; a.tr[0].sten_c = 0.0;
         return ifft_launch(f, a, f->ctx->stream);
     };
     if (!(f->P > 1 && f->P1 == 1 && f->p2p && n >= 2 && overlap && f->work1)) {
@@ -1068,6 +1071,12 @@ static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *co
     cudaStream_t ms = ctx->stream, xs = f->xstream;
     cudaEvent_t *evL = f->xev, *evS = f->xev + 4, *evP = f->xev + 8, evEntry = f->xev[12], evExit = f->xev[13];
     void *wk[2] = {f->work0, f->work1};
+    // fused lines with the finite-difference stencil: ONE launch transforms every line once and writes the lines of
+    // all three directions (three line buffers); otherwise one launch (or cuFFT call) per direction, two buffers
+    bool all3 = fused && n == 3 && fused->tr[0].sten_c != 0.0;
+    if (all3 && !f->work2 && cudaMalloc(&f->work2, f->work_bytes) != cudaSuccess) { cudaGetLastError(); f->work2 = NULL; all3 = false; }
+    void *wk3[3] = {f->work0, f->work1, f->work2};
+    auto wbuf = [&](int d) -> void * { return all3 ? wk3[d] : wk[d & 1]; };
     int xb[4];
     for (int d = 0; d < n; d++) { xb[d] = f->xcur; f->xcur ^= 1; }
     // entry
@@ -1075,6 +1084,20 @@ static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *co
     PMB_CUDA(cudaStreamWaitEvent(xs, evEntry, 0));
     PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
     auto line = [&](int d) -> int {          // L_d on the compute stream
+        if (all3) {
+            if (d > 0) return PMB_OK;         // written by the launch of d == 0
+            if (f->m1 > 0) {
+                PmbIfftArgs a = *fused;
+                a.ntr = 1;
+                a.tr[0].axis0mul = 0; a.tr[0].nout = 2;
+                a.tr[0].out[0] = wk3[1]; a.tr[0].linemul[0] = 1;
+                a.tr[0].out[1] = wk3[2]; a.tr[0].linemul[1] = 2;
+                a.tr[0].sten_out = wk3[0];
+                PMB_CHECK(ifft_launch(f, a, ms));
+            }
+            for (int e = 0; e < n; e++) PMB_CUDA(cudaEventRecord(evL[e], ms));
+            return PMB_OK;
+        }
         if (f->m1 > 0) {
             if (fused) PMB_CHECK(fused_lines(d, wk[d & 1]));
             else PMB_CHECK(exec_c2c(f, f->line, (void *) cplx_h[d], wk[d & 1], CUFFT_INVERSE));
@@ -1090,8 +1113,8 @@ static int c2r_multi_impl(pmb_fft *f, int n, const void *const *cplx_h, void *co
         }
         XDest dst;
         xdest_bwd(f, xb[d], &dst);
-        if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, wk[d & 1], f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
-        else PMB_CHECK(xpose_scatter<float2>(f, wk[d & 1], f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
+        if (f->elsize == 8) PMB_CHECK(xpose_scatter<double2>(f, wbuf(d), f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
+        else PMB_CHECK(xpose_scatter<float2>(f, wbuf(d), f->n[0], f->m1 * f->nc, f->n[1] * f->nc, dst, 1.0, -1, -1, 1, 0, xs));
         PMB_CHECK(pmb_stream_barrier_on(ctx, xs));
         PMB_CUDA(cudaEventRecord(evS[d], xs));
         return PMB_OK;
@@ -1513,6 +1536,14 @@ extern "C" int pmb_fft_c2r_grad3(pmb_fft *f, int kind, const double *boxsize_h, 
         return PMB_OK;
     }
     a.nlines = f->m1 * f->mc;
+    // slabs: the stencil coefficient tells c2r_multi_impl that one launch can serve the three directions (float64
+    // finite-difference gradient, see above); the per-direction launches ignore it
+    {
+        static int use_stencil = -1;
+        if (use_stencil < 0) { const char *e = getenv("PMB_IFFT_STENCIL"); use_stencil = e ? atoi(e) : 1; }
+        if (kind == PMB_TF_GRAVITY_FD4 && use_stencil && f->elsize == 8)
+            a.tr[0].sten_c = 1.0 / (12.0 * (boxsize_h[0] / (double) f->n[0]));
+    }
     const void *c[3] = {in, in, in};
     return c2r_multi_impl(f, 3, c, reals_h, &a);
 }
