@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-split", action="store_true",
                     help="P > 1: move every particle through take + alltoallv (Layout.exchange) instead of painting / reading the "
                          "rank's own particles where they lie (Layout.exchange_remote)")
+    ap.add_argument("--no-forward-fusion", action="store_true",
+                    help="one rank: full r2c by cuFFT, then the fused transfer + axis-0 inverse kernel (pm.gradient_fields)")
     ap.add_argument("--unfused", action="store_true",
                     help="transfer pass + cuFFT for all three axes of the backward transforms (the path before pmb_ifft.cuh)")
     ap.add_argument("--e2e-double", action="store_true", help="e2e: upload || compute || download with two position buffers")
@@ -227,9 +229,17 @@ class ForceStep(object):
             lpos = self._t("exchange", lambda: layout.exchange(X))
             self._t("paint", lambda: pm.paint(lpos, out=self.rho, mode=self.args.paint_mode))
         self._t("scale", lambda: self.rho.scale(1.0 * pm.Nmesh.prod() / ntot))
-        self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
-        from pmesh_b200.pm import apply_gradients, c2r_fields, gradient_fields, readout_fields
-        if self.args.unfused:
+        from pmesh_b200.pm import apply_gradients, c2r_fields, force_fields, gradient_fields, readout_fields
+        whole = pm.comm.size == 1 and not self.args.unfused and not self.args.no_forward_fusion
+        if whole:
+            # one rank: the last pass of r2c, the gravity transfers and the first pass of the three c2r are ONE kernel of
+            # this library (pmb_ifft.cuh, pmb_fft_force3); cuFFT transforms the planes; the density modes never reach HBM
+            real = self._t("r2c+transfer+c2r", lambda: force_fields(self.rho, self.tf, outs=self.treal))
+        else:
+            self._t("r2c", lambda: self.rho.r2c(out=self.rhok))
+        if whole:
+            pass
+        elif self.args.unfused:
             # the three gravity transfers read the density modes once (pm.apply_gradients) ...
             self._t("transfer", lambda: apply_gradients(self.rhok, self.tf, outs=self.tmp))
             # ... the three backward transforms overlap their NVLink transposes with each other's local FFTs

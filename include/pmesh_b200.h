@@ -339,6 +339,15 @@ int pmb_transfer_grad3(pmb_fft *plan, int kind, const double *boxsize_h, double 
  * partners are used as work space). */
 int pmb_fft_c2r_grad3(pmb_fft *plan, int kind, const double *boxsize_h, double prefactor, const void *in,
                       void *const *reals_h);
+/* The whole Fourier part of a force evaluation, reals_h[d] = c2r(i m_d(k_d) / k^2 * r2c(real_in) * prefactor), d = 0, 1, 2
+ * -- `[rho.r2c().apply(T_d).c2r() for d in range(3)]` (pm.py:655-694, 617-648, 987-1019; examples/nbody.py:205-213) --
+ * with the LAST pass of r2c, the transfers and the FIRST pass of the three c2r in one kernel of this library
+ * (pmb_ifft.cuh): cuFFT transforms the planes (axes 1, 2), the kernel takes every axis-0 line forward, multiplies and
+ * takes it back in registers / shared memory; the density modes are never written to memory.  prefactor carries the
+ * 1 / prod(Nmesh) of r2c (pm.py:692).  One rank, axis 0 a power of two in 64 .. 4096; otherwise PMB_EUNSUPPORTED (the
+ * caller composes pmb_fft_r2c + pmb_fft_c2r_grad3).  real_in is preserved. */
+int pmb_fft_force3(pmb_fft *plan, int kind, const double *boxsize_h, double prefactor, const void *real_in,
+                   void *const *reals_h);
 /* milliseconds inside the fused transfer + line-transform kernels and their number since the last reset */
 int pmb_fft_fused_stats(pmb_fft *plan, float *ms, int64_t *launches, int reset);
 

@@ -69,7 +69,7 @@ SYMBOLS = [
     "pmb_comm_unique_id", "pmb_comm_init_rank", "pmb_comm_destroy", "pmb_comm_rank", "pmb_alltoallv",
     "pmb_allreduce_f64", "pmb_allgather_bytes", "pmb_barrier",
     "pmb_fft_create", "pmb_fft_create_np", "pmb_fft_destroy", "pmb_fft_layout", "pmb_fft_r2c", "pmb_fft_c2r", "pmb_fft_c2r_multi", "pmb_fft_library_ms", "pmb_fft_transpose_stats",
-    "pmb_transfer", "pmb_transfer_scaled", "pmb_transfer_grad3", "pmb_fft_c2r_grad3", "pmb_fft_fused_stats", "pmb_cdot", "pmb_whitenoise",
+    "pmb_transfer", "pmb_transfer_scaled", "pmb_transfer_grad3", "pmb_fft_c2r_grad3", "pmb_fft_force3", "pmb_fft_fused_stats", "pmb_cdot", "pmb_whitenoise",
 ]
 
 _P = ctypes.c_void_p
@@ -120,7 +120,7 @@ _ARGTYPES = {
     "pmb_transfer_scaled": [_P, _I, _I, _P, _P, _D, _P, _P],
     "pmb_cdot": [_P, _P, _P, _P],
     "pmb_transfer_grad3": [_P, _I, _P, _D, _P, _P],
-    "pmb_fft_c2r_grad3": [_P, _I, _P, _D, _P, _P], "pmb_fft_fused_stats": [_P, _P, _P, _I],
+    "pmb_fft_c2r_grad3": [_P, _I, _P, _D, _P, _P], "pmb_fft_force3": [_P, _I, _P, _D, _P, _P], "pmb_fft_fused_stats": [_P, _P, _P, _I],
     "pmb_whitenoise": [_P, _P, _I, _P, _P, _P, _P, ctypes.c_uint, _I],
 }
 

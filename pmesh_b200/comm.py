@@ -102,15 +102,26 @@ class TorchComm(object):
         return box[0]
 
     def Alltoall(self, send, recv):
-        """one item per rank (the sendcounts -> recvcounts transpose of Layout)"""
+        """one item per rank (the sendcounts -> recvcounts transpose of Layout).  Whether the backend offers
+        all_to_all_single is found out ONCE and agreed between the ranks (a fallback that only some ranks take would
+        leave mismatched collectives behind); from then on every rank takes the same path."""
         import torch
         send = numpy.ascontiguousarray(send)
-        try:
+        if getattr(self, "_a2a_single", None) is None:
+            ok = True
+            try:
+                tin = torch.zeros(self.size, dtype=torch.int64)
+                tout = torch.empty_like(tin)
+                self._dist.all_to_all_single(tout, tin, group=self._group)
+            except (RuntimeError, NotImplementedError):
+                ok = False
+            self._a2a_single = all(self.allgather(ok))
+        if self._a2a_single:
             tin = torch.from_numpy(send.astype("int64") if send.dtype.kind in "iu" else send.astype("float64"))
             tout = torch.empty_like(tin)
             self._dist.all_to_all_single(tout, tin, group=self._group)
             recv[...] = tout.numpy().astype(recv.dtype)
-        except (RuntimeError, NotImplementedError):
+        else:
             rows = self.allgather(send.copy())
             for r in range(self.size):
                 recv[r] = rows[r][self.rank]

@@ -71,8 +71,8 @@ struct pmb_fft {
     // transfer + axis-0 inverse transform in one kernel (pmb_ifft.cuh): twiddle table, the 2-D c2r over all planes of
     // one rank (P == 1; P > 1 uses slab_c2r), time inside the fused kernel
     void *ifft_tw;
-    cufftHandle plane_c2r;
-    bool have_plane;
+    cufftHandle plane_c2r, plane_r2c;
+    bool have_plane, have_plane_r2c;
     float ifft_ms;
     int64_t ifft_launches;
 };
@@ -430,6 +430,7 @@ extern "C" int pmb_fft_destroy(pmb_fft *f)
     for (int i = 0; i < f->ntfc; i++) cudaFree(f->tfc[i].dev);
     if (f->ifft_tw) cudaFree(f->ifft_tw);
     if (f->have_plane) cufftDestroy(f->plane_c2r);
+    if (f->have_plane_r2c) cufftDestroy(f->plane_r2c);
     if (f->have_xstream) {
         cudaStreamSynchronize(f->xstream);
         cudaStreamDestroy(f->xstream);
@@ -1472,14 +1473,50 @@ static int ifft_twiddles(pmb_fft *f)
     return PMB_OK;
 }
 
+static int c2r_grad3_impl(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
+                         void *const *reals_h, int forward);
+
 extern "C" int pmb_fft_c2r_grad3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
                                  void *const *reals_h)
+{
+    return c2r_grad3_impl(f, kind, boxsize_h, prefactor, in, reals_h, 0);
+}
+
+// real_in -> 2-D r2c of every plane (cuFFT) -> [forward axis-0 transform, transfers, inverse axis-0 transform] in one
+// kernel -> 2-D c2r of every plane (cuFFT), three times
+extern "C" int pmb_fft_force3(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *real_in,
+                              void *const *reals_h)
+{
+    PMB_REQUIRE(f && boxsize_h && real_in && reals_h && reals_h[0] && reals_h[1] && reals_h[2], "null argument");
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("PMB_IFFT_FORWARD"); on = e ? atoi(e) : 1; }
+    if (!on || f->P != 1 || !ifft_supported(f, boxsize_h)) {
+        pmb_set_error("pmb_fft_force3 serves one rank and axis-0 lengths 64 .. 4096 (powers of two): use pmb_fft_r2c + pmb_fft_c2r_grad3");
+        return PMB_EUNSUPPORTED;
+    }
+    for (int d = 0; d < 3; d++) PMB_REQUIRE(reals_h[d] != real_in, "the input field must not be one of the outputs");
+    if (!f->have_plane_r2c) {
+        long long n2[2] = {f->n[1], f->n[2]};
+        long long inr[2] = {f->n[1], 2 * f->nc};
+        long long inc[2] = {f->n[1], f->nc};
+        PMB_CHECK(make_plan(f, &f->plane_r2c, 2, n2, inr, f->n[1] * 2 * f->nc, inc, f->n[1] * f->nc,
+                            f->elsize == 8 ? CUFFT_D2Z : CUFFT_R2C, f->n[0]));
+        f->have_plane_r2c = true;
+    }
+    // the planes' modes land in the buffer of output 2, which the kernel then overwrites in place (every thread writes
+    // the points of the line it read)
+    PMB_CHECK(exec_r2c(f, f->plane_r2c, real_in, reals_h[2]));
+    return c2r_grad3_impl(f, kind, boxsize_h, prefactor, reals_h[2], reals_h, 1);
+}
+
+static int c2r_grad3_impl(pmb_fft *f, int kind, const double *boxsize_h, double prefactor, const void *in,
+                         void *const *reals_h, int forward)
 {
     PMB_REQUIRE(f && boxsize_h && in && reals_h && reals_h[0] && reals_h[1] && reals_h[2], "null argument");
     PMB_REQUIRE(kind == PMB_TF_GRAVITY_FD4 || kind == PMB_TF_GRADIENT_K, "grad3 serves the two gradient transfers");
     PMB_REQUIRE(f->ndim == 3, "3-D meshes only");
     for (int d = 0; d < 3; d++) {
-        PMB_REQUIRE(reals_h[d] != in, "the input modes must not be one of the outputs");
+        PMB_REQUIRE(forward || reals_h[d] != in, "the input modes must not be one of the outputs");
         for (int e = 0; e < d; e++) PMB_REQUIRE(reals_h[d] != reals_h[e], "outputs %d and %d are the same buffer", e, d);
     }
     if (!ifft_supported(f, boxsize_h)) {
@@ -1501,6 +1538,7 @@ extern "C" int pmb_fft_c2r_grad3(pmb_fft *f, int kind, const double *boxsize_h, 
     for (int d = 0; d < 3; d++) { a.ktab[d] = (const double *) dev + off[d]; a.mtab[d] = (const double *) dev + ntab + off[d]; }
     a.tw = f->ifft_tw;
     a.pre = prefactor;
+    a.forward = forward;
     if (f->P == 1) {
         if (!f->have_plane) {
             long long n2[2] = {f->n[1], f->n[2]};

@@ -210,6 +210,10 @@ struct PmbIfftArgs {
     const double *mtab[3];   // gradient multiplier per global index of each axis
     const void *tw;          // W_N^k, k = 0 .. N-1, in the field's precision
     double pre;
+    // 1: `in` holds the field transformed along axes 1 and 2 only; the line is first transformed FORWARD along axis 0
+    // (in registers + shared memory, conj . IDFT . conj), then multiplied and transformed back: the last pass of r2c,
+    // the transfers and the first pass of the three c2r in one kernel -- the density modes never exist in HBM
+    int forward;
 };
 
 // 1 / x for a normal, positive double: hardware seed (MUFU.RCP64H) + three Newton steps, no special cases -- the host
@@ -285,6 +289,32 @@ pmb_k_ifft_grad(PmbIfftArgs a)
                 const int64_t step = (int64_t) TPL * estr;
 #pragma unroll
                 for (int r = 0; r < 16; r++) { v[r] = __ldcg(p); p += step; }      // L2 only: the second transform re-reads it there
+            }
+            if (a.forward) {
+                constexpr int RLf = F::R3 > 1 ? F::R3 : F::R2;
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[r].y = -v[r].y;
+                F::p1(sm, b, t, v);
+                __syncthreads();
+                F::p2_load(sm, b, t, v);
+                __syncthreads();
+                F::p2_compute(t, v, tw2);
+                if constexpr (F::R3 > 1) {
+                    F::p2_store(sm, b, t, v);
+                    __syncthreads();
+                    F::p3_load(sm, b, t, v);
+                    __syncthreads();
+                    F::p3_compute(t, v, tw3);
+                }
+                // output q of butterfly m is point t + TPL * (m + (16 / RL) q) of the line: exactly the points this thread
+                // feeds to pass 1 of the next transform -- the spectrum changes registers, not threads
+                C u[16];
+#pragma unroll
+                for (int m = 0; m < 16 / RLf; m++)
+#pragma unroll
+                    for (int q = 0; q < RLf; q++) u[m + (16 / RLf) * q] = pmb_cx<C>(v[m * RLf + q].x, -v[m * RLf + q].y);
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[r] = u[r];
             }
 #pragma unroll
             for (int r = 0; r < 16; r++) {

@@ -83,12 +83,16 @@ def force(pm, Q, S=None, factor=1.0):
         rho = pm.paint(lpos)
     N = pm.comm.allreduce(len(X))
     rho.scale(1.0 * pm.Nmesh.prod() / N * factor)
-    rhok = rho.r2c(out=Ellipsis)
     # the ndim force fields are kept side by side so that ONE sweep over the particles reads them all
     # (pm.readout_fields): positions, cell indices and weights are shared by the components
-    # ... and the transfers are folded into the first pass of the backward transforms (pm.gradient_fields)
-    from .pm import gradient_fields, readout_fields
-    f = gradient_fields(rhok, [force_transfer(d) for d in range(pm.ndim)])
+    # ... and the transfers are folded into the first pass of the backward transforms (pm.gradient_fields); on one
+    # rank the last pass of r2c joins them (pm.force_fields) and the density modes are never written to memory
+    from .pm import force_fields, gradient_fields, readout_fields
+    tfs = [force_transfer(d) for d in range(pm.ndim)]
+    if pm.comm.size == 1 and pm.ndim == 3:
+        f = force_fields(rho, tfs)
+    else:
+        f = gradient_fields(rho.r2c(out=Ellipsis), tfs)
     if split:
         return readout_fields(f, X, remote=(layout, lrem))
     return readout_fields(f, lpos, gather=layout)

@@ -896,6 +896,40 @@ def gradient_fields(field, transfers, outs=None):
     return list(outs)
 
 
+def force_fields(rho, transfers, outs=None):
+    """
+    ``[rho.r2c().apply(t).c2r(out=o) for t, o in zip(transfers, outs)]`` -- the Fourier part of a force evaluation
+    (examples/nbody.py:205-213) -- for the three gradient transfers.  On one rank the last pass of r2c, the transfers
+    and the first pass of the three c2r are ONE kernel (engine extension, pmb_fft_force3): the density modes are never
+    written to memory.  Anything else runs ``gradient_fields(rho.r2c(), transfers, outs)``.  ``rho`` is preserved.
+    """
+    pm = rho.pm
+    n = len(transfers)
+    tfs = [find_transfer(t) for t in transfers]
+    same = (n == 3 and pm.ndim == 3 and pm.comm.size == 1 and isinstance(rho, RealField) and all(t is not None for t in tfs)
+            and tfs[0].kind in (_lib.TF_GRAVITY_FD4, _lib.TF_GRADIENT_K) and all(t.kind == tfs[0].kind for t in tfs)
+            and [int(t.direction) for t in tfs] == [0, 1, 2])
+    if same:
+        if outs is None:
+            outs = [None] * n
+        outs = [RealField(pm) if o is None else o for o in outs]
+        same = (all(isinstance(o, RealField) and o.pm is pm and o._base is not rho._base for o in outs)
+                and len(set(id(o._base) for o in outs)) == 3)
+    if same:
+        src = rho._device(absorb=True)
+        box = (ctypes.c_double * 3)(*[float(b) for b in rho.BoxSize])
+        ptrs = (ctypes.c_void_p * 3)(*[o._dev.ptr for o in outs])
+        pre = float(rho._pending) * float(numpy.prod(pm.Nmesh.astype('f8') ** -1.0))
+        rc = pm.ctx.lib.pmb_fft_force3(pm._plan, tfs[0].kind, box, pre, src.ptr, ptrs)
+        if rc == 0:
+            for o in outs:
+                o._mark_device_written()
+            return list(outs)
+        if rc != -5:          # anything but PMB_EUNSUPPORTED
+            _lib.check(rc)
+    return gradient_fields(rho.r2c(), transfers, outs=outs)
+
+
 def readout_fields(fields, pos, resampler=None, transform=None, layout=None, gather=None, remote=None):
     """
     Read several RealFields of one ParticleMesh at the same positions in ONE sweep over the particles

@@ -297,6 +297,17 @@ def test_gradient_fields_fused_transfer_and_first_pass(P, oracle, dtype, n0):
     P.gradient_fields(cx, [T.GravityFD4(d) for d in range(3)], outs=outs)
     for d in range(3):
         assert numpy.array_equal(outs[d].value, first[d])
+    # the last pass of r2c joins the kernel (pm.force_fields, pmb_fft_force3): same fields from the REAL input
+    rx2 = pm.create(type="real", value=x)
+    rx2.scale(1.75)
+    keep_real = rx2.value.copy()
+    for make in (T.GravityFD4, T.GradientK):
+        tfs = [make(d) for d in range(3)]
+        whole = P.force_fields(rx2, tfs)
+        ref = P.gradient_fields(cx, tfs)
+        for d in range(3):
+            assert abs(whole[d].value - ref[d].value).max() <= tol * abs(ref[d].value).max(), (make.__name__, d)
+    assert numpy.array_equal(rx2.value, keep_real), "the input field is preserved"
     # any other combination of transfers goes through apply + c2r
     mixed = P.gradient_fields(cx, [T.GravityFD4(0), T.GradientK(1)])
     assert abs(mixed[1].value - cx.apply(T.GradientK(1)).c2r().value).max() <= tol * abs(mixed[1].value).max()

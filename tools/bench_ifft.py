@@ -60,6 +60,20 @@ def main():
                          "algorithmic_gb_per_launch": round(nbytes / 1e9, 3),
                          "achieved_gbs": round(nbytes / (ms / n * 1e-3) / 1e9, 1),
                          "frac_of_hbm_peak": round(nbytes / (ms / n * 1e-3) / 1e9 / peak, 4)}
+    if comm.size == 1:
+        from pmesh_b200.pm import force_fields
+        rho = pm.generate_whitenoise(2, type="real")
+        rk = pm.create("complex")
+        pm.fft_fused_stats(reset=True)
+        pm.fft_library_ms(reset=True)
+        out["r2c_then_fused_ms"] = round(timeit(lambda: gradient_fields(rho.r2c(out=rk), tf, outs=treal)), 3)
+        pm.fft_fused_stats(reset=True)
+        pm.fft_library_ms(reset=True)
+        out["whole_ms"] = round(timeit(lambda: force_fields(rho, tf, outs=treal)), 3)
+        ms, n = pm.fft_fused_stats(reset=True)
+        out["whole_cufft_ms"] = round(pm.fft_library_ms(reset=True) / (a.reps + 2), 3)
+        out["whole_kernel_ms_per_launch"] = round(ms / max(n, 1), 3)
+        del rho, rk
     if not a.no_unfused:
         out["unfused_ms"] = round(timeit(lambda: c2r_fields(apply_gradients(rhok, tf, outs=tmp), outs=[Ellipsis] * 3)), 3)
         out["unfused_cufft_ms"] = round(pm.fft_library_ms(reset=True) / (a.reps + 2), 3)
