@@ -188,12 +188,18 @@ class ForceStep(object):
         from pmesh_b200 import transfer as T
         self.pm, self.args = pm, args
         self.rho = pm.create("real")
-        self.rhok = pm.create("complex")
+        self._rhok = None         # density modes: only the paths that store them allocate the field
         self.tmp = [pm.create("complex") for d in range(3)]
         from pmesh_b200.pm import RealField
         self.treal = [RealField(pm, t._base) for t in self.tmp]
         self.tf = [T.GravityFD4(d) for d in range(3)]
         self.stage = {}
+
+    @property
+    def rhok(self):
+        if self._rhok is None:
+            self._rhok = self.pm.create("complex")
+        return self._rhok
 
     def _t(self, name, fn):
         if not self.args.breakdown:
@@ -286,7 +292,9 @@ def fused_block(pm, ms, launches, args, peak):
     return {"kernel": "pmb_k_ifft_grad", "launches_per_step": per_step, "ms_per_launch": round(ms_launch, 3),
             "algorithmic_gb_per_launch": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
             "frac_of_hbm_peak": round(gbs / peak, 4),
-            "replaces": "pmb_k_transfer_grad3 (64 B per complex cell) + the axis-0 pass of cuFFT in each of the three c2r (96 B)"}
+            "replaces": ("the axis-0 pass of cuFFT's r2c (32 B per complex cell: the kernel takes every line forward first, "
+                         "pm.force_fields) + " if pm.comm.size == 1 and not args.no_forward_fusion else "") +
+                        "pmb_k_transfer_grad3 (64 B per complex cell) + the axis-0 pass of cuFFT in each of the three c2r (96 B)"}
 
 
 def kernel_names(args, nl):

@@ -132,6 +132,32 @@ static void block_partition(int64_t n, int P, int rank, int64_t *blk, int64_t *s
 }
 
 static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long long *inembed, long long idist,
+                     long long *onembed, long long odist, cufftType type, long long batch);
+
+// whole-mesh r2c / c2r plans of one rank, made on first use
+static int ensure_full(pmb_fft *f)
+{
+    if (f->have_full) return PMB_OK;
+    const int ndim = f->ndim;
+    long long n[3], inr[3], inc[3];
+    for (int d = 0; d < ndim; d++) {
+        n[d] = f->n[3 - ndim + d];
+        inr[d] = n[d];
+        inc[d] = n[d];
+    }
+    inr[ndim - 1] = 2 * f->nc;
+    inc[ndim - 1] = f->nc;
+    long long rdist = 1, cdist = 1;
+    for (int d = 0; d < ndim; d++) { rdist *= inr[d]; cdist *= inc[d]; }
+    const bool dbl = f->elsize == 8;
+    PMB_CHECK(make_plan(f, &f->full_r2c, ndim, n, inr, rdist, inc, cdist, dbl ? CUFFT_D2Z : CUFFT_R2C, 1));
+    int rc = make_plan(f, &f->full_c2r, ndim, n, inc, cdist, inr, rdist, dbl ? CUFFT_Z2D : CUFFT_C2R, 1);
+    if (rc != PMB_OK) { cufftDestroy(f->full_r2c); return rc; }
+    f->have_full = true;
+    return PMB_OK;
+}
+
+static int make_plan(pmb_fft *f, cufftHandle *h, int rank, long long *n, long long *inembed, long long idist,
                      long long *onembed, long long odist, cufftType type, long long batch)
 {
     PMB_CUFFT(cufftCreate(h));
@@ -313,20 +339,8 @@ extern "C" int pmb_fft_create_np(pmb_ctx *ctx, int ndim, const int64_t *nmesh, i
     const bool dbl = dtype_elsize == 8;
     if (f->P == 1) {
         f->s0 = 0; f->m0 = f->n[0]; f->s1 = 0; f->m1 = f->n[1];
-        long long n[3], inr[3], inc[3];
-        int r = ndim;
-        for (int d = 0; d < ndim; d++) {
-            n[d] = f->n[3 - ndim + d];
-            inr[d] = n[d];
-            inc[d] = n[d];
-        }
-        inr[r - 1] = 2 * f->nc;
-        inc[r - 1] = f->nc;
-        long long rdist = 1, cdist = 1;
-        for (int d = 0; d < r; d++) { rdist *= inr[d]; cdist *= inc[d]; }
-        PMB_CHECK(make_plan(f, &f->full_r2c, r, n, inr, rdist, inc, cdist, dbl ? CUFFT_D2Z : CUFFT_R2C, 1));
-        PMB_CHECK(make_plan(f, &f->full_c2r, r, n, inc, cdist, inr, rdist, dbl ? CUFFT_Z2D : CUFFT_C2R, 1));
-        f->have_full = true;
+        // the two whole-mesh plans (and their cuFFT work areas) are made when first used (ensure_full): a force step that
+        // goes through pmb_fft_force3 never needs them
     } else if (f->P1 > 1) {
         // ---- pencils ----
         int64_t blk;
@@ -897,6 +911,7 @@ extern "C" int pmb_fft_r2c(pmb_fft *f, const void *real, void *cplx, double scal
     pmb_ctx *ctx = f->ctx;
     const size_t csz = 2 * (size_t) f->elsize;
     if (f->P == 1) {
+        PMB_CHECK(ensure_full(f));
         PMB_CHECK(exec_r2c(f, f->full_r2c, real, cplx));
         if (scale != 1.0) {
             const int64_t n = f->n[0] * f->n[1] * f->nc;
@@ -989,6 +1004,7 @@ extern "C" int pmb_fft_c2r(pmb_fft *f, const void *cplx, void *real)
         // cuFFT's multi-dimensional C2R may overwrite its input: go through the output buffer
         if (cplx != real)
             PMB_CUDA(cudaMemcpyAsync(real, cplx, (size_t) (f->n[0] * f->n[1] * f->nc) * csz, cudaMemcpyDeviceToDevice, ctx->stream));
+        PMB_CHECK(ensure_full(f));
         PMB_CHECK(exec_c2r(f, f->full_c2r, real, real));
         return PMB_OK;
     }

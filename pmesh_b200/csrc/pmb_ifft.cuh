@@ -1,13 +1,19 @@
-// pmb_ifft.cuh -- the first pass of the three backward transforms of a force evaluation, FUSED with the
-// gradient transfers:   out_d = IDFT_axis0( i m_d(k_d) / k^2 * rho_k ),  d = 0, 1, 2
+// pmb_ifft.cuh -- the axis-0 pass of the three backward transforms of a force evaluation, FUSED with the gradient
+// transfers (and, on one rank, with the last pass of r2c):   out_d = IDFT_axis0( i m_d(k_d) / k^2 * rho_k ),  d = 0, 1, 2
 //
 // Replaces, for `[rhok.apply(T_d).c2r() for d in 0..2]` (pmesh/pm.py:617-648 Field.apply, 987-1019 c2r;
 // examples/nbody.py:162-170, 211-216), the transfer pass over the modes (pmb_k_transfer_grad3: 16 B read +
 // 48 B written per complex cell) AND the axis-0 pass of cuFFT in each of the three transforms (3 x 32 B per
-// cell): the density modes are read once from HBM (the re-reads of directions 1 and 2 hit L2), multiplied on
-// load, transformed along axis 0 in registers + shared memory and written once per direction:
-// 16 + 48 bytes per complex cell instead of 64 + 96.  The remaining two axes of every transform stay with
-// cuFFT (batched 2-D c2r over the planes, library time).
+// cell): the modes are read once, multiplied on load, transformed along axis 0 in registers + shared memory and
+// written once per direction: 16 + 48 bytes per complex cell instead of 64 + 96.  The remaining two axes of every
+// transform stay with cuFFT (batched 2-D c2r over the planes, library time).
+//
+// Fewer transforms than directions.  The multipliers of directions 1 and 2 are constants of an axis-0 line, so both are
+// ONE transform phi = IDFT(pre / k^2 * rho_k) scaled at the store (i m_1 phi, i m_2 phi).  Direction 0 needs m_0(k_0)
+// inside the transform -- a second transform -- unless the gradient is the finite-difference one (PMB_TF_GRAVITY_FD4):
+// i kfinite(k_0) is the symbol of the 4th-order central difference, i.e. a 5-point stencil along the line of the same
+// phi, applied out of the exchange buffer.  With `forward` the line is first transformed forward (conj . IDFT . conj):
+// the kernel then starts from the planes' 2-D r2c and the density modes are never stored.
 //
 // One line of N = 16 * R2 * R3 points (R3 = 1: two passes) is transformed by N / 16 threads, each holding 16
 // points in registers: a Stockham autosort transform with radices (16, R2, R3) -- pass 1 reads global memory
@@ -15,7 +21,8 @@
 // element per 16: conflict-free for the stride-16 stores of pass 1), the last pass stores to global memory in
 // natural order.  A CTA owns a bundle of B lines:
 //   STRIDED (one rank, complex layout (n0, n1, nc): the elements of a line are n1*nc apart): B ADJACENT lines,
-//           thread = (point, line) with the line fastest, so every access of a row is B * 16 contiguous bytes;
+//           thread = (point, line) with the line fastest, so every access of a row is B * 16 contiguous bytes
+//           (B = 8 for 1024 double-precision points: whole 128-byte lines; 64-byte rows measured 2 x slower);
 //   CONTIG  (P ranks, "transposed" layout (m1, mc, n0): lines contiguous): B consecutive lines.
 // Twiddles W_N^k = exp(+2 pi i k / N) come from a table built on the host in double precision.
 //

@@ -216,8 +216,10 @@ def main():
     # 6d. transfers folded into the axis-0 pass of the backward transforms (pm.gradient_fields, pmb_ifft.cuh) on slabs:
     #     == transfer pass + cuFFT lines, for a fused length (64) and an unfused one (48, above), twice in a row
     from pmesh_b200.pm import gradient_fields
-    for dt, tol in (("f8", 1e-12), ("f4", 2e-5)):
-        pm64 = ParticleMesh(BoxSize=[L, 0.9 * L, 1.1 * L], Nmesh=[64, 40, 24], dtype=dt, comm=comm)
+    for dt, tol, shape in (("f8", 1e-12, [64, 40, 24]), ("f4", 2e-5, [64, 40, 24]), ("f8", 1e-12, [128, 16, 12]),
+                           ("f8", 1e-12, [256, 16, 12]), ("f8", 1e-12, [512, 16, 12]), ("f8", 1e-12, [1024, 16, 12]),
+                           ("f8", 1e-12, [2048, 16, 12]), ("f8", 1e-12, [4096, 16, 12]), ("f4", 2e-5, [1024, 16, 12])):
+        pm64 = ParticleMesh(BoxSize=[L, 0.9 * L, 1.1 * L], Nmesh=shape, dtype=dt, comm=comm)
         rk = pm64.generate_whitenoise(seed=77, type="complex")
         rk.scale(0.5)
         for make in (T.GravityFD4, T.GradientK):
