@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--paint-mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--breakdown", action="store_true", help="also time every stage separately (stderr)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--split", action="store_true", help="P > 1: always the split exchange (default: measured choice)")
     ap.add_argument("--no-split", action="store_true",
                     help="P > 1: move every particle through take + alltoallv (Layout.exchange) instead of painting / reading the "
                          "rank's own particles where they lie (Layout.exchange_remote)")
@@ -219,7 +220,13 @@ class ForceStep(object):
         for d in range(3):
             F[d] = None           # the previous evaluation's columns go back to the allocator before new ones are made
         layout = self._t("decompose", lambda: pm.decompose(X, smoothing=1.0 * pm.resampler.support))
-        split = pm.comm.size > 1 and not self.args.no_split and self.args.paint_mode == "atomic"
+        # P > 1: split or full exchange, whichever the first (warm-up) evaluations measured faster (domain.ExchangeTuner)
+        tuner = pm.exchange_tuner
+        if self.args.no_split or self.args.paint_mode != "atomic":
+            tuner.choice = 'full'
+        elif self.args.split:
+            tuner.choice = 'split' if pm.comm.size > 1 else 'full'
+        split = tuner.begin() == 'split'
         if split:
             # the particles a rank keeps are painted and read WHERE THEY LIE (the kernels clip to the local slab):
             # only the records that change rank are packed and travel (Layout.exchange_remote)
@@ -260,6 +267,7 @@ class ForceStep(object):
             Fn = self._t("readout+gather", lambda: readout_fields(real, X, remote=(layout, lrem)))
         else:
             Fn = self._t("readout+gather", lambda: readout_fields(real, lpos, gather=layout))
+        tuner.end()
         for d in range(3):
             F[d] = Fn[d]
         return F
@@ -702,6 +710,11 @@ def run_ours(args):
                 "nvlink_gbs_achieved": round(xp_bytes / max(xp_ms, 1e-9) / 1e6, 1), "nvlink_gbs_peak_measured": 770.0,
                 "note": "rank 0: bytes the fused transpose kernels stored into peer memory / their CUDA-event time"},
             "fused_transfer_ifft": fused_block(pm, fu_ms, fu_n, args, peak),
+            "exchange": None if comm.size == 1 else {
+                "mode": pm.exchange_tuner.choice, "measured_ms": getattr(pm.exchange_tuner, "measured", None),
+                "note": "split: the particles a rank keeps are painted / read where they lie, only records that change rank "
+                        "travel (Layout.exchange_remote); full: every record through take + alltoallv (Layout.exchange); "
+                        "chosen from one timed warm-up evaluation of each, slowest rank decides (domain.ExchangeTuner)"},
             "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "inputs": inputs, "e2e": e2e, "cpu_baseline": cpu,
             "verify": verify,

@@ -41,6 +41,38 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
     const int64_t begin = unit * per_unit;
     const int64_t end = min(begin + per_unit, npart);
     int c0 = 0, c1 = 0;
+    // HOME CELL of the warp: the domain cell of its first particle.  A particle whose smoothing interval lies inside that
+    // cell on every routed axis takes pmb_route_mask_x's interior path (l = r = p, one patch cell) with exactly this
+    // cell, so its mask is the cell's -- known without a search, a table lookup or a divergent branch.  When ALL 32
+    // particles of a step pass the test (nearly every step of a particle array that follows the decomposition) the
+    // general arithmetic is skipped; otherwise the whole warp takes it as before.  Same predicates, same results.
+    bool home_ok = false;
+    __shared__ double s_home[ROUTE_BLOCK / 32][3 * NDIM];       // per warp: the cell's edges and the box, per axis
+    double *hlo = s_home[threadIdx.x >> 5], *hhi = hlo + NDIM, *hbox = hlo + 2 * NDIM;
+    uint64_t home_mask = 0;
+    int home_rank = -1;
+    if (g.home && g.periodic && begin < end) {
+        home_ok = true;
+        int target = 0;
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) {
+            if (!pmb_route_axis_used(g, d)) continue;
+            const double x = g.scale[d] * pmb_ld_real_stream(pos, begin * ps0 + d * ps1, elsize);
+            const double *e = edges[d];
+            const int ne = g.nedges[d];
+            const double box = e[ne - 1];
+            const int p = pmb_digitize_near(pmb_pymod_fast(x, box), e, ne, g.inv_width[d]);
+            if (!(g.smoothing[d] >= 0.0) || p < 1 || p >= ne) { home_ok = false; continue; }
+            if (lane == 0) { hlo[d] = e[p - 1]; hhi[d] = e[p]; hbox[d] = box; }
+            target += (p - 1) * g.dstride[d];
+        }
+        __syncwarp();
+        if (home_ok) {
+            const int rank = g.assign[target];
+            const int deg = (rank >= 0 && rank < g.ndomains) ? g.degenerate[rank] : 0;
+            if (!deg && rank >= 0 && rank < ROUTE_MAXRANKS) { home_mask = (uint64_t) 1 << rank; home_rank = rank; }
+        }
+    }
     for (int64_t base = begin; base < end; base += 32 * UNROLL) {
         // all coordinates of the UNROLL particles of this lane are requested before the first one is used:
         // the routing arithmetic is branchy (fmod fall-backs, edge searches) and the compiler does not hoist
@@ -54,15 +86,36 @@ pmb_k_route_count(RouteGeom g, const void *pos, int elsize, int64_t ps0, int64_t
                 xs[u][d] = (i < end && pmb_route_axis_used(g, d)) ? pmb_ld_real_stream(pos, i * ps0 + d * ps1, elsize) : 0.0;
         }
         uint64_t mask[UNROLL];
+        bool fast[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
-            mask[u] = i < end ? pmb_route_mask_x<NDIM>(g, edges, xs[u]) : 0;
+            bool in = home_ok;
+#pragma unroll
+            for (int d = 0; d < NDIM; d++) {
+                if (!pmb_route_axis_used(g, d)) continue;
+                // the conditions of the interior path of pmb_route_mask_x, with the home cell's edges for e[p - 1], e[p]
+                const double x = g.scale[d] * xs[u][d];
+                const double c = x + 0.0, cl = c - g.smoothing[d], cr = c + g.smoothing[d];
+                in = in && x >= 0.0 && x < hbox[d] && cl >= 0.0 && cr < hbox[d] && hlo[d] <= cl && cr < hhi[d];
+            }
+            fast[u] = __all_sync(0xffffffffu, in || i >= end);
+            if (fast[u]) mask[u] = i < end ? home_mask : 0;
+            else mask[u] = i < end ? pmb_route_mask_x<NDIM>(g, edges, xs[u]) : 0;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * 32 + lane;
             if (i < end) __stcs(masks + i, (MaskT) mask[u]);
+            if (fast[u]) {
+                // one rank (or none) for the whole step
+                const int cnt = __popc(__ballot_sync(0xffffffffu, i < end));
+                if (home_rank >= 0) {
+                    if (lane == home_rank) c0 += cnt;
+                    if (lane + 32 == home_rank) c1 += cnt;
+                }
+                continue;
+            }
             // ranks that any lane of the warp targets (usually one or two)
             unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned) mask[u]);
             unsigned hi = g.nranks > 32 ? __reduce_or_sync(0xffffffffu, (unsigned) (mask[u] >> 32)) : 0u;
@@ -199,6 +252,11 @@ static int route_setup(pmb_ctx *ctx, const pmb_decompose_args *a, RouteGeom *g, 
         tot_edges += a->nedges[d];
     }
     g->ndomains = ndomains;
+    {
+        static int home = -1;
+        if (home < 0) { const char *e = getenv("PMB_ROUTE_HOME"); home = e ? atoi(e) : 1; }
+        g->home = home;
+    }
     int st = 1;
     for (int d = a->ndim - 1; d >= 0; d--) { g->dstride[d] = st; st *= g->shape[d]; }
     // one small device allocation holds edges | assign | degenerate

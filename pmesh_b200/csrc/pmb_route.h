@@ -30,6 +30,7 @@ struct RouteGeom {
     int nedges[3];
     const int32_t *assign;       // device [ndomains]
     const int16_t *degenerate;   // device [ndomains]
+    int home;                    // 1: the count kernel may take its home-cell shortcut (PMB_ROUTE_HOME=0 switches it off)
     int all_trivial;             // every axis is a single periodic domain: the mask is a constant
     uint64_t const_mask;
 };

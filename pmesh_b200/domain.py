@@ -56,6 +56,49 @@ def promote(data, comm):
     return data
 
 
+class ExchangeTuner(object):
+    """
+    Chooses, by measurement, between the two ways a force evaluation can serve the particles a rank keeps:
+    ``'split'`` (paint / read them where they lie, only the records that change rank travel: Layout.exchange_remote)
+    and ``'full'`` (every record through take + alltoallv: Layout.exchange, the reference's path).  Which one is faster
+    depends on the machine-wide picture (2 / 4 GPUs, 1024^3: split by 12 - 15 %; 8 GPUs: full), so the first
+    evaluations are timed with CUDA events -- one cold, then one of each -- the slowest rank decides for everybody
+    and every later evaluation takes the winner.  ``PMB_EXCHANGE=split|full`` fixes the choice.
+    """
+    ORDER = ('full', 'split', 'full')      # call 0 pays the one-time costs and is not compared
+
+    def __init__(self, comm, ctx, slot=7):
+        import os
+        self.comm, self.ctx, self.slot = comm, ctx, slot
+        self.calls = 0
+        self.ms = {}
+        env = os.environ.get("PMB_EXCHANGE", "")
+        self.choice = env if env in ('split', 'full') else None
+        if comm.size == 1:
+            self.choice = 'full'
+        self._timing = False
+
+    def begin(self):
+        """-> the mode of this evaluation"""
+        if self.choice is not None:
+            return self.choice
+        self.ctx.timer_start(self.slot)
+        self._timing = True
+        return self.ORDER[self.calls]
+
+    def end(self):
+        if not self._timing:
+            return
+        self._timing = False
+        ms = self.ctx.timer_stop(self.slot)
+        self.ms[self.ORDER[self.calls]] = ms          # the second 'full' overwrites the cold one
+        self.calls += 1
+        if self.calls == len(self.ORDER):
+            worst = dict((k, max(self.comm.allgather(float(v)))) for k, v in sorted(self.ms.items()))
+            self.choice = 'split' if worst['split'] < worst['full'] else 'full'
+            self.measured = worst
+
+
 class Layout(object):
     """
     The communication layout of a domain decomposition (reference domain.py:82-318).

@@ -72,7 +72,8 @@ def force(pm, Q, S=None, factor=1.0):
     layout = pm.decompose(X, smoothing=1.0 * pm.resampler.support)
     # P > 1: the particles a rank keeps are painted and read where they lie (every kernel clips to the local canvas);
     # only the records that change rank travel (Layout.exchange_remote)
-    split = pm.comm.size > 1
+    tuner = pm.exchange_tuner          # which of the two is faster is measured on the first evaluations
+    split = tuner.begin() == 'split'
     if split:
         lrem = layout.exchange_remote(X)
         rho = pm.paint(X)
@@ -94,8 +95,11 @@ def force(pm, Q, S=None, factor=1.0):
     else:
         f = gradient_fields(rho.r2c(out=Ellipsis), tfs)
     if split:
-        return readout_fields(f, X, remote=(layout, lrem))
-    return readout_fields(f, lpos, gather=layout)
+        F = readout_fields(f, X, remote=(layout, lrem))
+    else:
+        F = readout_fields(f, lpos, gather=layout)
+    tuner.end()
+    return F
 
 
 def lpt1(pm, dlinear, Q):

@@ -1186,6 +1186,14 @@ class ParticleMesh(object):
         _lib.check(self.ctx.lib.pmb_fft_library_ms(self._plan, ctypes.byref(ms), int(reset)))
         return ms.value
 
+    @property
+    def exchange_tuner(self):
+        """ measured choice between the split and the full particle exchange of a force evaluation (domain.ExchangeTuner) """
+        if getattr(self, "_exchange_tuner", None) is None:
+            from .domain import ExchangeTuner
+            self._exchange_tuner = ExchangeTuner(self.comm, self.ctx)
+        return self._exchange_tuner
+
     def fft_fused_stats(self, reset=False):
         """ (ms, launches): time inside the fused transfer + axis-0 transform kernels (pmb_ifft.cuh) since the last reset """
         ms = ctypes.c_float()

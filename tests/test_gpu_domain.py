@@ -84,6 +84,43 @@ def test_decompose_matches_oracle(D, oracle, case, posdtype):
         assert_array_equal(layout.indices, indices)
 
 
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_decompose_ordered_particles_home_cell_path(D, oracle, case):
+    """particle arrays that FOLLOW the decomposition (sorted along the axes: whole warps inside one domain cell) take
+    the routing kernel's home-cell shortcut; boundary layers, edge values, -0.0, out-of-box values and NaNs in between
+    send single warp steps down the general path.  Counts and indices bit-exact against the oracle."""
+    edges, P, smoothing, periodic = CASES[case]
+    nd = len(edges)
+    rng = numpy.random.default_rng(100 + case)
+    box = numpy.array([e[-1] for e in edges])
+    n = 60000
+    pos = rng.uniform(0.0, 1.0, (n, nd)) * box
+    # lexicographic order by domain cell: long runs of particles in one cell
+    cell = [numpy.digitize(pos[:, d], edges[d]) for d in range(nd)]
+    order = numpy.lexsort(tuple(cell[d] for d in reversed(range(nd))))
+    pos = pos[order]
+    # adversaries inside the runs
+    k = rng.choice(n, 400, replace=False)
+    pos[k[:50]] = 0.0
+    pos[k[50:100]] = -0.0
+    pos[k[100:150]] = box
+    pos[k[150:200]] = -1e-17
+    pos[k[200:260]] = rng.uniform(-0.5, 1.5, (60, nd)) * box
+    for d in range(nd):
+        e = numpy.asarray(edges[d], dtype="f8")
+        pos[k[260 + 40 * d:300 + 40 * d], d] = rng.choice(e, 40) + rng.choice([0.0, 1e-12, -1e-12], 40)
+    pos[k[380:390]] = numpy.nan
+    scale = numpy.array([1.0, 0.5, 2.0])[:nd] if case % 2 else None
+    for rank in (0, P - 1):
+        g = D.GridND(edges, comm=FakeComm(rank, P), periodic=periodic)
+        tr = None if scale is None else D.ScaleTransform(scale)
+        layout = g.decompose(pos, smoothing=smoothing, transform=tr)
+        counts, indices = oracle.decompose(pos, edges, P, smoothing=smoothing, periodic=periodic,
+                                           assign=g.DomainAssign, scale=scale)
+        assert_array_equal(layout.sendcounts, counts)
+        assert_array_equal(layout.indices, indices)
+
+
 def test_decompose_empty_and_device_positions(D, oracle):
     from pmesh_b200.device import DeviceArray
     g = D.GridND([numpy.linspace(0, 4, 3)] * 2, comm=FakeComm(0, 4))
