@@ -73,6 +73,9 @@ def force(pm, Q, S=None, factor=1.0):
     # P > 1: the particles a rank keeps are painted and read where they lie (every kernel clips to the local canvas);
     # only the records that change rank travel (Layout.exchange_remote)
     tuner = pm.exchange_tuner          # which of the two is faster is measured on the first evaluations
+    from .window import default_paint_mode
+    if default_paint_mode() != 'atomic':
+        tuner.choice = 'full'          # the deterministic paint sums in the particle order of the full exchange
     split = tuner.begin() == 'split'
     if split:
         lrem = layout.exchange_remote(X)
