@@ -54,3 +54,51 @@ def test_layout_offsets():
     assert_array_equal(lay.recvoffsets, [0, 5, 12])
     assert lay.recvlength == 23 and not lay.identity
     assert_array_equal(lay.get_exchange_cost(), [6, 6, 6])
+
+
+def test_exchange_tuner_measures_then_sticks():
+    """domain.ExchangeTuner: evaluations run full (cold), split, full under the timer; the slowest rank's times decide
+    for every rank; a single rank, or PMB_EXCHANGE, needs no measurement"""
+    import os
+    from pmesh_b200.domain import ExchangeTuner
+
+    class Ctx(object):
+        def __init__(self, times):
+            self.times = list(times)
+            self.started = 0
+
+        def timer_start(self, slot):
+            self.started += 1
+
+        def timer_stop(self, slot):
+            return self.times.pop(0)
+
+    class Comm(object):
+        def __init__(self, size, others):
+            self.size, self.others = size, others
+
+        def allgather(self, x):
+            return [x] + [o for o in self.others]
+
+    os.environ.pop("PMB_EXCHANGE", None)
+    # split faster on this rank and everywhere
+    t = ExchangeTuner(Comm(2, [1.0]), Ctx([90.0, 50.0, 60.0]))
+    modes = []
+    for _ in range(5):
+        modes.append(t.begin())
+        t.end()
+    assert modes == ['full', 'split', 'full', 'split', 'split'] and t.choice == 'split'
+    assert t.measured == {'full': 60.0, 'split': 50.0} and t.ctx.started == 3
+    # another rank is slow in the split path: it decides
+    t = ExchangeTuner(Comm(2, [70.0]), Ctx([90.0, 50.0, 60.0]))
+    for _ in range(3):
+        t.begin()
+        t.end()
+    assert t.choice == 'full' and t.begin() == 'full'
+    # one rank: nothing to exchange; the environment fixes the choice
+    assert ExchangeTuner(Comm(1, []), Ctx([])).begin() == 'full'
+    os.environ["PMB_EXCHANGE"] = "split"
+    try:
+        assert ExchangeTuner(Comm(4, [0.0] * 3), Ctx([])).begin() == 'split'
+    finally:
+        del os.environ["PMB_EXCHANGE"]
