@@ -102,3 +102,23 @@ def test_exchange_tuner_measures_then_sticks():
         assert ExchangeTuner(Comm(4, [0.0] * 3), Ctx([])).begin() == 'split'
     finally:
         del os.environ["PMB_EXCHANGE"]
+
+
+def test_fd4_gradient_is_a_stencil_along_the_line():
+    """the identity pmb_ifft.cuh uses for direction 0 of the finite-difference gradient (examples/nbody.py:162-170):
+    multiplying the modes by i * kfinite(k) = i (8 sin w - sin 2w) / (6 C), w = k C, equals the periodic 5-point stencil
+    (8 (phi[x+1] - phi[x-1]) - (phi[x+2] - phi[x-2])) / (12 C) on the inverse transform -- also with the wavenumber
+    convention of pm.py:1213-1219 (negative frequencies from N/2 on, Nyquist included)"""
+    import numpy
+    rng = numpy.random.default_rng(5)
+    for n, L in ((64, 100.0), (128, 7.0)):
+        C = L / n
+        i0 = numpy.arange(n)
+        k = numpy.where(i0 >= n // 2, i0 - n, i0) * (2 * numpy.pi / L)
+        w = k * C
+        kfinite = 1.0 / C * 1 / 6.0 * (8 * numpy.sin(w) - numpy.sin(2 * w))
+        modes = rng.normal(size=n) + 1j * rng.normal(size=n)
+        direct = numpy.fft.ifft(1j * kfinite * modes) * n
+        phi = numpy.fft.ifft(modes) * n
+        sten = (8 * (numpy.roll(phi, -1) - numpy.roll(phi, 1)) - (numpy.roll(phi, -2) - numpy.roll(phi, 2))) / (12 * C)
+        assert abs(sten - direct).max() <= 1e-12 * abs(direct).max()
